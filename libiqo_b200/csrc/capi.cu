@@ -1,0 +1,611 @@
+// C ABI of the CUDA backend (include/iqo_cuda.h).  Host logic only; kernels live in kernels.cu.
+#include "../../include/iqo_cuda.h"
+
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "kernels.cuh"
+#include "plan.hpp"
+
+using namespace iqo_b200;
+
+namespace {
+
+thread_local std::string t_lastError;
+
+int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    t_lastError = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (expr);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(IQO_CUDA_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev;
+    bool ok;
+    explicit DeviceGuard(int dev) : prev(-1), ok(false)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) return;
+        ok = (prev == dev) || (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+struct AxisTables {
+    int32_t *first, *row, *coef, *deno;
+    AxisTables() : first(0), row(0), coef(0), deno(0) {}
+};
+
+size_t alignUp(size_t v, size_t a)
+{
+    return (v + a - 1) / a * a;
+}
+
+}  // namespace
+
+struct iqo_cuda_resizer {
+    Plan plan;
+    int device;
+    AxisTables tx, ty;
+    GenericGeom geom;
+    int path;
+    const char *lastKernel;
+    cudaStream_t stream[2];
+    cudaEvent_t evUp[2], evDone[2];
+    // staging for host-pointer calls: two slots of `slotFrames` frames each
+    uint8_t *dSrc[2], *dDst[2];
+    size_t srcPitch, dstPitch;  // device pitches of the staging frames
+    size_t slotFrames;
+
+    iqo_cuda_resizer() : device(0), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
+    {
+        for (int i = 0; i < 2; ++i) {
+            stream[i] = 0;
+            evUp[i] = evDone[i] = 0;
+            dSrc[i] = dDst[i] = 0;
+        }
+    }
+};
+
+namespace {
+
+int uploadAxis(const AxisPlan &a, AxisTables &t)
+{
+    CUDA_TRY(cudaMalloc(&t.first, a.first.size() * 4));
+    CUDA_TRY(cudaMalloc(&t.row, a.row.size() * 4));
+    CUDA_TRY(cudaMalloc(&t.coef, a.coef.size() * 4));
+    CUDA_TRY(cudaMalloc(&t.deno, a.deno.size() * 4));
+    CUDA_TRY(cudaMemcpy(t.first, a.first.data(), a.first.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.row, a.row.data(), a.row.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.coef, a.coef.data(), a.coef.size() * 4, cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(t.deno, a.deno.data(), a.deno.size() * 4, cudaMemcpyHostToDevice));
+    return IQO_CUDA_OK;
+}
+
+void freeAxis(AxisTables &t)
+{
+    cudaFree(t.first);
+    cudaFree(t.row);
+    cudaFree(t.coef);
+    cudaFree(t.deno);
+}
+
+AxisDev axisDev(const AxisPlan &a, const AxisTables &t)
+{
+    AxisDev d;
+    d.first = t.first;
+    d.row = t.row;
+    d.coef = t.coef;
+    d.deno = t.deno;
+    d.N = a.N;
+    d.S = int(a.S);
+    d.D = int(a.D);
+    return d;
+}
+
+// true when p is device memory (or managed); host / unregistered otherwise
+bool isDevicePointer(const void *p)
+{
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+}
+
+int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, size_t srcRow0, size_t srcRows,
+           size_t srcSt, size_t srcFrameStride, const uint8_t *src,
+           size_t dstSt, size_t dstFrameStride, uint8_t *dst, cudaStream_t stream)
+{
+    ResizeArgs a;
+    a.x = axisDev(r->plan.x, r->tx);
+    a.y = axisDev(r->plan.y, r->ty);
+    a.src = src;
+    a.dst = dst;
+    a.srcPitch = (long long)srcSt;
+    a.dstPitch = (long long)dstSt;
+    a.srcFrameStride = (long long)srcFrameStride;
+    a.dstFrameStride = (long long)dstFrameStride;
+    a.nFrames = int(nFrames);
+    a.srcRow0 = int(srcRow0);
+    a.srcRows = int(srcRows);
+    a.dstRow0 = int(dstRow0);
+    a.dstRows = int(dstRows);
+    a.shift = r->plan.shift;
+    a.lanczos = r->plan.kind == kLanczos;
+    a.workSigned = r->plan.workSigned;
+    r->lastKernel = "generic";
+    CUDA_TRY(launchGeneric(a, r->geom, stream));
+    return IQO_CUDA_OK;
+}
+
+int checkStrides(const iqo_cuda_resizer *r, size_t srcSt, const void *src, size_t dstSt, const void *dst)
+{
+    if (!r) return fail(IQO_CUDA_E_ARG, "NULL resizer");
+    if (!src || !dst) return fail(IQO_CUDA_E_ARG, "NULL image pointer");
+    if (srcSt < size_t(r->plan.x.S)) return fail(IQO_CUDA_E_ARG, "srcSt (%zu) < srcW (%lld)", srcSt, (long long)r->plan.x.S);
+    if (dstSt < size_t(r->plan.x.D)) return fail(IQO_CUDA_E_ARG, "dstSt (%zu) < dstW (%lld)", dstSt, (long long)r->plan.x.D);
+    return IQO_CUDA_OK;
+}
+
+// (re)allocate the two staging slots so that each holds `frames` frames
+int ensureStaging(iqo_cuda_resizer *r, size_t frames)
+{
+    if (r->slotFrames >= frames) return IQO_CUDA_OK;
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(r->dSrc[i]);
+        cudaFree(r->dDst[i]);
+        r->dSrc[i] = r->dDst[i] = 0;
+    }
+    r->slotFrames = 0;
+    r->srcPitch = alignUp(size_t(r->plan.x.S), 16);
+    r->dstPitch = alignUp(size_t(r->plan.x.D), 16);
+    const size_t sBytes = r->srcPitch * size_t(r->plan.y.S) * frames;
+    const size_t dBytes = r->dstPitch * size_t(r->plan.y.D) * frames;
+    for (int i = 0; i < 2; ++i) {
+        if (cudaMalloc(&r->dSrc[i], sBytes) != cudaSuccess || cudaMalloc(&r->dDst[i], dBytes) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(IQO_CUDA_E_NOMEM, "cannot allocate %zu bytes of device staging", sBytes + dBytes);
+        }
+    }
+    r->slotFrames = frames;
+    return IQO_CUDA_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int iqo_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+const char *iqo_cuda_version(void)
+{
+    return "libiqo_b200 0.1 (sm_100a)";
+}
+
+const char *iqo_cuda_last_error(void)
+{
+    return t_lastError.c_str();
+}
+
+unsigned long long iqo_cuda_launch_count(void)
+{
+    return launchCount();
+}
+
+void *iqo_cuda_host_alloc(size_t bytes)
+{
+    void *p = 0;
+    if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        fail(IQO_CUDA_E_NOMEM, "cudaHostAlloc(%zu) failed", bytes);
+        return 0;
+    }
+    return p;
+}
+
+void iqo_cuda_host_free(void *p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int iqo_cuda_create_on(iqo_cuda_resizer **out, int device, int kind, unsigned degree,
+                       size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale)
+{
+    if (!out) return fail(IQO_CUDA_E_ARG, "NULL output handle");
+    *out = 0;
+    iqo_cuda_resizer *r = new iqo_cuda_resizer();
+    int rc = buildPlan(r->plan, kind, degree, srcW, srcH, dstW, dstH, pxScale);
+    if (rc != kPlanOk) {
+        std::string msg = r->plan.error;
+        delete r;
+        return fail(rc, "%s", msg.c_str());  // PlanError values equal the IQO_CUDA_E_* codes
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        delete r;
+        return fail(IQO_CUDA_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) {
+        delete r;
+        return fail(IQO_CUDA_E_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    }
+    r->device = device;
+    DeviceGuard guard(device);
+    if (!guard.ok) {
+        delete r;
+        return fail(IQO_CUDA_E_CUDA, "cannot select device %d", device);
+    }
+    rc = IQO_CUDA_OK;
+    {
+        cudaError_t e = initKernels();
+        if (e != cudaSuccess) rc = fail(IQO_CUDA_E_CUDA, "kernel setup failed: %s", cudaGetErrorString(e));
+    }
+    if (rc == IQO_CUDA_OK) rc = uploadAxis(r->plan.x, r->tx);
+    if (rc == IQO_CUDA_OK) rc = uploadAxis(r->plan.y, r->ty);
+    for (int i = 0; i < 2 && rc == IQO_CUDA_OK; ++i) {
+        if (cudaStreamCreateWithFlags(&r->stream[i], cudaStreamNonBlocking) != cudaSuccess ||
+            cudaEventCreateWithFlags(&r->evUp[i], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&r->evDone[i], cudaEventDisableTiming) != cudaSuccess)
+            rc = fail(IQO_CUDA_E_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    if (rc != IQO_CUDA_OK) {
+        std::string keep = t_lastError;
+        iqo_cuda_destroy(r);
+        t_lastError = keep;
+        return rc;
+    }
+    r->geom = chooseGenericGeom(r->plan.x.first.data(), r->plan.x.N, int(r->plan.x.S), int(r->plan.x.D));
+    *out = r;
+    return IQO_CUDA_OK;
+}
+
+int iqo_cuda_create(iqo_cuda_resizer **out, int kind, unsigned degree,
+                    size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale)
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        // still run the planner so that argument errors are reported as such
+        Plan p;
+        int rc = buildPlan(p, kind, degree, srcW, srcH, dstW, dstH, pxScale);
+        if (rc != kPlanOk) return fail(rc, "%s", p.error.c_str());
+        return fail(IQO_CUDA_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    }
+    return iqo_cuda_create_on(out, dev, kind, degree, srcW, srcH, dstW, dstH, pxScale);
+}
+
+void iqo_cuda_destroy(iqo_cuda_resizer *r)
+{
+    if (!r) return;
+    DeviceGuard guard(r->device);
+    for (int i = 0; i < 2; ++i) {
+        if (r->stream[i]) {
+            cudaStreamSynchronize(r->stream[i]);
+            cudaStreamDestroy(r->stream[i]);
+        }
+        if (r->evUp[i]) cudaEventDestroy(r->evUp[i]);
+        if (r->evDone[i]) cudaEventDestroy(r->evDone[i]);
+        cudaFree(r->dSrc[i]);
+        cudaFree(r->dDst[i]);
+    }
+    freeAxis(r->tx);
+    freeAxis(r->ty);
+    cudaGetLastError();
+    delete r;
+}
+
+int iqo_cuda_sync(iqo_cuda_resizer *r)
+{
+    if (!r) return fail(IQO_CUDA_E_ARG, "NULL resizer");
+    DeviceGuard guard(r->device);
+    CUDA_TRY(cudaStreamSynchronize(r->stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(r->stream[1]));
+    return IQO_CUDA_OK;
+}
+
+int iqo_cuda_set_path(iqo_cuda_resizer *r, int path)
+{
+    if (!r || path < 0 || path > IQO_CUDA_PATH_GENERIC) return fail(IQO_CUDA_E_ARG, "bad path");
+    r->path = path;
+    return IQO_CUDA_OK;
+}
+
+const char *iqo_cuda_last_kernel(const iqo_cuda_resizer *r)
+{
+    return r ? r->lastKernel : "none";
+}
+
+int iqo_cuda_get_table(const iqo_cuda_resizer *r, int axis, int *numCoefs, int *numTables, int32_t *out, size_t cap)
+{
+    if (!r || axis < 0 || axis > 1) return fail(IQO_CUDA_E_ARG, "bad argument");
+    const AxisPlan &a = axis ? r->plan.y : r->plan.x;
+    if (numCoefs) *numCoefs = a.N;
+    if (numTables) *numTables = a.identity ? 1 : int(a.rD);
+    if (out) {
+        size_t n = size_t(a.N) * size_t(a.identity ? 1 : a.rD);
+        for (size_t i = 0; i < n && i < cap; ++i) out[i] = a.coef[i];
+    }
+    return IQO_CUDA_OK;
+}
+
+int iqo_cuda_plan_query(int kind, unsigned degree, size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale,
+                        int axis, int *numCoefs, int *numTables, int *numRows, long long *mainBegin, long long *mainEnd,
+                        int32_t *coefs, size_t coefCap, int32_t *first, int32_t *row, size_t indexCap)
+{
+    if (axis < 0 || axis > 1) return fail(IQO_CUDA_E_ARG, "bad axis");
+    Plan p;
+    int rc = buildPlan(p, kind, degree, srcW, srcH, dstW, dstH, pxScale);
+    if (rc != kPlanOk) return fail(rc, "%s", p.error.c_str());
+    const AxisPlan &a = axis ? p.y : p.x;
+    if (numCoefs) *numCoefs = a.N;
+    if (numTables) *numTables = a.identity ? 1 : int(a.rD);
+    if (numRows) *numRows = a.numRows;
+    if (mainBegin) *mainBegin = a.mainBegin;
+    if (mainEnd) *mainEnd = a.mainEnd;
+    if (coefs)
+        for (size_t i = 0; i < a.coef.size() && i < coefCap; ++i) coefs[i] = a.coef[i];
+    for (size_t i = 0; i < a.first.size() && i < indexCap; ++i) {
+        if (first) first[i] = a.first[i];
+        if (row) row[i] = a.row[i];
+    }
+    return IQO_CUDA_OK;
+}
+
+int iqo_cuda_resize_batch(iqo_cuda_resizer *r, size_t nFrames,
+                          size_t srcSt, size_t srcFrameStride, const uint8_t *src,
+                          size_t dstSt, size_t dstFrameStride, uint8_t *dst, void *stream)
+{
+    int rc = checkStrides(r, srcSt, src, dstSt, dst);
+    if (rc) return rc;
+    if (nFrames == 0) return IQO_CUDA_OK;
+    if (nFrames > (size_t(1) << 30)) return fail(IQO_CUDA_E_TOO_LARGE, "too many frames");
+    DeviceGuard guard(r->device);
+    if (!isDevicePointer(src) || !isDevicePointer(dst))
+        return fail(IQO_CUDA_E_ARG, "iqo_cuda_resize_batch needs device pointers (use iqo_cuda_resize_batch_host)");
+    cudaStream_t s = stream ? (cudaStream_t)stream : r->stream[0];
+    return launch(r, nFrames, 0, size_t(r->plan.y.D), 0, size_t(r->plan.y.S),
+                  srcSt, srcFrameStride, src, dstSt, dstFrameStride, dst, s);
+}
+
+int iqo_cuda_band_src_rows(const iqo_cuda_resizer *r, size_t dstRow0, size_t dstRows, size_t *srcRow0, size_t *srcRows)
+{
+    if (!r || !srcRow0 || !srcRows) return fail(IQO_CUDA_E_ARG, "NULL argument");
+    const AxisPlan &y = r->plan.y;
+    if (dstRows == 0 || dstRow0 + dstRows > size_t(y.D)) return fail(IQO_CUDA_E_ARG, "band outside the image");
+    int64_t lo = y.S - 1, hi = 0;
+    // first[] is non-decreasing; the band is spanned by its first and last row
+    lo = std::min<int64_t>(std::max<int64_t>(y.first[dstRow0], 0), y.S - 1);
+    hi = std::min<int64_t>(std::max<int64_t>(int64_t(y.first[dstRow0 + dstRows - 1]) + y.N - 1, 0), y.S - 1);
+    *srcRow0 = size_t(lo);
+    *srcRows = size_t(hi - lo + 1);
+    return IQO_CUDA_OK;
+}
+
+int iqo_cuda_resize_band(iqo_cuda_resizer *r, size_t dstRow0, size_t dstRows, size_t srcRow0, size_t srcRows,
+                         size_t srcSt, const uint8_t *src, size_t dstSt, uint8_t *dst, void *stream)
+{
+    int rc = checkStrides(r, srcSt, src, dstSt, dst);
+    if (rc) return rc;
+    size_t need0, needN;
+    rc = iqo_cuda_band_src_rows(r, dstRow0, dstRows, &need0, &needN);
+    if (rc) return rc;
+    if (srcRow0 > need0 || srcRow0 + srcRows < need0 + needN)
+        return fail(IQO_CUDA_E_ARG, "band needs source rows [%zu,%zu) but the buffer holds [%zu,%zu)",
+                    need0, need0 + needN, srcRow0, srcRow0 + srcRows);
+    DeviceGuard guard(r->device);
+    if (!isDevicePointer(src) || !isDevicePointer(dst))
+        return fail(IQO_CUDA_E_ARG, "iqo_cuda_resize_band needs device pointers");
+    cudaStream_t s = stream ? (cudaStream_t)stream : r->stream[0];
+    return launch(r, 1, dstRow0, dstRows, srcRow0, srcRows, srcSt, 0, src, dstSt, 0, dst, s);
+}
+
+int iqo_cuda_resize_batch_host(iqo_cuda_resizer *r, size_t nFrames,
+                               size_t srcSt, size_t srcFrameStride, const uint8_t *src,
+                               size_t dstSt, size_t dstFrameStride, uint8_t *dst)
+{
+    int rc = checkStrides(r, srcSt, src, dstSt, dst);
+    if (rc) return rc;
+    if (nFrames == 0) return IQO_CUDA_OK;
+    DeviceGuard guard(r->device);
+    const size_t SW = size_t(r->plan.x.S), SH = size_t(r->plan.y.S);
+    const size_t DW = size_t(r->plan.x.D), DH = size_t(r->plan.y.D);
+    // chunk: about 64 MiB of source per slot, at least one frame
+    const size_t frameBytes = alignUp(SW, 16) * SH + alignUp(DW, 16) * DH;
+    size_t chunk = std::max<size_t>(1, (size_t(96) << 20) / frameBytes);
+    chunk = std::min(chunk, nFrames);
+    rc = ensureStaging(r, chunk);
+    if (rc) return rc;
+    const size_t sFrame = r->srcPitch * SH, dFrame = r->dstPitch * DH;
+    // frames whose rows follow each other at the row stride can be moved by one 2-D copy per chunk
+    const bool srcRegular = (srcFrameStride == srcSt * SH);
+    const bool dstRegular = (dstFrameStride == dstSt * DH);
+
+    size_t done = 0;
+    int slot = 0;
+    while (done < nFrames) {
+        const size_t n = std::min(chunk, nFrames - done);
+        cudaStream_t s = r->stream[slot];
+        // the slot's previous download must have finished before its buffers are reused:
+        // same stream, so ordering is implicit.
+        const uint8_t *hs = src + done * srcFrameStride;
+        uint8_t *hd = dst + done * dstFrameStride;
+        if (srcRegular) {
+            CUDA_TRY(cudaMemcpy2DAsync(r->dSrc[slot], r->srcPitch, hs, srcSt, SW, SH * n, cudaMemcpyHostToDevice, s));
+        } else {
+            for (size_t f = 0; f < n; ++f)
+                CUDA_TRY(cudaMemcpy2DAsync(r->dSrc[slot] + f * sFrame, r->srcPitch, hs + f * srcFrameStride, srcSt,
+                                           SW, SH, cudaMemcpyHostToDevice, s));
+        }
+        rc = launch(r, n, 0, DH, 0, SH, r->srcPitch, sFrame, r->dSrc[slot], r->dstPitch, dFrame, r->dDst[slot], s);
+        if (rc) return rc;
+        if (dstRegular) {
+            CUDA_TRY(cudaMemcpy2DAsync(hd, dstSt, r->dDst[slot], r->dstPitch, DW, DH * n, cudaMemcpyDeviceToHost, s));
+        } else {
+            for (size_t f = 0; f < n; ++f)
+                CUDA_TRY(cudaMemcpy2DAsync(hd + f * dstFrameStride, dstSt, r->dDst[slot] + f * dFrame, r->dstPitch,
+                                           DW, DH, cudaMemcpyDeviceToHost, s));
+        }
+        done += n;
+        slot ^= 1;
+    }
+    CUDA_TRY(cudaStreamSynchronize(r->stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(r->stream[1]));
+    return IQO_CUDA_OK;
+}
+
+int iqo_cuda_resize(iqo_cuda_resizer *r, size_t srcSt, const uint8_t *src, size_t dstSt, uint8_t *dst)
+{
+    int rc = checkStrides(r, srcSt, src, dstSt, dst);
+    if (rc) return rc;
+    DeviceGuard guard(r->device);
+    const size_t SW = size_t(r->plan.x.S), SH = size_t(r->plan.y.S);
+    const size_t DW = size_t(r->plan.x.D), DH = size_t(r->plan.y.D);
+    const bool srcDev = isDevicePointer(src), dstDev = isDevicePointer(dst);
+    cudaStream_t s = r->stream[0];
+    const uint8_t *ksrc = src;
+    uint8_t *kdst = dst;
+    size_t kSrcSt = srcSt, kDstSt = dstSt;
+    if (!srcDev || !dstDev) {
+        rc = ensureStaging(r, 1);
+        if (rc) return rc;
+    }
+    if (!srcDev) {
+        CUDA_TRY(cudaMemcpy2DAsync(r->dSrc[0], r->srcPitch, src, srcSt, SW, SH, cudaMemcpyHostToDevice, s));
+        ksrc = r->dSrc[0];
+        kSrcSt = r->srcPitch;
+    }
+    if (!dstDev) {
+        kdst = r->dDst[0];
+        kDstSt = r->dstPitch;
+    }
+    rc = launch(r, 1, 0, DH, 0, SH, kSrcSt, 0, ksrc, kDstSt, 0, kdst, s);
+    if (rc) return rc;
+    if (!dstDev) CUDA_TRY(cudaMemcpy2DAsync(dst, dstSt, r->dDst[0], r->dstPitch, DW, DH, cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return IQO_CUDA_OK;
+}
+
+// ---- multi-device drivers: one host thread + one handle per device, no collectives ----
+
+int iqo_cuda_resize_batch_multi(int kind, unsigned degree,
+                                size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale,
+                                size_t nFrames,
+                                size_t srcSt, size_t srcFrameStride, const uint8_t *src,
+                                size_t dstSt, size_t dstFrameStride, uint8_t *dst,
+                                int nDevices, const int *devices)
+{
+    if (nDevices <= 0) return fail(IQO_CUDA_E_ARG, "nDevices must be positive");
+    if (!src || !dst) return fail(IQO_CUDA_E_ARG, "NULL image pointer");
+    std::vector<int> rcs(nDevices, IQO_CUDA_OK);
+    std::vector<std::string> msgs(nDevices);
+    std::vector<std::thread> threads;
+    const size_t per = (nFrames + nDevices - 1) / nDevices;
+    for (int i = 0; i < nDevices; ++i) {
+        threads.push_back(std::thread([=, &rcs, &msgs]() {
+            const size_t f0 = std::min(nFrames, per * i), f1 = std::min(nFrames, f0 + per);
+            const int dev = devices ? devices[i] : i;
+            iqo_cuda_resizer *r = 0;
+            int rc = iqo_cuda_create_on(&r, dev, kind, degree, srcW, srcH, dstW, dstH, pxScale);
+            if (rc == IQO_CUDA_OK && f1 > f0)
+                rc = iqo_cuda_resize_batch_host(r, f1 - f0, srcSt, srcFrameStride, src + f0 * srcFrameStride,
+                                                dstSt, dstFrameStride, dst + f0 * dstFrameStride);
+            if (rc != IQO_CUDA_OK) msgs[i] = iqo_cuda_last_error();
+            iqo_cuda_destroy(r);
+            rcs[i] = rc;
+        }));
+    }
+    for (size_t i = 0; i < threads.size(); ++i) threads[i].join();
+    for (int i = 0; i < nDevices; ++i)
+        if (rcs[i] != IQO_CUDA_OK) return fail(rcs[i], "device %d: %s", devices ? devices[i] : i, msgs[i].c_str());
+    return IQO_CUDA_OK;
+}
+
+int iqo_cuda_resize_bands_multi(int kind, unsigned degree,
+                                size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale,
+                                size_t srcSt, const uint8_t *src, size_t dstSt, uint8_t *dst,
+                                int nDevices, const int *devices)
+{
+    if (nDevices <= 0) return fail(IQO_CUDA_E_ARG, "nDevices must be positive");
+    if (!src || !dst) return fail(IQO_CUDA_E_ARG, "NULL image pointer");
+    if (srcSt < srcW || dstSt < dstW) return fail(IQO_CUDA_E_ARG, "stride smaller than width");
+    std::vector<int> rcs(nDevices, IQO_CUDA_OK);
+    std::vector<std::string> msgs(nDevices);
+    std::vector<std::thread> threads;
+    const size_t per = (dstH + nDevices - 1) / nDevices;
+    for (int i = 0; i < nDevices; ++i) {
+        threads.push_back(std::thread([=, &rcs, &msgs]() {
+            const size_t y0 = std::min(dstH, per * i), y1 = std::min(dstH, y0 + per);
+            const int dev = devices ? devices[i] : i;
+            if (y1 <= y0) return;
+            iqo_cuda_resizer *r = 0;
+            uint8_t *dS = 0, *dD = 0;
+            int rc = iqo_cuda_create_on(&r, dev, kind, degree, srcW, srcH, dstW, dstH, pxScale);
+            if (rc == IQO_CUDA_OK) {
+                cudaSetDevice(dev);
+                size_t s0 = 0, sn = 0;
+                rc = iqo_cuda_band_src_rows(r, y0, y1 - y0, &s0, &sn);
+                const size_t sp = alignUp(srcW, 16), dp = alignUp(dstW, 16);
+                cudaStream_t st = r->stream[0];
+                if (rc == IQO_CUDA_OK &&
+                    (cudaMalloc(&dS, sp * sn) != cudaSuccess || cudaMalloc(&dD, dp * (y1 - y0)) != cudaSuccess))
+                    rc = fail(IQO_CUDA_E_NOMEM, "band buffers: %s", cudaGetErrorString(cudaGetLastError()));
+                // the band's halo rows are part of its own upload: no device-to-device exchange
+                if (rc == IQO_CUDA_OK &&
+                    cudaMemcpy2DAsync(dS, sp, src + s0 * srcSt, srcSt, srcW, sn, cudaMemcpyHostToDevice, st) != cudaSuccess)
+                    rc = fail(IQO_CUDA_E_CUDA, "band upload: %s", cudaGetErrorString(cudaGetLastError()));
+                if (rc == IQO_CUDA_OK) rc = iqo_cuda_resize_band(r, y0, y1 - y0, s0, sn, sp, dS, dp, dD, st);
+                if (rc == IQO_CUDA_OK &&
+                    (cudaMemcpy2DAsync(dst + y0 * dstSt, dstSt, dD, dp, dstW, y1 - y0, cudaMemcpyDeviceToHost, st) != cudaSuccess ||
+                     cudaStreamSynchronize(st) != cudaSuccess))
+                    rc = fail(IQO_CUDA_E_CUDA, "band download: %s", cudaGetErrorString(cudaGetLastError()));
+            }
+            if (rc != IQO_CUDA_OK) msgs[i] = iqo_cuda_last_error();
+            cudaFree(dS);
+            cudaFree(dD);
+            iqo_cuda_destroy(r);
+            rcs[i] = rc;
+        }));
+    }
+    for (size_t i = 0; i < threads.size(); ++i) threads[i].join();
+    for (int i = 0; i < nDevices; ++i)
+        if (rcs[i] != IQO_CUDA_OK) return fail(rcs[i], "device %d: %s", devices ? devices[i] : i, msgs[i].c_str());
+    return IQO_CUDA_OK;
+}
+
+}  // extern "C"

@@ -142,6 +142,16 @@ void iqo_ref_public_delete(void *hv)
     delete h;
 }
 
+// torchrun exports OMP_NUM_THREADS=1 to its workers; the baseline wants all host cores
+void iqo_ref_set_threads(int n)
+{
+#if defined(_OPENMP)
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int iqo_ref_threads(void)
 {
 #if defined(_OPENMP)

@@ -94,6 +94,8 @@ def ref_full():
             lib.iqo_ref_public_delete.restype = None
             lib.iqo_ref_public_delete.argtypes = [C.c_void_p]
             lib.iqo_ref_threads.restype = C.c_int
+            lib.iqo_ref_set_threads.restype = None
+            lib.iqo_ref_set_threads.argtypes = [C.c_int]
             lib.iqo_ref_generic_resize.restype = C.c_int
             lib.iqo_ref_generic_resize.argtypes = [C.c_int, C.c_uint, _sz, _sz, _sz, _sz, _sz, _sz, _u8p, _sz, _u8p]
         _ref_full = lib

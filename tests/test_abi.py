@@ -1,0 +1,111 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports every symbol that
+include/iqo_cuda.h declares, reports errors without a GPU (no CPU fallback), and its host
+planner produces the reference's tables and index maps.  No kernel is launched here."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import libiqo_b200 as iqo
+from oracle_lib import AREA, LANCZOS, LINEAR, oracle_table
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "iqo_cuda.h")).read()
+    return sorted(set(re.findall(r"IQO_CUDA_API\s+[\w\s\*]+?\b(iqo_cuda_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree():
+    assert _declared_symbols() == iqo.exported_symbols()
+
+
+def test_library_exports_every_declared_symbol():
+    lib = iqo.lib()
+    out = subprocess.check_output(["nm", "-D", "--defined-only", iqo.LIB_PATH]).decode()
+    exported = set(re.findall(r"\bT (iqo_cuda_\w+)", out))
+    for name in _declared_symbols():
+        assert name in exported, name
+        assert getattr(lib, name) is not None
+    # and the C++ classes with the reference's mangled signatures (iqo::LanczosResizer etc.)
+    cxx = subprocess.check_output(["nm", "-DC", "--defined-only", iqo.LIB_PATH]).decode()
+    for sig in ("iqo::LanczosResizer::LanczosResizer(unsigned int, unsigned long, unsigned long, unsigned long, unsigned long, unsigned long)",
+                "iqo::LanczosResizer::resize(unsigned long, unsigned char const*, unsigned long, unsigned char*)",
+                "iqo::AreaResizer::AreaResizer(unsigned long, unsigned long, unsigned long, unsigned long)",
+                "iqo::AreaResizer::resize(unsigned long, unsigned char const*, unsigned long, unsigned char*)",
+                "iqo::LinearResizer::LinearResizer(unsigned long, unsigned long, unsigned long, unsigned long)",
+                "iqo::LinearResizer::resize(unsigned long, unsigned char const*, unsigned long, unsigned char*)",
+                "iqo::LanczosResizer::~LanczosResizer()"):
+        assert sig in cxx, sig
+
+
+def test_version_and_error_strings():
+    lib = iqo.lib()
+    assert b"sm_100a" in lib.iqo_cuda_version()
+    assert isinstance(lib.iqo_cuda_last_error(), bytes)
+
+
+def test_no_cpu_fallback_without_device():
+    if iqo.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(iqo.IqoCudaError) as e:
+        iqo.LanczosResizer(3, 64, 48, 32, 24)
+    assert e.value.code == -5 and "no CPU fallback" in str(e.value)
+
+
+def test_argument_errors_are_reported_before_touching_cuda():
+    for args, code in (((LANCZOS, 3, 0, 10, 5, 5, 1), -1), ((LANCZOS, 0, 10, 10, 5, 5, 1), -1),
+                       ((LANCZOS, 3, 8, 8, 5, 5, 1), -2),      # source shorter than the kernel
+                       ((LANCZOS, 1, 100, 100, 99, 99, 1), -3),  # border denominator 0
+                       ((AREA, 0, 1 << 31, 10, 5, 5, 1), -4)):
+        with pytest.raises(iqo.IqoCudaError) as e:
+            iqo.plan_query(*args, 0)
+        assert e.value.code == code, args
+
+
+CASES = [
+    (LANCZOS, 3, 1920, 1080, 1280, 720, 1), (LANCZOS, 3, 1920, 1080, 960, 540, 1),
+    (LANCZOS, 2, 3840, 2160, 1920, 1080, 1), (LANCZOS, 2, 1920, 1080, 960, 540, 2),
+    (LANCZOS, 4, 32768, 32768, 12000, 12000, 1), (LANCZOS, 3, 40, 30, 64, 48, 1),
+    (LANCZOS, 5, 641, 479, 333, 211, 1), (LANCZOS, 2, 333, 211, 641, 479, 1),
+    (LANCZOS, 9, 1000, 900, 77, 50, 1), (LANCZOS, 4, 100, 80, 50, 40, 2),
+    (AREA, 0, 3840, 2160, 1920, 1080, 1), (AREA, 0, 1920, 1080, 1280, 720, 1),
+    (AREA, 0, 641, 479, 333, 211, 1), (AREA, 0, 40, 30, 64, 48, 1),
+    (LINEAR, 0, 1280, 720, 3840, 2160, 1), (LINEAR, 0, 40, 30, 100, 75, 1), (LINEAR, 0, 333, 211, 641, 479, 1),
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_planner_tables_match_oracle(case):
+    kind, deg, sw, sh, dw, dh, px = case
+    for axis, S, D in ((0, sw, dw), (1, sh, dh)):
+        q = iqo.plan_query(kind, deg, sw, sh, dw, dh, px, axis)
+        ref = oracle_table(kind, axis, S, D, deg, px)
+        assert q["numCoefs"] == ref.shape[1] and q["numTables"] == ref.shape[0]
+        assert np.array_equal(q["coefs"][: ref.shape[0]], ref)
+
+
+def test_planner_index_maps():
+    # Lanczos3 1080 -> 540: first = 2d - 5, border rows 3 + 3
+    q = iqo.plan_query(LANCZOS, 3, 1920, 1080, 960, 540, 1, 1)
+    assert (q["mainBegin"], q["mainEnd"]) == (3, 537)
+    assert np.array_equal(q["first"], 2 * np.arange(540) - 5)
+    assert (q["row"][3:537] == 0).all() and (q["row"][:3] > 0).all() and (q["row"][537:] > 0).all()
+    assert q["numRows"] == 1 + 6
+    # border rows: out-of-range taps removed
+    assert q["coefs"][q["row"][0]].tolist() == [0, 0, 0, 0, 0, 28, 28, 9, -4, -2, 1, 0]
+    # Area: first = floor(d*S/D); Linear 3x: first = floor(((2d+1)S - D)/(2D)) with replicated ends
+    q = iqo.plan_query(AREA, 0, 1920, 1080, 1280, 720, 1, 0)
+    assert np.array_equal(q["first"], np.arange(1280) * 1920 // 1280)
+    q = iqo.plan_query(LINEAR, 0, 1280, 720, 3840, 2160, 1, 0)
+    d = np.arange(3840)
+    f = ((2 * d + 1) * 1280 - 3840) // (2 * 3840)
+    f[0], f[-1] = 0, 1279
+    assert np.array_equal(q["first"], f)
+    assert q["coefs"][q["row"][0]].tolist() == [32768, 0] and q["coefs"][q["row"][-1]].tolist() == [32768, 0]
+    # identity axis is a single tap of weight one
+    q = iqo.plan_query(LANCZOS, 3, 64, 48, 64, 30, 1, 0)
+    assert q["numCoefs"] == 1 and q["coefs"].tolist() == [[16384]] and np.array_equal(q["first"], np.arange(64))

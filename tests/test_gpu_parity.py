@@ -1,0 +1,206 @@
+"""GPU parity tests (run on the B200 box with -m gpu).  Everything goes through the C ABI
+(libiqo_b200 -> libiqo_cuda.so) and is compared bit-for-bit with the oracle / golden fixtures."""
+import random
+
+import numpy as np
+import pytest
+
+import golden_cases as G
+import libiqo_b200 as iqo
+from oracle_lib import AREA, LANCZOS, LINEAR, fnv1a, lcg_image, oracle_resize
+
+pytestmark = pytest.mark.gpu
+
+PATHS = [iqo.PATH_AUTO, iqo.PATH_GENERIC]
+
+
+def gpu_resize(kind, src, dw, dh, deg=0, px=1, sw=None, dst_stride=None, path=iqo.PATH_AUTO):
+    sh, sst = src.shape
+    sw = sw or sst
+    dst_stride = dst_stride or dw
+    dst = np.full((dh, dst_stride), 0xA5, dtype=np.uint8)
+    with iqo.make_resizer(kind, deg, sw, sh, dw, dh, px) as r:
+        r.set_path(path)
+        r.resize(sst, src, dst_stride, dst)
+        kernel = r.last_kernel()
+    return dst, kernel
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("i", range(len(G.SMALL)), ids=[G.case_id(c) for c in G.SMALL])
+def test_golden_small(i, path):
+    kind, deg, px, sw, sh, dw, dh, spad, dpad, seed = G.SMALL[i]
+    dst, _ = gpu_resize(kind, G.case_src(G.SMALL[i]), dw, dh, deg, px, sw=sw, dst_stride=dw + dpad, path=path)
+    assert np.array_equal(dst[:, :dw], G.small_expected(i))
+    assert (dst[:, dw:] == 0xA5).all(), "bytes beyond dstW must not be written"
+
+
+@pytest.mark.parametrize("path", PATHS)
+@pytest.mark.parametrize("c", G.LARGE, ids=[G.case_id(c) for c in G.LARGE])
+def test_golden_hash(c, path):
+    kind, deg, px, sw, sh, dw, dh, spad, dpad, seed, h = c
+    dst, _ = gpu_resize(kind, G.case_src(c), dw, dh, deg, px, sw=sw, dst_stride=dw + dpad, path=path)
+    assert "%016x" % fnv1a(dst, dw) == h
+
+
+@pytest.mark.parametrize("path", PATHS)
+def test_random_sweep_against_oracle(path):
+    rng = random.Random(99)
+    checked = 0
+    for _ in range(160):
+        kind = rng.choice([LANCZOS, LANCZOS, AREA, LINEAR])
+        sw, sh = rng.randint(1, 300), rng.randint(1, 200)
+        if kind == LINEAR:
+            dw, dh = rng.randint(sw, 3 * sw), rng.randint(sh, 3 * sh)
+        elif kind == AREA:
+            dw, dh = rng.randint(1, sw + 8), rng.randint(1, sh + 8)
+        else:
+            dw, dh = rng.randint(1, 400), rng.randint(1, 300)
+        if rng.random() < 0.15:
+            dw = sw
+        if rng.random() < 0.15:
+            dh = sh
+        deg = rng.randint(1, 9) if kind == LANCZOS else 0
+        px = rng.choice([1, 1, 2]) if kind == LANCZOS else 1
+        src = lcg_image(sh, sw + rng.randint(0, 5), seed=rng.randint(1, 1 << 30))
+        dpad = rng.randint(0, 5)
+        rc, want = oracle_resize(kind, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+        if rc != 0:
+            with pytest.raises(iqo.IqoCudaError) as e:
+                iqo.make_resizer(kind, deg, sw, sh, dw, dh, px)
+            assert e.value.code == rc
+            continue
+        got, _ = gpu_resize(kind, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad, path=path)
+        assert np.array_equal(got, want), (kind, deg, px, sw, sh, dw, dh)
+        checked += 1
+    assert checked > 100
+
+
+@pytest.mark.parametrize("v", [0, 100, 255])
+def test_constant_images(v):
+    src = np.full((108, 192), v, dtype=np.uint8)
+    for kind, deg, px, dw, dh in ((AREA, 0, 1, 96, 54), (LINEAR, 0, 1, 384, 216), (LANCZOS, 3, 1, 96, 54),
+                                  (LANCZOS, 2, 2, 96, 54), (LANCZOS, 3, 1, 128, 72)):
+        rc, want = oracle_resize(kind, src, dw, dh, deg, px)
+        got, _ = gpu_resize(kind, src, dw, dh, deg, px)
+        assert rc == 0 and np.array_equal(got, want)
+        if kind != LANCZOS:
+            assert (got == v).all()
+
+
+def test_device_pointers_and_batch():
+    torch = pytest.importorskip("torch")
+    n, sw, sh, dw, dh = 5, 192, 108, 96, 54
+    frames = np.stack([lcg_image(sh, sw, seed=10 + f) for f in range(n)])
+    want = np.stack([oracle_resize(LANCZOS, frames[f], dw, dh, 3)[1] for f in range(n)])
+    dsrc = torch.from_numpy(frames).cuda()
+    ddst = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
+    with iqo.LanczosResizer(3, sw, sh, dw, dh) as r:
+        # single frame, device pointers, through resize()
+        r.resize(sw, dsrc[2], dw, ddst[2])
+        assert np.array_equal(ddst[2].cpu().numpy(), want[2])
+        ddst.zero_()
+        # one launch for the batch on torch's current stream
+        r.resize_batch(n, sw, sw * sh, dsrc, dw, dw * dh, ddst, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(ddst.cpu().numpy(), want)
+        # host-resident batch through the pipelined path
+        out = np.zeros_like(want)
+        r.resize_batch_host(n, sw, sw * sh, frames, dw, dw * dh, out)
+        assert np.array_equal(out, want)
+        # host pointers are rejected by the device-batch entry point
+        with pytest.raises(iqo.IqoCudaError):
+            r.resize_batch(n, sw, sw * sh, frames, dw, dw * dh, out)
+
+
+def test_batch_host_irregular_strides_and_many_chunks():
+    # frame strides that are not rows*stride, and enough frames for several pipeline chunks
+    n, sw, sh, dw, dh = 40, 1920, 1080, 960, 540
+    sst, dst_st = sw + 16, dw + 8
+    sfs, dfs = sst * sh + 64, dst_st * dh + 32
+    src = np.zeros(n * sfs, dtype=np.uint8)
+    base = lcg_image(sh, sst, seed=77)
+    for f in range(n):
+        src[f * sfs: f * sfs + sst * sh] = np.roll(base, f, axis=0).ravel()
+    dst = np.full(n * dfs, 0xA5, dtype=np.uint8)
+    with iqo.LanczosResizer(3, sw, sh, dw, dh) as r:
+        r.resize_batch_host(n, sst, sfs, src, dst_st, dfs, dst)
+    for f in (0, 1, 17, 39):
+        rc, want = oracle_resize(LANCZOS, np.roll(base, f, axis=0), dw, dh, 3, sw=sw, dst_stride=dst_st)
+        got = dst[f * dfs: f * dfs + dst_st * dh].reshape(dh, dst_st)
+        assert np.array_equal(got, want)
+    assert (dst[dst_st * dh: dfs] == 0xA5).all()
+
+
+@pytest.mark.parametrize("case", [(LANCZOS, 4, 1, 1024, 768, 375, 281), (AREA, 0, 1, 600, 500, 333, 211),
+                                  (LINEAR, 0, 1, 200, 150, 500, 420), (LANCZOS, 2, 1, 300, 200, 450, 330)])
+def test_row_bands_equal_whole_image(case):
+    torch = pytest.importorskip("torch")
+    kind, deg, px, sw, sh, dw, dh = case
+    src = lcg_image(sh, sw, seed=5)
+    rc, want = oracle_resize(kind, src, dw, dh, deg, px)
+    assert rc == 0
+    out = np.zeros((dh, dw), dtype=np.uint8)
+    with iqo.make_resizer(kind, deg, sw, sh, dw, dh, px) as r:
+        bands = [(0, 7), (7, dh // 3), (7 + dh // 3, dh - 7 - dh // 3)]
+        for y0, n in bands:
+            s0, sn = r.band_src_rows(y0, n)
+            dsrc = torch.from_numpy(src[s0:s0 + sn].copy()).cuda()   # band + halo only
+            ddst = torch.zeros((n, dw), dtype=torch.uint8, device="cuda")
+            r.resize_band(y0, n, s0, sn, sw, dsrc, dw, ddst)
+            r.sync()
+            out[y0:y0 + n] = ddst.cpu().numpy()
+        # a buffer that misses halo rows is refused
+        s0, sn = r.band_src_rows(7, dh // 3)
+        if sn > 2:
+            with pytest.raises(iqo.IqoCudaError):
+                r.resize_band(7, dh // 3, s0 + 1, sn - 1, sw, dsrc, dw, ddst)
+    assert np.array_equal(out, want)
+
+
+def test_multi_device_drivers_on_available_devices():
+    ndev = iqo.device_count()
+    devices = list(range(min(ndev, 2))) * (2 if ndev == 1 else 1)   # 2 shards even on one GPU
+    sw, sh, dw, dh = 640, 480, 400, 300
+    src = lcg_image(sh, sw, seed=3)
+    rc, want = oracle_resize(LANCZOS, src, dw, dh, 3)
+    out = np.zeros((dh, dw), dtype=np.uint8)
+    iqo.resize_bands_multi(LANCZOS, 3, sw, sh, dw, dh, 1, sw, src, dw, out, devices)
+    assert np.array_equal(out, want)
+    n = 7
+    frames = np.stack([lcg_image(sh, sw, seed=20 + f) for f in range(n)])
+    outs = np.zeros((n, dh, dw), dtype=np.uint8)
+    iqo.resize_batch_multi(LANCZOS, 3, sw, sh, dw, dh, 1, n, sw, sw * sh, frames, dw, dw * dh, outs, devices)
+    for f in range(n):
+        assert np.array_equal(outs[f], oracle_resize(LANCZOS, frames[f], dw, dh, 3)[1])
+
+
+def test_full_size_batch_properties():
+    """cfg4 shape at a batch size the oracle cannot check frame by frame: identical frames give
+    identical results, and frame 0 hashes to the reference's golden value."""
+    torch = pytest.importorskip("torch")
+    n, sw, sh, dw, dh = 64, 1920, 1080, 960, 540
+    base = torch.from_numpy(lcg_image(sh, sw, seed=1)).cuda()
+    dsrc = base.unsqueeze(0).repeat(n, 1, 1).contiguous()
+    ddst = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
+    with iqo.LanczosResizer(3, sw, sh, dw, dh) as r:
+        r.resize_batch(n, sw, sw * sh, dsrc, dw, dw * dh, ddst, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    out = ddst.cpu().numpy()
+    assert "%016x" % fnv1a(out[0]) == "bc3ae031361c0774"
+    assert (out == out[0]).all()
+
+
+def test_errors():
+    with pytest.raises(iqo.IqoCudaError) as e:
+        iqo.LanczosResizer(3, 8, 8, 5, 5)
+    assert e.value.code == -2
+    with iqo.AreaResizer(64, 48, 32, 24) as r:
+        src = np.zeros((48, 64), dtype=np.uint8)
+        dst = np.zeros((24, 32), dtype=np.uint8)
+        with pytest.raises(iqo.IqoCudaError):
+            r.resize(63, src, 32, dst)   # stride < width
+        with pytest.raises(iqo.IqoCudaError):
+            r.resize(64, 0, 32, dst)     # NULL
+        r.resize(64, src, 32, dst)
+        assert iqo.launch_count() > 0

@@ -82,7 +82,7 @@ IQO_CUDA_API int iqo_cuda_resize(iqo_cuda_resizer *r, size_t srcSt, const uint8_
                                  size_t dstSt, uint8_t *dst);
 
 /* Device-resident batch of independent frames in ONE launch sequence on `stream`
- * (a cudaStream_t passed as void*; NULL = the handle's own stream).  Frame f lives at
+ * (a cudaStream_t passed as void*; NULL = the default stream, as everywhere in CUDA).  Frame f lives at
  * src + f*srcFrameStride / dst + f*dstFrameStride.  Asynchronous: returns after enqueueing.
  * The batched form of resize(): the reference's callers loop over frames
  * (benchmark/benchmark.cpp:1017-1033). */
@@ -142,6 +142,12 @@ IQO_CUDA_API int iqo_cuda_plan_query(int kind, unsigned degree,
                                      long long *mainBegin, long long *mainEnd,
                                      int32_t *coefs, size_t coefCap,
                                      int32_t *first, int32_t *row, size_t indexCap);
+/* Host-only: which kernel IQO_CUDA_PATH_AUTO selects for this shape when the buffers are
+ * suitably aligned ("half_sym", "half", "generic"), and, for "generic", why the specialised
+ * kernel is not eligible.  Both strings are copied NUL-terminated into the caller's buffers. */
+IQO_CUDA_API int iqo_cuda_plan_kernel(int kind, unsigned degree,
+                                      size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale,
+                                      char *kernel, size_t kernelCap, char *why, size_t whyCap);
 IQO_CUDA_API int iqo_cuda_set_path(iqo_cuda_resizer *r, int path);
 /* name of the kernel the last launch used, e.g. "generic" */
 IQO_CUDA_API const char *iqo_cuda_last_kernel(const iqo_cuda_resizer *r);

@@ -54,6 +54,7 @@ _SIGNATURES = {
                                       C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
                                       C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                       _vp, _sz, _vp, _vp, _sz]),
+    "iqo_cuda_plan_kernel": (C.c_int, [C.c_int, C.c_uint, _sz, _sz, _sz, _sz, _sz, C.c_char_p, _sz, C.c_char_p, _sz]),
     "iqo_cuda_set_path": (C.c_int, [_vp, C.c_int]),
     "iqo_cuda_last_kernel": (C.c_char_p, [_vp]),
     "iqo_cuda_launch_count": (C.c_ulonglong, []),
@@ -255,6 +256,13 @@ def plan_query(kind, degree, srcW, srcH, dstW, dstH, pxScale, axis):
                                      first.ctypes.data, row.ctypes.data, D))
     return dict(numCoefs=n.value, numTables=t.value, numRows=rws.value, mainBegin=mb.value, mainEnd=me.value,
                 coefs=coefs.reshape(rws.value, n.value), first=first, row=row)
+
+
+def plan_kernel(kind, degree, srcW, srcH, dstW, dstH, pxScale=1):
+    """(kernel name AUTO would select for aligned buffers, reason when it is "generic").  Needs no GPU."""
+    k, w = C.create_string_buffer(64), C.create_string_buffer(256)
+    _check(lib().iqo_cuda_plan_kernel(kind, degree, srcW, srcH, dstW, dstH, pxScale, k, 64, w, 256))
+    return k.value.decode(), w.value.decode()
 
 
 def device_count():

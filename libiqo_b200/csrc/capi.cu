@@ -3,6 +3,7 @@
 
 #include <cuda_runtime.h>
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 
@@ -70,6 +71,8 @@ struct iqo_cuda_resizer {
     int device;
     AxisTables tx, ty;
     GenericGeom geom;
+    HalfPlan half;
+    uint32_t *dBorderY;
     int path;
     const char *lastKernel;
     cudaStream_t stream[2];
@@ -79,7 +82,7 @@ struct iqo_cuda_resizer {
     size_t srcPitch, dstPitch;  // device pitches of the staging frames
     size_t slotFrames;
 
-    iqo_cuda_resizer() : device(0), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
+    iqo_cuda_resizer() : device(0), dBorderY(0), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
     {
         for (int i = 0; i < 2; ++i) {
             stream[i] = 0;
@@ -158,6 +161,51 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
     a.shift = r->plan.shift;
     a.lanczos = r->plan.kind == kLanczos;
     a.workSigned = r->plan.workSigned;
+    const bool whole = dstRow0 == 0 && dstRows == size_t(r->plan.y.D) && srcRow0 == 0;
+    if (r->path == IQO_CUDA_PATH_AUTO && r->half.eligible && whole &&
+        ((uintptr_t)src % 4) == 0 && srcSt % 4 == 0 && srcFrameStride % 4 == 0) {
+        const HalfPlan &hp = r->half;
+        HalfArgs h;
+        h.src = src;
+        h.dst = dst;
+        h.srcPitch = (long long)srcSt;
+        h.dstPitch = (long long)dstSt;
+        h.srcFrameStride = (long long)srcFrameStride;
+        h.dstFrameStride = (long long)dstFrameStride;
+        h.SW = int(r->plan.x.S);
+        h.SH = int(r->plan.y.S);
+        h.DW = int(r->plan.x.D);
+        h.DH = int(r->plan.y.D);
+        h.nFrames = int(nFrames);
+        const int tiles = (h.DH + 63) / 64;
+        h.tileRows = 2 * ((h.DH + 2 * tiles - 1) / (2 * tiles));
+        h.dstVec = ((uintptr_t)dst % 8) == 0 && dstSt % 8 == 0 && dstFrameStride % 8 == 0;
+        h.qmin = hp.qmin;
+        h.NG = hp.NG;
+        memcpy(h.cwY, hp.cwY, sizeof h.cwY);
+        h.borderY = r->dBorderY;
+        h.rowY = r->ty.row;
+        h.denoY = r->ty.deno;
+        h.mbY = int(r->plan.y.mainBegin);
+        h.meY = int(r->plan.y.mainEnd);
+        h.workBias = hp.workBias;
+        h.NWX = hp.NWX;
+        h.symmetric = hp.symmetric;
+        memcpy(h.cwX, hp.cwX, sizeof h.cwX);
+        memcpy(h.cwXs, hp.cwXs, sizeof h.cwXs);
+        h.accInit = hp.accInit;
+        h.mbX = int(r->plan.x.mainBegin);
+        h.meX = int(r->plan.x.mainEnd);
+        h.firstX = r->tx.first;
+        h.rowX = r->tx.row;
+        h.coefX = r->tx.coef;
+        h.denoX = r->tx.deno;
+        h.NX = r->plan.x.N;
+        h.zero = 0;
+        r->lastKernel = hp.symmetric ? "half_sym" : "half";
+        CUDA_TRY(launchHalf(h, stream));
+        return IQO_CUDA_OK;
+    }
     r->lastKernel = "generic";
     CUDA_TRY(launchGeneric(a, r->geom, stream));
     return IQO_CUDA_OK;
@@ -290,6 +338,16 @@ int iqo_cuda_create_on(iqo_cuda_resizer **out, int device, int kind, unsigned de
         t_lastError = keep;
         return rc;
     }
+    buildHalfPlan(r->plan, r->half);
+    if (r->half.eligible) {
+        DeviceGuard g2(device);
+        const size_t bytes = r->half.borderY.size() * sizeof(uint32_t);
+        if (cudaMalloc(&r->dBorderY, bytes) != cudaSuccess ||
+            cudaMemcpy(r->dBorderY, r->half.borderY.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError();
+            r->half.eligible = false;
+        }
+    }
     r->geom = chooseGenericGeom(r->plan.x.first.data(), r->plan.x.N, int(r->plan.x.S), int(r->plan.x.D));
     *out = r;
     return IQO_CUDA_OK;
@@ -326,6 +384,7 @@ void iqo_cuda_destroy(iqo_cuda_resizer *r)
     }
     freeAxis(r->tx);
     freeAxis(r->ty);
+    cudaFree(r->dBorderY);
     cudaGetLastError();
     delete r;
 }
@@ -387,6 +446,19 @@ int iqo_cuda_plan_query(int kind, unsigned degree, size_t srcW, size_t srcH, siz
     return IQO_CUDA_OK;
 }
 
+int iqo_cuda_plan_kernel(int kind, unsigned degree, size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale,
+                         char *kernel, size_t kernelCap, char *why, size_t whyCap)
+{
+    Plan p;
+    int rc = buildPlan(p, kind, degree, srcW, srcH, dstW, dstH, pxScale);
+    if (rc != kPlanOk) return fail(rc, "%s", p.error.c_str());
+    HalfPlan h;
+    buildHalfPlan(p, h);
+    if (kernel && kernelCap) snprintf(kernel, kernelCap, "%s", h.eligible ? (h.symmetric ? "half_sym" : "half") : "generic");
+    if (why && whyCap) snprintf(why, whyCap, "%s", h.why.c_str());
+    return IQO_CUDA_OK;
+}
+
 int iqo_cuda_resize_batch(iqo_cuda_resizer *r, size_t nFrames,
                           size_t srcSt, size_t srcFrameStride, const uint8_t *src,
                           size_t dstSt, size_t dstFrameStride, uint8_t *dst, void *stream)
@@ -398,7 +470,7 @@ int iqo_cuda_resize_batch(iqo_cuda_resizer *r, size_t nFrames,
     DeviceGuard guard(r->device);
     if (!isDevicePointer(src) || !isDevicePointer(dst))
         return fail(IQO_CUDA_E_ARG, "iqo_cuda_resize_batch needs device pointers (use iqo_cuda_resize_batch_host)");
-    cudaStream_t s = stream ? (cudaStream_t)stream : r->stream[0];
+    cudaStream_t s = (cudaStream_t)stream;  // NULL = the legacy default stream, as everywhere in CUDA
     return launch(r, nFrames, 0, size_t(r->plan.y.D), 0, size_t(r->plan.y.S),
                   srcSt, srcFrameStride, src, dstSt, dstFrameStride, dst, s);
 }
@@ -431,7 +503,7 @@ int iqo_cuda_resize_band(iqo_cuda_resizer *r, size_t dstRow0, size_t dstRows, si
     DeviceGuard guard(r->device);
     if (!isDevicePointer(src) || !isDevicePointer(dst))
         return fail(IQO_CUDA_E_ARG, "iqo_cuda_resize_band needs device pointers");
-    cudaStream_t s = stream ? (cudaStream_t)stream : r->stream[0];
+    cudaStream_t s = (cudaStream_t)stream;  // NULL = the legacy default stream, as everywhere in CUDA
     return launch(r, 1, dstRow0, dstRows, srcRow0, srcRows, srcSt, 0, src, dstSt, 0, dst, s);
 }
 

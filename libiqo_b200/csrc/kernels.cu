@@ -113,6 +113,373 @@ __global__ void __launch_bounds__(256) resizeGenericKernel(ResizeArgs a, int til
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Specialised kernel: Lanczos 2:1 down-sampling on both axes, single-phase tables
+// (BASELINE configs 3 and 4).  One CTA = 256 threads = one tile of 120 x tileRows
+// destination pixels of one frame.
+//
+//  vertical pass   thread = 4 adjacent source columns (one aligned 32-bit word per source row)
+//                  x one strip of destination rows.  Source rows are read straight from global
+//                  memory (a warp reads 128 contiguous bytes per row), four rows at a time;
+//                  the 4x4 byte block is transposed in registers (8 PRMT) so that one register
+//                  holds four vertically adjacent bytes of a column, and each destination row is
+//                  NG dp4a(u8 x s8) per column against packed coefficient words.  A sliding
+//                  window of NG groups lives in registers, so every source row is loaded and
+//                  transposed once per strip.  Results (+bias, so they are non-negative u16) go
+//                  to shared memory as 16-bit pairs; the intermediate never reaches HBM.
+//  horizontal pass thread = 8 adjacent destination pixels of one row: four conflict-free 16-byte
+//                  shared loads (XOR-swizzled chunks), then per pixel dp2a(u16 x u8 / u16 x s8)
+//                  over "natural" pairs (source columns 2m, 2m+1) with the 14-bit coefficients
+//                  split into an unsigned low and a signed high byte plane.  For palindromic
+//                  tables mirrored pairs are first added as packed 16-bit halves (one IADD for
+//                  two taps), which halves the dp2a count.  One rounding shift, saturating pack,
+//                  8-byte coalesced store.
+//  borders         Lanczos border rows use masked coefficient words + the reference's truncating
+//                  division in the same dp4a structure; border columns (<= 6 per row) are
+//                  recomputed by a scalar loop from the generic tables.
+// All arithmetic is integer and order independent => bit-exact with the reference.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+__device__ __forceinline__ int dp4a_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ int dp2a_lo_uu(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+__device__ __forceinline__ int dp2a_hi_us(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+// d = (sat_u8(hi) << 8) | sat_u8(lo) | (upper << 16)
+__device__ __forceinline__ uint32_t packSatU8(int hi, int lo, uint32_t upper)
+{
+    uint32_t d;
+    asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(hi), "r"(lo), "r"(upper));
+    return d;
+}
+
+// physical 32-bit word index inside a 128-word W row: 16-byte chunks are XOR-swizzled so that
+// both the 8-byte column writes and the 32-byte-strided 16-byte reads are bank-conflict free
+__device__ __forceinline__ int swzWord(int word)
+{
+    const int chunk = word >> 2;
+    return ((chunk ^ ((chunk >> 3) & 1)) << 2) | (word & 3);
+}
+
+constexpr int kHalfTileW = 120;   // destination columns per tile
+constexpr int kHalfRowWords = 128;  // W row: 256 u16 = 128 words
+constexpr int kHalfMaxRows = 64;
+
+// Vertical pass of one strip (see resizeHalfKernel).  EDGE = the strip touches the top/bottom of
+// the image: source row indices are clamped and Lanczos border rows (masked coefficient words +
+// truncating division) may occur.  The interior version carries none of that code.
+template <int NG, bool EDGE>
+__device__ __forceinline__ void halfVerticalStrip(const HalfArgs &a, const uint8_t *__restrict__ colPtr, bool colOk,
+                                                  uint32_t *__restrict__ wout, int ty0, int k0, int k1)
+{
+    const int B = a.workBias;
+    const int kg0 = ty0 >> 1;  // global index of the tile's first row pair (ty0 is even)
+    const int SHm1 = a.SH - 1;
+    const long long pitch = a.srcPitch;
+    uint32_t raw[4];
+    int g = kg0 + k0 + a.qmin;                                   // next group to fetch
+    const uint8_t *gp = colPtr + (long long)(4 * g) * pitch;     // its first row (interior strips only)
+
+    auto fetch = [&]() {  // issue the loads of source rows 4g .. 4g+3, then advance to the next group
+        if (EDGE) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int row = min(max(4 * g + j, 0), SHm1);
+                raw[j] = colOk ? __ldg(reinterpret_cast<const uint32_t *>(colPtr + (long long)row * pitch)) : 0u;
+            }
+        } else {
+            const uint8_t *p1 = gp + pitch;
+            raw[0] = __ldg(reinterpret_cast<const uint32_t *>(gp));
+            raw[1] = __ldg(reinterpret_cast<const uint32_t *>(p1));
+            raw[2] = __ldg(reinterpret_cast<const uint32_t *>(gp + 2 * pitch));
+            raw[3] = __ldg(reinterpret_cast<const uint32_t *>(p1 + 2 * pitch));
+            gp += 4 * pitch;
+        }
+        ++g;
+    };
+    auto transposed = [&]() -> uint4 {  // .x/.y/.z/.w = four vertical bytes of column 0/1/2/3
+        const uint32_t t0 = prmt(raw[0], raw[1], 0x5140), t1 = prmt(raw[0], raw[1], 0x7362);
+        const uint32_t t2 = prmt(raw[2], raw[3], 0x5140), t3 = prmt(raw[2], raw[3], 0x7362);
+        uint4 c;
+        c.x = prmt(t0, t2, 0x5410);
+        c.y = prmt(t0, t2, 0x7632);
+        c.z = prmt(t1, t3, 0x5410);
+        c.w = prmt(t1, t3, 0x7632);
+        return c;
+    };
+
+    uint4 win[NG];
+#pragma unroll
+    for (int j = 0; j < NG - 1; ++j) {
+        fetch();
+        win[j] = transposed();
+    }
+    fetch();
+
+    for (int k = k0; k < k1; k += NG) {
+#pragma unroll
+        for (int s = 0; s < NG; ++s) {
+            if (s == 0 || k + s < k1) {
+                win[(s + NG - 1) % NG] = transposed();
+                fetch();  // prefetch the next pair's newest group (overshoots by one group at the strip end)
+#pragma unroll
+                for (int par = 0; par < 2; ++par) {
+                    const int rl = 2 * (k + s) + par;  // local destination row
+                    uint32_t c0 = a.cwY[par][0], c1 = NG > 1 ? a.cwY[par][1] : 0u, c2 = NG > 2 ? a.cwY[par][2] : 0u;
+                    int deno = 0;
+                    if (EDGE) {
+                        const int y = ty0 + rl;
+                        if (y < a.DH && (y < a.mbY || y >= a.meY)) {
+                            const int row = __ldg(a.rowY + y);
+                            deno = __ldg(a.denoY + row);
+                            c0 = __ldg(a.borderY + row * 3);
+                            c1 = __ldg(a.borderY + row * 3 + 1);
+                            c2 = __ldg(a.borderY + row * 3 + 2);
+                        }
+                    }
+                    const int init = (EDGE && deno) ? 0 : B;
+                    int v0 = init, v1 = init, v2 = init, v3 = init;
+                    {
+                        const uint4 q = win[s % NG];
+                        v0 = dp4a_us(q.x, c0, v0);
+                        v1 = dp4a_us(q.y, c0, v1);
+                        v2 = dp4a_us(q.z, c0, v2);
+                        v3 = dp4a_us(q.w, c0, v3);
+                    }
+                    if (NG > 1) {
+                        const uint4 q = win[(s + 1) % NG];
+                        v0 = dp4a_us(q.x, c1, v0);
+                        v1 = dp4a_us(q.y, c1, v1);
+                        v2 = dp4a_us(q.z, c1, v2);
+                        v3 = dp4a_us(q.w, c1, v3);
+                    }
+                    if (NG > 2) {
+                        const uint4 q = win[(s + 2) % NG];
+                        v0 = dp4a_us(q.x, c2, v0);
+                        v1 = dp4a_us(q.y, c2, v1);
+                        v2 = dp4a_us(q.z, c2, v2);
+                        v3 = dp4a_us(q.w, c2, v3);
+                    }
+                    if (EDGE && deno) {
+                        // resizeYborder: int16 numerator * 64 / denominator, C division
+                        v0 = (int)(short)(((int)(short)v0 * 64) / deno) + B;
+                        v1 = (int)(short)(((int)(short)v1 * 64) / deno) + B;
+                        v2 = (int)(short)(((int)(short)v2 * 64) / deno) + B;
+                        v3 = (int)(short)(((int)(short)v3 * 64) / deno) + B;
+                    }
+                    uint2 o;
+                    o.x = prmt((uint32_t)v0, (uint32_t)v1, 0x5410);
+                    o.y = prmt((uint32_t)v2, (uint32_t)v3, 0x5410);
+                    *reinterpret_cast<uint2 *>(wout + rl * kHalfRowWords) = o;
+                }
+            }
+        }
+    }
+}
+
+// Border columns of a tile (Lanczos: at most N/2 per side), recomputed after the main pass by
+// the whole CTA, one (row, column) item per thread so that no warp diverges into a scalar loop:
+// masked taps and the truncating division of resizeXborder (reference ..._Generic.cpp:539-574)
+// from the generic tables.  [c0, c1) are the tile's border columns.
+__device__ __noinline__ void halfBorderColumns(const HalfArgs &a, const uint32_t *W, uint8_t *dstTile, int xs0,
+                                               int tx0, int c0, int c1, int th)
+{
+    const int nb = c1 - c0;
+    for (int item = threadIdx.x; item < nb * th; item += blockDim.x) {
+        const int r = item / nb;
+        const int d = c0 + (item - r * nb);
+        const uint32_t *wr = W + r * kHalfRowWords;
+        const int fx = __ldg(a.firstX + d);
+        const int rx = __ldg(a.rowX + d);
+        const int deno = __ldg(a.denoX + rx);
+        int nume = 0;
+        for (int i = 0; i < a.NX; ++i) {
+            const int c = __ldg(a.coefX + rx * a.NX + i);
+            const int e = min(max(fx + i, 0), a.SW - 1) - xs0;
+            const uint32_t word = wr[swzWord(e >> 1)];
+            const int val = (int)((e & 1) ? (word >> 16) : (word & 0xffffu)) - a.workBias;
+            nume += c * val;
+        }
+        const int v = (int)(short)((nume + (1 << 19)) / (deno * 64));
+        dstTile[(long long)r * a.dstPitch + (d - tx0)] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+__device__ __noinline__ void halfStoreBytes(uint8_t *out, uint2 o, int count)
+{
+    for (int p = 0; p < count; ++p) out[p] = (uint8_t)(((p < 4 ? o.x : o.y) >> (8 * (p & 3))) & 0xffu);
+}
+
+template <int NG, int NWX, bool SYM>
+__global__ void __launch_bounds__(256, 3) resizeHalfKernel(const __grid_constant__ HalfArgs a)
+{
+    __shared__ __align__(16) uint32_t W[kHalfMaxRows * kHalfRowWords];
+
+    const int tx0 = blockIdx.x * kHalfTileW;
+    const int ty0 = blockIdx.y * a.tileRows;
+    const int th = min(a.tileRows, a.DH - ty0);
+    const uint8_t *__restrict__ src = a.src + (long long)blockIdx.z * a.srcFrameStride;
+    uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
+    const int xs0 = 2 * tx0 - 8;  // source column of W element 0 (multiple of 4)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ================= vertical pass =================
+    {
+        const int cw = ((warp & 1) << 5) | lane;  // column word 0..63
+        const int strip = warp >> 1;              // 0..3
+        const int pairs = (th + 1) >> 1;
+        const int k0 = (strip * pairs) >> 2, k1 = ((strip + 1) * pairs) >> 2;
+        const int col = xs0 + 4 * cw;
+        const bool colOk = (col >= 0) && (col < a.SW);
+        const uint8_t *colPtr = src + (colOk ? col : 0);
+        uint32_t *wout = W + swzWord(2 * cw);
+        if (k0 < k1) {
+            // source rows this strip touches, including the one-group prefetch overshoot
+            const int gFirst = (ty0 >> 1) + k0 + a.qmin;
+            const int gLast = (ty0 >> 1) + k1 + a.qmin + NG - 1;
+            const bool edge = (gFirst < 0) || (4 * gLast + 3 >= a.SH) || (ty0 + 2 * k0 < a.mbY) || (ty0 + 2 * k1 > a.meY);
+            if (edge || !colOk)
+                halfVerticalStrip<NG, true>(a, colPtr, colOk, wout, ty0, k0, k1);
+            else
+                halfVerticalStrip<NG, false>(a, colPtr, true, wout, ty0, k0, k1);
+        }
+    }
+    __syncthreads();
+
+    // ================= horizontal pass =================
+    {
+        const int half = lane >> 4, l = lane & 15;
+        const int d0 = tx0 + 8 * l;  // first destination column of this thread
+        if (l < 15 && d0 < a.DW) {
+            int pc[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) pc[j] = swzWord(4 * (2 * l + j));
+            constexpr int kBase = 4 - (NWX - 1) / 2;  // pair word of tap pair 0 for pixel 0 (wa + 4)
+            const bool vecStore = a.dstVec && (d0 + 8 <= a.DW);
+            uint8_t *out = dst + (long long)(ty0 + 2 * warp + half) * a.dstPitch + d0;
+            const long long outStep = 2 * a.dstPitch;
+            for (int r = 2 * warp + half; r < th; r += 16, out += 8 * outStep) {
+                const uint32_t *wr = W + r * kHalfRowWords;
+                uint32_t n[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(wr + pc[j]);
+                    n[4 * j] = q.x;
+                    n[4 * j + 1] = q.y;
+                    n[4 * j + 2] = q.z;
+                    n[4 * j + 3] = q.w;
+                }
+                int v[8];
+                if (SYM) {
+                    constexpr int m = NWX / 2;
+                    // swapped halves of the words that serve as mirror partners
+                    uint32_t sw[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) sw[i] = (i >= kBase + m + 1 && i <= kBase + NWX - 2 + 7) ? prmt(n[i], n[i], 0x1032) : 0u;
+                    // mirrored pairs are added as packed u16 halves (no carry can cross: every
+                    // half-sum fits 16 bits).  The third addend is a kernel argument that is always
+                    // 0: a three-input add can only be an IADD3, which keeps these adds off the
+                    // multiplier pipe that the dp2a/dp4a instructions saturate.
+                    uint32_t sum[8][m > 1 ? m - 1 : 1];
+#pragma unroll
+                    for (int j = 1; j < m; ++j)
+#pragma unroll
+                        for (int p = 0; p < 8; ++p) sum[p][j - 1] = n[kBase + p + j] + sw[kBase + p + NWX - 1 - j] + a.zero;
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        const uint32_t ctr = n[kBase + p + m];
+                        const uint32_t ends = prmt(n[kBase + p], n[kBase + p + NWX - 1], 0x3254);
+                        // low byte plane first; the high plane continues from (low >> 8):
+                        // floor((lo + 256 hi) / 2^20) == floor((floor(lo / 256) + hi) / 2^12)
+                        int acc = a.accInit;
+#pragma unroll
+                        for (int j = 1; j < m; ++j) acc = dp2a_lo_uu(sum[p][j - 1], a.cwXs[j - 1], acc);
+                        acc = dp2a_lo_uu(ctr, a.cwXs[m - 1], acc);
+                        acc = dp2a_lo_uu(ends, a.cwXs[m], acc);
+                        acc >>= 8;
+#pragma unroll
+                        for (int j = 1; j < m; ++j) acc = dp2a_hi_us(sum[p][j - 1], a.cwXs[j - 1], acc);
+                        acc = dp2a_hi_us(ctr, a.cwXs[m - 1], acc);
+                        acc = dp2a_hi_us(ends, a.cwXs[m], acc);
+                        v[p] = acc >> 12;
+                    }
+                } else {
+#pragma unroll
+                    for (int p = 0; p < 8; ++p) {
+                        int acc = a.accInit;
+#pragma unroll
+                        for (int j = 0; j < NWX; ++j) acc = dp2a_lo_uu(n[kBase + p + j], a.cwX[j], acc);
+                        acc >>= 8;
+#pragma unroll
+                        for (int j = 0; j < NWX; ++j) acc = dp2a_hi_us(n[kBase + p + j], a.cwX[j], acc);
+                        v[p] = acc >> 12;
+                    }
+                }
+                uint2 o;
+                o.x = packSatU8(v[1], v[0], packSatU8(v[3], v[2], 0u));
+                o.y = packSatU8(v[5], v[4], packSatU8(v[7], v[6], 0u));
+                if (vecStore)
+                    *reinterpret_cast<uint2 *>(out) = o;
+                else
+                    halfStoreBytes(out, o, min(8, a.DW - d0));
+            }
+        }
+    }
+    // ================= border columns =================
+    {
+        const int txEnd = min(tx0 + kHalfTileW, a.DW);
+        const bool left = tx0 < a.mbX, right = txEnd > a.meX;
+        if (left || right) {
+            __syncthreads();  // the main stores of these pixels come first (block-scope ordering)
+            uint8_t *dstTile = dst + (long long)ty0 * a.dstPitch + tx0;
+            if (left) halfBorderColumns(a, W, dstTile, xs0, tx0, tx0, min(a.mbX, txEnd), th);
+            if (right) halfBorderColumns(a, W, dstTile, xs0, tx0, max(a.meX, max(tx0, a.mbX)), txEnd, th);
+        }
+    }
+}
+
+template <int NG, int NWX, bool SYM>
+cudaError_t launchHalfT(const HalfArgs &a, cudaStream_t stream)
+{
+    const int tilesX = (a.DW + kHalfTileW - 1) / kHalfTileW;
+    const int tilesY = (a.DH + a.tileRows - 1) / a.tileRows;
+    for (int f0 = 0; f0 < a.nFrames; f0 += 65535) {
+        HalfArgs b = a;
+        b.nFrames = std::min(65535, a.nFrames - f0);
+        b.src = a.src + (long long)f0 * a.srcFrameStride;
+        b.dst = a.dst + (long long)f0 * a.dstFrameStride;
+        dim3 grid(tilesX, tilesY, b.nFrames);
+        resizeHalfKernel<NG, NWX, SYM><<<grid, 256, 0, stream>>>(b);
+        g_launches.fetch_add(1);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
 }  // namespace
 
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D)
@@ -164,6 +531,24 @@ cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_
         if (e != cudaSuccess) return e;
     }
     return cudaSuccess;
+}
+
+cudaError_t launchHalf(const HalfArgs &a, cudaStream_t stream)
+{
+#define IQO_HALF_CASE(G, NW)                                                           \
+    if (a.NG == G && a.NWX == NW)                                                      \
+        return a.symmetric ? launchHalfT<G, NW, true>(a, stream) : launchHalfT<G, NW, false>(a, stream);
+    IQO_HALF_CASE(3, 7)
+    IQO_HALF_CASE(3, 5)
+    IQO_HALF_CASE(2, 3)
+    IQO_HALF_CASE(2, 5)
+    IQO_HALF_CASE(2, 7)
+    IQO_HALF_CASE(1, 3)
+    IQO_HALF_CASE(3, 3)
+    IQO_HALF_CASE(1, 5)
+    IQO_HALF_CASE(1, 7)
+#undef IQO_HALF_CASE
+    return cudaErrorInvalidValue;
 }
 
 unsigned long long launchCount()

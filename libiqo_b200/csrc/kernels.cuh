@@ -39,6 +39,36 @@ struct GenericGeom {
     size_t smemBytes;
 };
 
+// Arguments of the specialised 2:1 x 2:1 single-phase Lanczos kernel (see plan.hpp HalfPlan).
+struct HalfArgs {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long srcPitch, dstPitch, srcFrameStride, dstFrameStride;
+    int SW, SH, DW, DH;
+    int nFrames;
+    int tileRows;             // destination rows per tile (even, <= 64)
+    int dstVec;               // destination rows may be written with 8-byte stores
+    // vertical
+    int qmin, NG;
+    uint32_t cwY[2][3];
+    const uint32_t *borderY;  // [numRowsY][3]
+    const int32_t *rowY;      // [DH]
+    const int32_t *denoY;     // [numRowsY]
+    int mbY, meY;
+    int workBias;
+    // horizontal
+    int NWX, symmetric;
+    uint32_t cwX[7];
+    uint32_t cwXs[4];
+    int accInit;
+    int mbX, meX;
+    const int32_t *firstX, *rowX, *coefX, *denoX;  // generic tables, used for the border columns
+    int NX;
+    uint32_t zero;            // always 0 (see the pair sums in resizeHalfKernel)
+};
+
+cudaError_t launchHalf(const HalfArgs &a, cudaStream_t stream);
+
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D);
 cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_t stream);
 cudaError_t initKernels();  // sets function attributes once per device

@@ -339,3 +339,135 @@ int buildPlan(Plan &p, int kind, unsigned degree, size_t srcW, size_t srcH, size
 }
 
 }  // namespace iqo_b200
+
+// ---------------------------------------------------------------------------------------------
+// Specialised plan for 2:1 / 2:1 single-phase Lanczos (kernels.cu: resizeHalfKernel)
+// ---------------------------------------------------------------------------------------------
+namespace iqo_b200 {
+
+namespace {
+
+int floorDivI(int a, int b)
+{
+    int q = a / b;
+    return (a % b != 0 && ((a < 0) != (b < 0))) ? q - 1 : q;
+}
+
+// coefficient c (|c| <= 16384) as unsigned low byte + signed high byte: c = hi*256 + lo
+void splitPlanes(int c, uint32_t &lo, uint32_t &hi)
+{
+    int h = floorDivI(c, 256);
+    lo = uint32_t(c - h * 256) & 0xffu;
+    hi = uint32_t(h) & 0xffu;
+}
+
+uint32_t pairWord(int cLowHalf, int cHighHalf)
+{
+    uint32_t l0, h0, l1, h1;
+    splitPlanes(cLowHalf, l0, h0);
+    splitPlanes(cHighHalf, l1, h1);
+    return l0 | (l1 << 8) | (h0 << 16) | (h1 << 24);
+}
+
+}  // namespace
+
+void buildHalfPlan(const Plan &p, HalfPlan &h)
+{
+    h.eligible = false;
+    h.why.clear();
+    const AxisPlan &X = p.x, &Y = p.y;
+    if (p.kind != kLanczos) { h.why = "not Lanczos"; return; }
+    if (X.rD != 1 || X.rS != 2 || Y.rD != 1 || Y.rS != 2) { h.why = "not 2:1 on both axes"; return; }
+    if (X.S % 4 != 0) { h.why = "source width not a multiple of 4"; return; }
+    const int NY = Y.N, NX = X.N;
+    if (NX > 12 || (NX & 1) || ((NX / 2) & 1)) { h.why = "horizontal kernel longer than 12 taps or of odd half-length"; return; }
+    if (Y.coefMin < -128 || Y.coefMax > 127) { h.why = "vertical coefficients do not fit int8"; return; }
+
+    // ---- vertical: trim zero taps of the main phase, place taps into 4-row groups ----
+    const int32_t *cy = &Y.coef[0];
+    int lead = 0, trail = 0;
+    while (lead < NY - 1 && cy[lead] == 0) ++lead;
+    while (trail < NY - 1 - lead && cy[NY - 1 - trail] == 0) ++trail;
+    const int cy0 = 1 - NY / 2 + lead;        // first non-zero tap of row y sits on source row 2y + cy0
+    const int NYt = NY - lead - trail;
+    int qlo = 1 << 30, qhi = -(1 << 30);
+    for (int par = 0; par < 2; ++par) {
+        qlo = std::min(qlo, floorDivI(2 * par + cy0, 4));
+        qhi = std::max(qhi, floorDivI(2 * par + cy0 + NYt - 1, 4));
+    }
+    h.qmin = qlo;
+    h.NG = qhi - qlo + 1;
+    if (h.NG > 3) { h.why = "vertical kernel spans more than three 4-row groups"; return; }
+    // packed words of every coefficient row; a row r >= 1 belongs to one destination row y
+    std::vector<int> rowOwner(size_t(Y.numRows), -1);
+    for (int64_t y = 0; y < Y.D; ++y)
+        if (Y.row[y] != 0) rowOwner[size_t(Y.row[y])] = int(y);
+    h.borderY.assign(size_t(Y.numRows) * 3, 0);
+    for (int par = 0; par < 2; ++par)
+        for (int g = 0; g < 3; ++g) h.cwY[par][g] = 0;
+    for (int r = 0; r < Y.numRows; ++r) {
+        for (int par = 0; par < 2; ++par) {
+            if (r > 0 && (rowOwner[size_t(r)] & 1) != par) continue;
+            uint32_t w[3] = {0, 0, 0};
+            for (int i = 0; i < NY; ++i) {
+                const int c = Y.coef[size_t(r) * NY + i];
+                if (c == 0) continue;
+                const int pos = 2 * par + (1 - NY / 2 + i) - 4 * h.qmin;  // byte position inside the NG groups
+                if (pos < 0 || pos >= 4 * h.NG) { h.why = "internal: tap outside the group window"; return; }
+                w[pos >> 2] |= (uint32_t(c) & 0xffu) << (8 * (pos & 3));
+            }
+            for (int g = 0; g < 3; ++g) {
+                if (r == 0) h.cwY[par][g] = w[g];
+                else h.borderY[size_t(r) * 3 + g] = w[g];
+            }
+        }
+    }
+    // range of the intermediate over all rows (border rows are rescaled by 64/deno)
+    long long wmin = 0, wmax = 0;
+    for (int r = 0; r < Y.numRows; ++r) {
+        long long pos = 0, neg = 0;
+        for (int i = 0; i < NY; ++i) {
+            const int c = Y.coef[size_t(r) * NY + i];
+            (c > 0 ? pos : neg) += c;
+        }
+        long long lo = 255 * neg, hi = 255 * pos;
+        if (lo < -32768 || hi > 32767) { h.why = "vertical sum may wrap int16"; return; }
+        const int den = Y.deno[size_t(r)];
+        if (den != 0) {
+            if (den < 0) { h.why = "negative border denominator"; return; }
+            lo = lo * 64 / den - 1;
+            hi = hi * 64 / den + 1;
+        }
+        wmin = std::min(wmin, lo);
+        wmax = std::max(wmax, hi);
+    }
+    h.workBias = int(-wmin);
+    if (wmax + h.workBias > 32767) { h.why = "intermediate range too wide for pair sums"; return; }
+
+    // ---- horizontal ----
+    const int32_t *cx = &X.coef[0];
+    const int cx0 = 1 - NX / 2;               // odd
+    h.wa = (cx0 - 1) / 2;                     // exact: cx0 - 1 is even and negative
+    h.NWX = NX / 2 + 1;
+    for (int i = 0; i < 7; ++i) h.cwX[i] = 0;
+    for (int i = 0; i < h.NWX; ++i) {
+        const int ta = 2 * i - 1, tb = 2 * i;  // taps in the low / high half of pair word i
+        h.cwX[i] = pairWord(ta >= 0 ? cx[ta] : 0, tb < NX ? cx[tb] : 0);
+    }
+    h.symmetric = true;
+    for (int i = 0; i < NX; ++i)
+        if (cx[i] != cx[NX - 1 - i]) h.symmetric = false;
+    for (int i = 0; i < 4; ++i) h.cwXs[i] = 0;
+    if (h.symmetric) {
+        const int m = h.NWX / 2;               // centre pair word
+        for (int j = 1; j < m; ++j) h.cwXs[j - 1] = pairWord(cx[2 * j - 1], cx[2 * j]);
+        h.cwXs[m - 1] = pairWord(cx[2 * m - 1], cx[2 * m]);
+        h.cwXs[m] = pairWord(cx[NX - 1], cx[0]);  // low half: last tap, high half: first tap
+    }
+    long long sumX = 0;
+    for (int i = 0; i < NX; ++i) sumX += cx[i];
+    h.accInit = int((1ll << (p.shift - 1)) - (long long)h.workBias * sumX);
+    h.eligible = true;
+}
+
+}  // namespace iqo_b200

@@ -67,3 +67,29 @@ int lanczosNumCoefs(int degree, uint64_t rS, uint64_t rD, uint64_t pxScale);
 int areaNumCoefs(uint64_t rS, uint64_t rD);
 
 }  // namespace iqo_b200
+
+namespace iqo_b200 {
+
+// Parameters of the specialised kernel for 2:1 down-sampling on both axes with single-phase
+// Lanczos tables (BASELINE configs 3 and 4).  See kernels.cu (resizeHalfKernel) for the layout.
+struct HalfPlan {
+    bool eligible;
+    std::string why;          // reason when not eligible
+    // vertical pass: u8 x s8 dp4a over groups of 4 source rows aligned to multiples of 4
+    int qmin;                 // destination row pair k uses source-row groups k+qmin .. k+qmin+NG-1
+    int NG;                   // 1..3
+    uint32_t cwY[2][3];       // [row parity][group] packed s8 coefficients of the main phase
+    std::vector<uint32_t> borderY;  // [numRowsY][3] packed words of every coefficient row (row 0 = main, unused)
+    int workBias;             // added to every intermediate so that it is a non-negative u16
+    // horizontal pass: dp2a over "natural" 16-bit pairs (columns 2m, 2m+1)
+    int wa;                   // destination column d uses pair words d+wa .. d+wa+NWX-1
+    int NWX;                  // N/2 + 1  (<= 7)
+    bool symmetric;           // palindromic table: mirrored pairs are pre-added
+    uint32_t cwX[7];          // general form, per pair word: bytes (lo(c_a), lo(c_b), hi(c_a), hi(c_b))
+    uint32_t cwXs[4];         // symmetric form: [0..m-2] summed pairs, [m-1] centre, [m] the two end taps
+    int accInit;              // rounding constant minus the bias contribution
+};
+
+void buildHalfPlan(const Plan &plan, HalfPlan &h);
+
+}  // namespace iqo_b200

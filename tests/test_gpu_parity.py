@@ -204,3 +204,49 @@ def test_errors():
             r.resize(64, 0, 32, dst)     # NULL
         r.resize(64, src, 32, dst)
         assert iqo.launch_count() > 0
+
+
+HALF_CASES = [
+    # (degree, pxScale, srcW, srcH, srcPad, dstPad, expected kernel)
+    (3, 1, 1920, 1080, 0, 0, "half_sym"),     # cfg4
+    (2, 1, 3840, 2160, 0, 0, "half_sym"),     # cfg3 luma
+    (2, 2, 1920, 1080, 0, 0, "half"),         # cfg3 chroma (asymmetric 4-tap table)
+    (3, 1, 480, 272, 0, 0, "half_sym"),       # several tiles, last tile row partial
+    (3, 1, 488, 250, 4, 0, "half_sym"),       # width not a multiple of the tile, odd dstH, padded src
+    (2, 1, 264, 100, 8, 3, "half_sym"),       # unaligned dst stride -> byte stores
+    (1, 1, 256, 64, 0, 0, "half_sym"),
+    (3, 2, 960, 540, 0, 0, "generic"),        # negative border denominator: specialised kernel declines
+    (2, 1, 64, 32, 0, 0, "half_sym"),         # image smaller than a tile
+    (3, 1, 28, 26, 0, 0, "half_sym"),
+]
+
+
+@pytest.mark.parametrize("case", HALF_CASES)
+def test_half_kernel(case):
+    deg, px, sw, sh, spad, dpad, kname = case
+    dw, dh = sw // 2, sh // 2
+    src = lcg_image(sh, sw + spad, seed=11)
+    rc, want = oracle_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+    assert rc == 0
+    got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+    assert kernel == kname
+    assert iqo.plan_kernel(LANCZOS, deg, sw, sh, dw, dh, px)[0] == kname
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, (len(bad), bad[:8].tolist())
+
+
+def test_half_kernel_extreme_values():
+    # all-255 / all-0 / checkerboards maximise the intermediate range (bias and pair-sum headroom)
+    sw, sh = 480, 272
+    yy, xx = np.mgrid[0:sh, 0:sw]
+    for name, src in (("white", np.full((sh, sw), 255, np.uint8)), ("black", np.zeros((sh, sw), np.uint8)),
+                      ("checker1", (((yy + xx) & 1) * 255).astype(np.uint8)),
+                      ("checker2", ((((yy >> 1) + (xx >> 1)) & 1) * 255).astype(np.uint8)),
+                      ("vstripes", ((xx & 1) * 255).astype(np.uint8)), ("hstripes", ((yy & 1) * 255).astype(np.uint8)),
+                      ("vstripes2", (((xx >> 1) & 1) * 255).astype(np.uint8)),
+                      ("hstripes2", (((yy >> 1) & 1) * 255).astype(np.uint8))):
+        for deg, px in ((3, 1), (2, 1), (2, 2), (1, 1)):
+            rc, want = oracle_resize(LANCZOS, src, sw // 2, sh // 2, deg, px)
+            got, kernel = gpu_resize(LANCZOS, src, sw // 2, sh // 2, deg, px)
+            assert kernel.startswith("half")
+            assert np.array_equal(got, want), (name, deg, px)

@@ -56,7 +56,10 @@ enum {
 /* kernel selection, for tests and benchmarks (iqo_cuda_set_path) */
 enum {
     IQO_CUDA_PATH_AUTO = 0,    /* fastest eligible kernel                                          */
-    IQO_CUDA_PATH_GENERIC = 1  /* the general tile kernel (any stride, ratio, kind)                */
+    IQO_CUDA_PATH_GENERIC = 1, /* the general tile kernel (any stride, ratio, kind)                */
+    IQO_CUDA_PATH_NO_TMA = 2   /* like AUTO, but specialised kernels read the source with plain
+                                  global loads instead of TMA (what AUTO itself does when the
+                                  source pitch or base is not 16-byte aligned)                     */
 };
 
 /* Replaces: I{Lanczos,Area,Linear}ResizerImpl::init (reference src/IQOLanczosResizerImpl.hpp:17-22,

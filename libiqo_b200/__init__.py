@@ -18,10 +18,10 @@ import ctypes as C
 import os
 
 __all__ = ["LanczosResizer", "AreaResizer", "LinearResizer", "IqoCudaError", "lib", "build",
-           "LANCZOS", "AREA", "LINEAR", "PATH_AUTO", "PATH_GENERIC", "exported_symbols"]
+           "LANCZOS", "AREA", "LINEAR", "PATH_AUTO", "PATH_GENERIC", "PATH_NO_TMA", "exported_symbols"]
 
 LANCZOS, AREA, LINEAR = 0, 1, 2
-PATH_AUTO, PATH_GENERIC = 0, 1
+PATH_AUTO, PATH_GENERIC, PATH_NO_TMA = 0, 1, 2
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libiqo_cuda.so")

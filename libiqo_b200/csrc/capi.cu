@@ -59,6 +59,26 @@ struct AxisTables {
     AxisTables() : first(0), row(0), coef(0), deno(0) {}
 };
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+EncodeTiledFn encodeTiled()
+{
+    static EncodeTiledFn fn = []() -> EncodeTiledFn {
+        void *p = 0;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+            q != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return 0;
+        }
+        return reinterpret_cast<EncodeTiledFn>(p);
+    }();
+    return fn;
+}
+
 size_t alignUp(size_t v, size_t a)
 {
     return (v + a - 1) / a * a;
@@ -72,7 +92,9 @@ struct iqo_cuda_resizer {
     AxisTables tx, ty;
     GenericGeom geom;
     HalfPlan half;
-    uint32_t *dBorderY;
+    uint32_t *dBorderY, *dMagicY;
+    int32_t *dBorderX;
+    bool useTma;
     int path;
     const char *lastKernel;
     cudaStream_t stream[2];
@@ -82,7 +104,7 @@ struct iqo_cuda_resizer {
     size_t srcPitch, dstPitch;  // device pitches of the staging frames
     size_t slotFrames;
 
-    iqo_cuda_resizer() : device(0), dBorderY(0), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
+    iqo_cuda_resizer() : device(0), dBorderY(0), dMagicY(0), dBorderX(0), useTma(true), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
     {
         for (int i = 0; i < 2; ++i) {
             stream[i] = 0;
@@ -196,14 +218,36 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         h.accInit = hp.accInit;
         h.mbX = int(r->plan.x.mainBegin);
         h.meX = int(r->plan.x.mainEnd);
-        h.firstX = r->tx.first;
-        h.rowX = r->tx.row;
-        h.coefX = r->tx.coef;
-        h.denoX = r->tx.deno;
+        h.magicY = r->dMagicY;
+        h.borderX = r->dBorderX;
         h.NX = r->plan.x.N;
         h.zero = 0;
-        r->lastKernel = hp.symmetric ? "half_sym" : "half";
-        CUDA_TRY(launchHalf(h, stream));
+        const int boxRows = 4 * (h.tileRows / 2 + hp.NG - 1);
+        const bool tmaOk = r->useTma && encodeTiled() != 0 && boxRows <= halfSourceRowsMax() &&
+                           ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 && (nFrames == 1 || srcFrameStride % 16 == 0);
+        for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
+            const size_t nf = std::min<size_t>(65535, nFrames - f0);
+            h.src = src + f0 * srcFrameStride;
+            h.dst = dst + f0 * dstFrameStride;
+            h.nFrames = int(nf);
+            CUtensorMap tmap;
+            bool tma = tmaOk;
+            if (tma) {
+                // 3-D tensor (x, y, frame) of bytes; box = 256 columns x boxRows rows x 1 frame.
+                // Out-of-image coordinates (negative too) are filled with zeros by the hardware.
+                const cuuint64_t dims[3] = {cuuint64_t(h.SW), cuuint64_t(h.SH), cuuint64_t(nf)};
+                const cuuint64_t strides[2] = {cuuint64_t(srcSt), cuuint64_t(nf > 1 ? srcFrameStride : srcSt * size_t(h.SH))};
+                const cuuint32_t box[3] = {256, cuuint32_t(boxRows), 1};
+                const cuuint32_t estr[3] = {1, 1, 1};
+                CUresult cr = encodeTiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<uint8_t *>(h.src), dims, strides,
+                                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (cr != CUDA_SUCCESS) tma = false;  // e.g. a stride the descriptor cannot express
+            }
+            h.tileShift = tma ? 4 : 0;
+            r->lastKernel = tma ? (hp.symmetric ? "half_sym_tma" : "half_tma") : (hp.symmetric ? "half_sym" : "half");
+            CUDA_TRY(launchHalf(h, tma ? &tmap : 0, boxRows, stream));
+        }
         return IQO_CUDA_OK;
     }
     r->lastKernel = "generic";
@@ -341,9 +385,13 @@ int iqo_cuda_create_on(iqo_cuda_resizer **out, int device, int kind, unsigned de
     buildHalfPlan(r->plan, r->half);
     if (r->half.eligible) {
         DeviceGuard g2(device);
-        const size_t bytes = r->half.borderY.size() * sizeof(uint32_t);
-        if (cudaMalloc(&r->dBorderY, bytes) != cudaSuccess ||
-            cudaMemcpy(r->dBorderY, r->half.borderY.data(), bytes, cudaMemcpyHostToDevice) != cudaSuccess) {
+        const HalfPlan &hp = r->half;
+        const size_t b0 = hp.borderY.size() * 4, b1 = hp.magicY.size() * 4, b2 = std::max<size_t>(4, hp.borderX.size() * 4);
+        if (cudaMalloc(&r->dBorderY, b0) != cudaSuccess || cudaMalloc(&r->dMagicY, b1) != cudaSuccess ||
+            cudaMalloc(&r->dBorderX, b2) != cudaSuccess ||
+            cudaMemcpy(r->dBorderY, hp.borderY.data(), b0, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(r->dMagicY, hp.magicY.data(), b1, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(r->dBorderX, hp.borderX.data(), hp.borderX.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
             cudaGetLastError();
             r->half.eligible = false;
         }
@@ -385,6 +433,8 @@ void iqo_cuda_destroy(iqo_cuda_resizer *r)
     freeAxis(r->tx);
     freeAxis(r->ty);
     cudaFree(r->dBorderY);
+    cudaFree(r->dMagicY);
+    cudaFree(r->dBorderX);
     cudaGetLastError();
     delete r;
 }
@@ -400,8 +450,9 @@ int iqo_cuda_sync(iqo_cuda_resizer *r)
 
 int iqo_cuda_set_path(iqo_cuda_resizer *r, int path)
 {
-    if (!r || path < 0 || path > IQO_CUDA_PATH_GENERIC) return fail(IQO_CUDA_E_ARG, "bad path");
-    r->path = path;
+    if (!r || path < 0 || path > IQO_CUDA_PATH_NO_TMA) return fail(IQO_CUDA_E_ARG, "bad path");
+    r->useTma = (path != IQO_CUDA_PATH_NO_TMA);
+    r->path = (path == IQO_CUDA_PATH_GENERIC) ? IQO_CUDA_PATH_GENERIC : IQO_CUDA_PATH_AUTO;
     return IQO_CUDA_OK;
 }
 

@@ -184,31 +184,42 @@ __device__ __forceinline__ int swzWord(int word)
     return ((chunk ^ ((chunk >> 3) & 1)) << 2) | (word & 3);
 }
 
-constexpr int kHalfTileW = 120;   // destination columns per tile
+constexpr int kHalfTileW = 120;     // destination columns per tile
 constexpr int kHalfRowWords = 128;  // W row: 256 u16 = 128 words
-constexpr int kHalfMaxRows = 64;
+constexpr int kHalfMaxRows = 64;    // destination rows per tile (<=)
+constexpr int kHalfSrcRowBytes = 256;                                   // source window of a tile, bytes per row
+constexpr int kHalfSrcMaxRows = 4 * (kHalfMaxRows / 2 + 3);             // 140: groups of the tile + prefetch slack
+constexpr int kHalfTileBytes = kHalfSrcMaxRows * kHalfSrcRowBytes;      // 35840 (multiple of 128)
+constexpr int kHalfWBytes = kHalfMaxRows * kHalfRowWords * 4;           // 32768
 
-// Vertical pass of one strip (see resizeHalfKernel).  EDGE = the strip touches the top/bottom of
-// the image: source row indices are clamped and Lanczos border rows (masked coefficient words +
-// truncating division) may occur.  The interior version carries none of that code.
-template <int NG, bool EDGE>
-__device__ __forceinline__ void halfVerticalStrip(const HalfArgs &a, const uint8_t *__restrict__ colPtr, bool colOk,
+// Vertical pass of one strip (see resizeHalfKernel).
+//   SMEM  = the tile's source window was staged in shared memory by TMA (out-of-image rows and
+//           columns are zero filled by the hardware); otherwise rows are read from global memory.
+//   EDGE  = the strip may contain Lanczos border rows (masked coefficient words + truncating
+//           division) and, when reading global memory, needs its row indices clamped.
+// `base` points at this thread's 4-byte column word in row 0 of the tile (SMEM) or of the frame.
+template <int NG, bool EDGE, bool SMEM>
+__device__ __forceinline__ void halfVerticalStrip(const HalfArgs &a, const uint8_t *__restrict__ base,
                                                   uint32_t *__restrict__ wout, int ty0, int k0, int k1)
 {
     const int B = a.workBias;
-    const int kg0 = ty0 >> 1;  // global index of the tile's first row pair (ty0 is even)
     const int SHm1 = a.SH - 1;
-    const long long pitch = a.srcPitch;
+    const long long pitch = SMEM ? (long long)kHalfSrcRowBytes : a.srcPitch;
     uint32_t raw[4];
-    int g = kg0 + k0 + a.qmin;                                   // next group to fetch
-    const uint8_t *gp = colPtr + (long long)(4 * g) * pitch;     // its first row (interior strips only)
+    // SMEM: tile group j holds source rows 4(ty0/2 + qmin + j)...; global: absolute group index
+    int g = SMEM ? k0 : (ty0 >> 1) + k0 + a.qmin;
+    const uint8_t *gp = base + (long long)(4 * g) * pitch;
 
-    auto fetch = [&]() {  // issue the loads of source rows 4g .. 4g+3, then advance to the next group
-        if (EDGE) {
+    auto fetch = [&]() {  // issue the loads of the four rows of group g, then advance to the next group
+        if (SMEM) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) raw[j] = *reinterpret_cast<const uint32_t *>(gp + j * kHalfSrcRowBytes);
+            gp += 4 * kHalfSrcRowBytes;
+        } else if (EDGE) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int row = min(max(4 * g + j, 0), SHm1);
-                raw[j] = colOk ? __ldg(reinterpret_cast<const uint32_t *>(colPtr + (long long)row * pitch)) : 0u;
+                raw[j] = __ldg(reinterpret_cast<const uint32_t *>(base + (long long)row * pitch));
             }
         } else {
             const uint8_t *p1 = gp + pitch;
@@ -250,11 +261,13 @@ __device__ __forceinline__ void halfVerticalStrip(const HalfArgs &a, const uint8
                     const int rl = 2 * (k + s) + par;  // local destination row
                     uint32_t c0 = a.cwY[par][0], c1 = NG > 1 ? a.cwY[par][1] : 0u, c2 = NG > 2 ? a.cwY[par][2] : 0u;
                     int deno = 0;
+                    uint32_t magic = 0;
                     if (EDGE) {
                         const int y = ty0 + rl;
                         if (y < a.DH && (y < a.mbY || y >= a.meY)) {
                             const int row = __ldg(a.rowY + y);
                             deno = __ldg(a.denoY + row);
+                            magic = __ldg(a.magicY + row);
                             c0 = __ldg(a.borderY + row * 3);
                             c1 = __ldg(a.borderY + row * 3 + 1);
                             c2 = __ldg(a.borderY + row * 3 + 2);
@@ -284,11 +297,19 @@ __device__ __forceinline__ void halfVerticalStrip(const HalfArgs &a, const uint8
                         v3 = dp4a_us(q.w, c2, v3);
                     }
                     if (EDGE && deno) {
-                        // resizeYborder: int16 numerator * 64 / denominator, C division
-                        v0 = (int)(short)(((int)(short)v0 * 64) / deno) + B;
-                        v1 = (int)(short)(((int)(short)v1 * 64) / deno) + B;
-                        v2 = (int)(short)(((int)(short)v2 * 64) / deno) + B;
-                        v3 = (int)(short)(((int)(short)v3 * 64) / deno) + B;
+                        // resizeYborder: int16 numerator * 64 / denominator, C (truncating) division;
+                        // |numerator * 64| <= 2^21 and 1 <= deno <= 127, so floor(n / deno) is the
+                        // multiply-high by floor(2^32 / deno) + 1 (deno == 1: magic == 0, identity)
+                        auto bdiv = [&](int v) -> int {
+                            const int n = (int)(short)v * 64;
+                            const uint32_t m = (uint32_t)abs(n);
+                            const int q = magic ? (int)__umulhi(m, magic) : (int)m;
+                            return (int)(short)(n < 0 ? -q : q) + B;
+                        };
+                        v0 = bdiv(v0);
+                        v1 = bdiv(v1);
+                        v2 = bdiv(v2);
+                        v3 = bdiv(v3);
                     }
                     uint2 o;
                     o.x = prmt((uint32_t)v0, (uint32_t)v1, 0x5410);
@@ -300,184 +321,306 @@ __device__ __forceinline__ void halfVerticalStrip(const HalfArgs &a, const uint8
     }
 }
 
+// Vertical pass of a tile: 8 warps = 2 column halves x 4 strips of destination row pairs.
+template <int NG, bool SMEM>
+__device__ __forceinline__ void halfVertical(const HalfArgs &a, const uint8_t *__restrict__ srcOrTile, uint32_t *W,
+                                             int xs0, int tx0, int ty0, int th)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cw = ((warp & 1) << 5) | lane;  // column word 0..63
+    const int strip = warp >> 1;              // 0..3
+    const int pairs = (th + 1) >> 1;
+    const int k0 = (strip * pairs) >> 2, k1 = ((strip + 1) * pairs) >> 2;
+    if (k0 >= k1) return;
+    // column words right of the last source column any pixel of this tile needs do no work
+    // (matters for the nearly empty last tile of a shifted grid)
+    const int lastCol = 2 * (min(tx0 + kHalfTileW, a.DW) - 1) + a.NX / 2;
+    if (xs0 + 4 * cw > lastCol) return;
+    uint32_t *wout = W + swzWord(2 * cw);
+    const bool borderRows = (ty0 + 2 * k0 < a.mbY) || (ty0 + 2 * k1 > a.meY);
+    if (SMEM) {
+        const uint8_t *base = srcOrTile + 4 * cw;
+        if (borderRows)
+            halfVerticalStrip<NG, true, true>(a, base, wout, ty0, k0, k1);
+        else
+            halfVerticalStrip<NG, false, true>(a, base, wout, ty0, k0, k1);
+    } else {
+        // columns outside the image only ever meet zero coefficients: read column 0 instead
+        const int col = xs0 + 4 * cw;
+        const uint8_t *base = srcOrTile + ((col >= 0 && col < a.SW) ? col : 0);
+        // source rows this strip touches, including the one-group prefetch overshoot
+        const int gFirst = (ty0 >> 1) + k0 + a.qmin;
+        const int gLast = (ty0 >> 1) + k1 + a.qmin + NG - 1;
+        if (borderRows || gFirst < 0 || 4 * gLast + 3 >= a.SH)
+            halfVerticalStrip<NG, true, false>(a, base, wout, ty0, k0, k1);
+        else
+            halfVerticalStrip<NG, false, false>(a, base, wout, ty0, k0, k1);
+    }
+}
+
 // Border columns of a tile (Lanczos: at most N/2 per side), recomputed after the main pass by
-// the whole CTA, one (row, column) item per thread so that no warp diverges into a scalar loop:
-// masked taps and the truncating division of resizeXborder (reference ..._Generic.cpp:539-574)
-// from the generic tables.  [c0, c1) are the tile's border columns.
-__device__ __noinline__ void halfBorderColumns(const HalfArgs &a, const uint32_t *W, uint8_t *dstTile, int xs0,
+// the whole CTA, one (row, column) item per thread so that no warp diverges: the masked taps of
+// resizeXborder (reference ..._Generic.cpp:539-574) as planner-made pair words through the same
+// dp2a planes, then its truncating division.  [c0, c1) are the tile's border columns, `bx` the
+// table entry of column c0.
+template <int NWX>
+__device__ __noinline__ void halfBorderColumns(const HalfArgs &a, const uint32_t *W, uint8_t *dstTile, const int32_t *bx,
                                                int tx0, int c0, int c1, int th)
 {
+    constexpr int kBase = 4 - (NWX - 1) / 2;
     const int nb = c1 - c0;
     for (int item = threadIdx.x; item < nb * th; item += blockDim.x) {
         const int r = item / nb;
-        const int d = c0 + (item - r * nb);
+        const int j = item - r * nb;
+        const int d = c0 + j;
         const uint32_t *wr = W + r * kHalfRowWords;
-        const int fx = __ldg(a.firstX + d);
-        const int rx = __ldg(a.rowX + d);
-        const int deno = __ldg(a.denoX + rx);
-        int nume = 0;
-        for (int i = 0; i < a.NX; ++i) {
-            const int c = __ldg(a.coefX + rx * a.NX + i);
-            const int e = min(max(fx + i, 0), a.SW - 1) - xs0;
-            const uint32_t word = wr[swzWord(e >> 1)];
-            const int val = (int)((e & 1) ? (word >> 16) : (word & 0xffffu)) - a.workBias;
-            nume += c * val;
+        const int32_t *e = bx + j * 9;
+        int lo = __ldg(e + 8), hi = 0;
+#pragma unroll
+        for (int i = 0; i < NWX; ++i) {
+            const uint32_t word = wr[swzWord(d - tx0 + kBase + i)];
+            const uint32_t cw = (uint32_t)__ldg(e + i);
+            lo = dp2a_lo_uu(word, cw, lo);
+            hi = dp2a_hi_us(word, cw, hi);
         }
-        const int v = (int)(short)((nume + (1 << 19)) / (deno * 64));
+        const int v = (int)(short)((lo + (hi << 8)) / __ldg(e + 7));
         dstTile[(long long)r * a.dstPitch + (d - tx0)] = (uint8_t)min(max(v, 0), 255);
     }
 }
 
-__device__ __noinline__ void halfStoreBytes(uint8_t *out, uint2 o, int count)
+__device__ __noinline__ void halfStoreBytes(uint8_t *out, uint2 o, int lo, int hi)
 {
-    for (int p = 0; p < count; ++p) out[p] = (uint8_t)(((p < 4 ? o.x : o.y) >> (8 * (p & 3))) & 0xffu);
+    for (int p = lo; p < hi; ++p) out[p] = (uint8_t)(((p < 4 ? o.x : o.y) >> (8 * (p & 3))) & 0xffu);
 }
 
+// Horizontal pass of a tile + border columns.  The caller has synchronised after the vertical pass.
+template <int NWX, bool SYM>
+__device__ __forceinline__ void halfHorizontal(const HalfArgs &a, const uint32_t *W, uint8_t *__restrict__ dst,
+                                               int xs0, int tx0, int ty0, int th)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int kBase = 4 - (NWX - 1) / 2;  // pair word of tap pair 0 for pixel 0 (wa + 4)
+    const int txEnd = min(tx0 + kHalfTileW, a.DW);
+    const int groups = (txEnd - tx0 + 7) >> 3;  // 8-pixel groups holding at least one pixel of the image
+
+    // eight adjacent destination pixels (group l) of local row r
+    auto doGroup = [&](int r, int l) {
+        const int d0 = tx0 + 8 * l;
+        int pc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) pc[j] = swzWord(4 * (2 * l + j));
+        // 8-byte store when the pixel group is 8-aligned, two 4-byte stores when the tile grid is
+        // shifted by 4 (TMA variant), bytes for partial groups or unaligned destinations
+        const bool vecStore = a.dstVec && d0 >= 0 && (d0 + 8 <= a.DW);
+        const bool vec8 = (d0 & 7) == 0;
+        // a group cut in half by the image edge (shifted grid): one aligned 4-byte store
+        const bool halfLo = a.dstVec && !vecStore && d0 >= 0 && d0 + 4 == a.DW;
+        const bool halfHi = a.dstVec && !vecStore && d0 == -4 && a.DW >= 4;
+        uint8_t *out = dst + (long long)(ty0 + r) * a.dstPitch + d0;
+        {
+        const uint32_t *wr = W + r * kHalfRowWords;
+        uint32_t n[16];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint4 q = *reinterpret_cast<const uint4 *>(wr + pc[j]);
+            n[4 * j] = q.x;
+            n[4 * j + 1] = q.y;
+            n[4 * j + 2] = q.z;
+            n[4 * j + 3] = q.w;
+        }
+        int v[8];
+        if (SYM) {
+            constexpr int m = NWX / 2;
+            // swapped halves of the words that serve as mirror partners
+            uint32_t sw[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) sw[i] = (i >= kBase + m + 1 && i <= kBase + NWX - 2 + 7) ? prmt(n[i], n[i], 0x1032) : 0u;
+            // mirrored pairs are added as packed u16 halves (no carry can cross: every
+            // half-sum fits 16 bits).  The third addend is a kernel argument that is always
+            // 0: a three-input add can only be an IADD3, which keeps these adds off the
+            // multiplier pipe that the dp2a/dp4a instructions saturate.
+            uint32_t sum[8][m > 1 ? m - 1 : 1];
+#pragma unroll
+            for (int j = 1; j < m; ++j)
+#pragma unroll
+                for (int p = 0; p < 8; ++p) sum[p][j - 1] = n[kBase + p + j] + sw[kBase + p + NWX - 1 - j] + a.zero;
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const uint32_t ctr = n[kBase + p + m];
+                const uint32_t ends = prmt(n[kBase + p], n[kBase + p + NWX - 1], 0x3254);
+                // low byte plane first; the high plane continues from (low >> 8):
+                // floor((lo + 256 hi) / 2^20) == floor((floor(lo / 256) + hi) / 2^12)
+                int acc = a.accInit;
+#pragma unroll
+                for (int j = 1; j < m; ++j) acc = dp2a_lo_uu(sum[p][j - 1], a.cwXs[j - 1], acc);
+                acc = dp2a_lo_uu(ctr, a.cwXs[m - 1], acc);
+                acc = dp2a_lo_uu(ends, a.cwXs[m], acc);
+                acc >>= 8;
+#pragma unroll
+                for (int j = 1; j < m; ++j) acc = dp2a_hi_us(sum[p][j - 1], a.cwXs[j - 1], acc);
+                acc = dp2a_hi_us(ctr, a.cwXs[m - 1], acc);
+                acc = dp2a_hi_us(ends, a.cwXs[m], acc);
+                v[p] = acc >> 12;
+            }
+        } else {
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                int acc = a.accInit;
+#pragma unroll
+                for (int j = 0; j < NWX; ++j) acc = dp2a_lo_uu(n[kBase + p + j], a.cwX[j], acc);
+                acc >>= 8;
+#pragma unroll
+                for (int j = 0; j < NWX; ++j) acc = dp2a_hi_us(n[kBase + p + j], a.cwX[j], acc);
+                v[p] = acc >> 12;
+            }
+        }
+        uint2 o;
+        o.x = packSatU8(v[1], v[0], packSatU8(v[3], v[2], 0u));
+        o.y = packSatU8(v[5], v[4], packSatU8(v[7], v[6], 0u));
+        if (vecStore) {
+            if (vec8) {
+                *reinterpret_cast<uint2 *>(out) = o;
+            } else {
+                *reinterpret_cast<uint32_t *>(out) = o.x;
+                *reinterpret_cast<uint32_t *>(out + 4) = o.y;
+            }
+        } else if (halfLo || halfHi) {
+            if (halfLo) *reinterpret_cast<uint32_t *>(out) = o.x;
+            if (halfHi) *reinterpret_cast<uint32_t *>(out + 4) = o.y;
+        } else {
+            halfStoreBytes(out, o, max(0, -d0), min(8, a.DW - d0));
+        }
+
+        }
+    };
+
+    if (groups == 15) {
+        // full tile: a half-warp per row (15 of 16 lanes busy), two rows per warp and iteration
+        const int half = lane >> 4, l = lane & 15;
+        if (l < 15)
+            for (int r = 2 * warp + half; r < th; r += 16) doGroup(r, l);
+    } else if (groups > 0) {
+        // partial tile (image edge): pack (row, group) items densely over the CTA
+        const uint32_t rcp = (65536u + groups - 1) / groups;
+        for (int item = threadIdx.x; item < groups * th; item += blockDim.x) {
+            const int r = (int)(((uint32_t)item * rcp) >> 16);
+            doGroup(r, item - r * groups);
+        }
+    }
+    // border columns
+    const bool left = tx0 < a.mbX, right = txEnd > a.meX;
+    if (left || right) {
+        __syncthreads();  // the main stores of these pixels come first (block-scope ordering)
+        uint8_t *dstTile = dst + (long long)ty0 * a.dstPitch + tx0;
+        if (left) halfBorderColumns<NWX>(a, W, dstTile, a.borderX + 9 * max(tx0, 0), tx0, max(tx0, 0), min(a.mbX, txEnd), th);
+        if (right) {
+            const int c0 = max(a.meX, max(tx0, a.mbX));
+            halfBorderColumns<NWX>(a, W, dstTile, a.borderX + 9 * (a.mbX + c0 - a.meX), tx0, c0, txEnd, th);
+        }
+    }
+}
+
+// ---- variant 1: source rows read with ordinary global loads (any 4-byte aligned pitch) ----
 template <int NG, int NWX, bool SYM>
 __global__ void __launch_bounds__(256, 3) resizeHalfKernel(const __grid_constant__ HalfArgs a)
 {
     __shared__ __align__(16) uint32_t W[kHalfMaxRows * kHalfRowWords];
-
-    const int tx0 = blockIdx.x * kHalfTileW;
+    const int tx0 = blockIdx.x * kHalfTileW - a.tileShift;
     const int ty0 = blockIdx.y * a.tileRows;
     const int th = min(a.tileRows, a.DH - ty0);
     const uint8_t *__restrict__ src = a.src + (long long)blockIdx.z * a.srcFrameStride;
     uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
     const int xs0 = 2 * tx0 - 8;  // source column of W element 0 (multiple of 4)
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    // ================= vertical pass =================
-    {
-        const int cw = ((warp & 1) << 5) | lane;  // column word 0..63
-        const int strip = warp >> 1;              // 0..3
-        const int pairs = (th + 1) >> 1;
-        const int k0 = (strip * pairs) >> 2, k1 = ((strip + 1) * pairs) >> 2;
-        const int col = xs0 + 4 * cw;
-        const bool colOk = (col >= 0) && (col < a.SW);
-        const uint8_t *colPtr = src + (colOk ? col : 0);
-        uint32_t *wout = W + swzWord(2 * cw);
-        if (k0 < k1) {
-            // source rows this strip touches, including the one-group prefetch overshoot
-            const int gFirst = (ty0 >> 1) + k0 + a.qmin;
-            const int gLast = (ty0 >> 1) + k1 + a.qmin + NG - 1;
-            const bool edge = (gFirst < 0) || (4 * gLast + 3 >= a.SH) || (ty0 + 2 * k0 < a.mbY) || (ty0 + 2 * k1 > a.meY);
-            if (edge || !colOk)
-                halfVerticalStrip<NG, true>(a, colPtr, colOk, wout, ty0, k0, k1);
-            else
-                halfVerticalStrip<NG, false>(a, colPtr, true, wout, ty0, k0, k1);
-        }
-    }
+    halfVertical<NG, false>(a, src, W, xs0, tx0, ty0, th);
     __syncthreads();
+    halfHorizontal<NWX, SYM>(a, W, dst, xs0, tx0, ty0, th);
+}
 
-    // ================= horizontal pass =================
-    {
-        const int half = lane >> 4, l = lane & 15;
-        const int d0 = tx0 + 8 * l;  // first destination column of this thread
-        if (l < 15 && d0 < a.DW) {
-            int pc[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) pc[j] = swzWord(4 * (2 * l + j));
-            constexpr int kBase = 4 - (NWX - 1) / 2;  // pair word of tap pair 0 for pixel 0 (wa + 4)
-            const bool vecStore = a.dstVec && (d0 + 8 <= a.DW);
-            uint8_t *out = dst + (long long)(ty0 + 2 * warp + half) * a.dstPitch + d0;
-            const long long outStep = 2 * a.dstPitch;
-            for (int r = 2 * warp + half; r < th; r += 16, out += 8 * outStep) {
-                const uint32_t *wr = W + r * kHalfRowWords;
-                uint32_t n[16];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint4 q = *reinterpret_cast<const uint4 *>(wr + pc[j]);
-                    n[4 * j] = q.x;
-                    n[4 * j + 1] = q.y;
-                    n[4 * j + 2] = q.z;
-                    n[4 * j + 3] = q.w;
-                }
-                int v[8];
-                if (SYM) {
-                    constexpr int m = NWX / 2;
-                    // swapped halves of the words that serve as mirror partners
-                    uint32_t sw[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) sw[i] = (i >= kBase + m + 1 && i <= kBase + NWX - 2 + 7) ? prmt(n[i], n[i], 0x1032) : 0u;
-                    // mirrored pairs are added as packed u16 halves (no carry can cross: every
-                    // half-sum fits 16 bits).  The third addend is a kernel argument that is always
-                    // 0: a three-input add can only be an IADD3, which keeps these adds off the
-                    // multiplier pipe that the dp2a/dp4a instructions saturate.
-                    uint32_t sum[8][m > 1 ? m - 1 : 1];
-#pragma unroll
-                    for (int j = 1; j < m; ++j)
-#pragma unroll
-                        for (int p = 0; p < 8; ++p) sum[p][j - 1] = n[kBase + p + j] + sw[kBase + p + NWX - 1 - j] + a.zero;
-#pragma unroll
-                    for (int p = 0; p < 8; ++p) {
-                        const uint32_t ctr = n[kBase + p + m];
-                        const uint32_t ends = prmt(n[kBase + p], n[kBase + p + NWX - 1], 0x3254);
-                        // low byte plane first; the high plane continues from (low >> 8):
-                        // floor((lo + 256 hi) / 2^20) == floor((floor(lo / 256) + hi) / 2^12)
-                        int acc = a.accInit;
-#pragma unroll
-                        for (int j = 1; j < m; ++j) acc = dp2a_lo_uu(sum[p][j - 1], a.cwXs[j - 1], acc);
-                        acc = dp2a_lo_uu(ctr, a.cwXs[m - 1], acc);
-                        acc = dp2a_lo_uu(ends, a.cwXs[m], acc);
-                        acc >>= 8;
-#pragma unroll
-                        for (int j = 1; j < m; ++j) acc = dp2a_hi_us(sum[p][j - 1], a.cwXs[j - 1], acc);
-                        acc = dp2a_hi_us(ctr, a.cwXs[m - 1], acc);
-                        acc = dp2a_hi_us(ends, a.cwXs[m], acc);
-                        v[p] = acc >> 12;
-                    }
-                } else {
-#pragma unroll
-                    for (int p = 0; p < 8; ++p) {
-                        int acc = a.accInit;
-#pragma unroll
-                        for (int j = 0; j < NWX; ++j) acc = dp2a_lo_uu(n[kBase + p + j], a.cwX[j], acc);
-                        acc >>= 8;
-#pragma unroll
-                        for (int j = 0; j < NWX; ++j) acc = dp2a_hi_us(n[kBase + p + j], a.cwX[j], acc);
-                        v[p] = acc >> 12;
-                    }
-                }
-                uint2 o;
-                o.x = packSatU8(v[1], v[0], packSatU8(v[3], v[2], 0u));
-                o.y = packSatU8(v[5], v[4], packSatU8(v[7], v[6], 0u));
-                if (vecStore)
-                    *reinterpret_cast<uint2 *>(out) = o;
-                else
-                    halfStoreBytes(out, o, min(8, a.DW - d0));
-            }
-        }
-    }
-    // ================= border columns =================
-    {
-        const int txEnd = min(tx0 + kHalfTileW, a.DW);
-        const bool left = tx0 < a.mbX, right = txEnd > a.meX;
-        if (left || right) {
-            __syncthreads();  // the main stores of these pixels come first (block-scope ordering)
-            uint8_t *dstTile = dst + (long long)ty0 * a.dstPitch + tx0;
-            if (left) halfBorderColumns(a, W, dstTile, xs0, tx0, tx0, min(a.mbX, txEnd), th);
-            if (right) halfBorderColumns(a, W, dstTile, xs0, tx0, max(a.meX, max(tx0, a.mbX)), txEnd, th);
-        }
-    }
+// ---- variant 2: the tile's source window (256 bytes x boxRows rows) is staged by one TMA
+// (cp.async.bulk.tensor) per tile; rows/columns outside the image arrive as zeros ----
+struct HalfTmaArgs {
+    alignas(64) CUtensorMap tmap;  // 3-D: (x, y, frame), u8, box 256 x boxRows x 1
+    HalfArgs h;
+    int boxRows;
+};
+
+__device__ __forceinline__ uint32_t smemAddr(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
 }
 
 template <int NG, int NWX, bool SYM>
-cudaError_t launchHalfT(const HalfArgs &a, cudaStream_t stream)
+__global__ void __launch_bounds__(256, 3) resizeHalfTmaKernel(const __grid_constant__ HalfTmaArgs p)
 {
-    const int tilesX = (a.DW + kHalfTileW - 1) / kHalfTileW;
-    const int tilesY = (a.DH + a.tileRows - 1) / a.tileRows;
-    for (int f0 = 0; f0 < a.nFrames; f0 += 65535) {
-        HalfArgs b = a;
-        b.nFrames = std::min(65535, a.nFrames - f0);
-        b.src = a.src + (long long)f0 * a.srcFrameStride;
-        b.dst = a.dst + (long long)f0 * a.dstFrameStride;
-        dim3 grid(tilesX, tilesY, b.nFrames);
-        resizeHalfKernel<NG, NWX, SYM><<<grid, 256, 0, stream>>>(b);
-        g_launches.fetch_add(1);
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
+    extern __shared__ __align__(128) uint8_t smemDyn[];
+    uint8_t *tile = smemDyn;
+    uint32_t *W = reinterpret_cast<uint32_t *>(smemDyn + kHalfTileBytes);
+    __shared__ __align__(8) unsigned long long mbar;
+    const HalfArgs &a = p.h;
+
+    // the tile grid is shifted by 4 destination pixels so that the box starts on a 16-byte
+    // boundary (2*tx0 - 8 = 240*i - 16): TMA requires that of the innermost coordinate
+    const int tx0 = blockIdx.x * kHalfTileW - a.tileShift;
+    const int ty0 = blockIdx.y * a.tileRows;
+    const int th = min(a.tileRows, a.DH - ty0);
+    uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
+    const int xs0 = 2 * tx0 - 8;
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smemAddr(&mbar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    return cudaSuccess;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t bytes = (uint32_t)p.boxRows * kHalfSrcRowBytes;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(&mbar)), "r"(bytes) : "memory");
+        const int y0 = 4 * ((ty0 >> 1) + a.qmin);  // first source row of the tile's first group
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+            ::"r"(smemAddr(tile)), "l"(reinterpret_cast<unsigned long long>(&p.tmap)), "r"(xs0), "r"(y0), "r"((int)blockIdx.z),
+              "r"(smemAddr(&mbar))
+            : "memory");
+    }
+    {
+        // every thread waits for the transaction bytes to land (phase 0)
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n\t.reg .pred q;\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%1], 0;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+                : "=r"(done)
+                : "r"(smemAddr(&mbar))
+                : "memory");
+        }
+    }
+    halfVertical<NG, true>(a, tile, W, xs0, tx0, ty0, th);
+    __syncthreads();
+    halfHorizontal<NWX, SYM>(a, W, dst, xs0, tx0, ty0, th);
+}
+
+template <int NG, int NWX, bool SYM>
+cudaError_t launchHalfT(const HalfArgs &a, const CUtensorMap *tmap, int boxRows, cudaStream_t stream)
+{
+    const int tilesX = (a.DW + a.tileShift + kHalfTileW - 1) / kHalfTileW;
+    const int tilesY = (a.DH + a.tileRows - 1) / a.tileRows;
+    dim3 grid(tilesX, tilesY, a.nFrames);
+    if (tmap) {
+        static bool attrSet = false;  // per instantiation; a benign race sets it twice at worst
+        const int smem = kHalfTileBytes + kHalfWBytes;
+        if (!attrSet) {
+            cudaError_t e = cudaFuncSetAttribute(resizeHalfTmaKernel<NG, NWX, SYM>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            attrSet = true;
+        }
+        HalfTmaArgs p;
+        p.tmap = *tmap;
+        p.h = a;
+        p.boxRows = boxRows;
+        resizeHalfTmaKernel<NG, NWX, SYM><<<grid, 256, smem, stream>>>(p);
+    } else {
+        resizeHalfKernel<NG, NWX, SYM><<<grid, 256, 0, stream>>>(a);
+    }
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
 }
 
 }  // namespace
@@ -533,11 +676,12 @@ cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_
     return cudaSuccess;
 }
 
-cudaError_t launchHalf(const HalfArgs &a, cudaStream_t stream)
+cudaError_t launchHalf(const HalfArgs &a, const CUtensorMap *tmap, int boxRows, cudaStream_t stream)
 {
-#define IQO_HALF_CASE(G, NW)                                                           \
-    if (a.NG == G && a.NWX == NW)                                                      \
-        return a.symmetric ? launchHalfT<G, NW, true>(a, stream) : launchHalfT<G, NW, false>(a, stream);
+#define IQO_HALF_CASE(G, NW)                                                                           \
+    if (a.NG == G && a.NWX == NW)                                                                      \
+        return a.symmetric ? launchHalfT<G, NW, true>(a, tmap, boxRows, stream)                        \
+                           : launchHalfT<G, NW, false>(a, tmap, boxRows, stream);
     IQO_HALF_CASE(3, 7)
     IQO_HALF_CASE(3, 5)
     IQO_HALF_CASE(2, 3)
@@ -549,6 +693,11 @@ cudaError_t launchHalf(const HalfArgs &a, cudaStream_t stream)
     IQO_HALF_CASE(1, 7)
 #undef IQO_HALF_CASE
     return cudaErrorInvalidValue;
+}
+
+int halfSourceRowsMax()
+{
+    return kHalfSrcMaxRows - 4;  // the last group is prefetch slack
 }
 
 unsigned long long launchCount()

@@ -1,6 +1,7 @@
 // Device-side interface between the C ABI (capi.cu) and the sm_100a kernels (kernels.cu).
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -47,6 +48,7 @@ struct HalfArgs {
     int SW, SH, DW, DH;
     int nFrames;
     int tileRows;             // destination rows per tile (even, <= 64)
+    int tileShift;            // tiles start at 120*i - tileShift destination columns (0, or 4 for TMA)
     int dstVec;               // destination rows may be written with 8-byte stores
     // vertical
     int qmin, NG;
@@ -62,12 +64,16 @@ struct HalfArgs {
     uint32_t cwXs[4];
     int accInit;
     int mbX, meX;
-    const int32_t *firstX, *rowX, *coefX, *denoX;  // generic tables, used for the border columns
+    const uint32_t *magicY;   // [numRowsY] multiply-high constants of the border-row divisions
+    const int32_t *borderX;   // [border columns][9]: 7 pair words, denominator*64, accumulator init
     int NX;
     uint32_t zero;            // always 0 (see the pair sums in resizeHalfKernel)
 };
 
-cudaError_t launchHalf(const HalfArgs &a, cudaStream_t stream);
+// tmap == NULL: source rows are read with global loads; otherwise a 3-D tensor map (x, y, frame)
+// over the source frames with box 256 x boxRows x 1 (at most 65535 frames per launch either way).
+cudaError_t launchHalf(const HalfArgs &a, const CUtensorMap *tmap, int boxRows, cudaStream_t stream);
+int halfSourceRowsMax();
 
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D);
 cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_t stream);

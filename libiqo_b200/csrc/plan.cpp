@@ -467,6 +467,25 @@ void buildHalfPlan(const Plan &p, HalfPlan &h)
     long long sumX = 0;
     for (int i = 0; i < NX; ++i) sumX += cx[i];
     h.accInit = int((1ll << (p.shift - 1)) - (long long)h.workBias * sumX);
+
+    // ---- borders ----
+    h.magicY.assign(size_t(Y.numRows), 0);
+    for (int r = 0; r < Y.numRows; ++r)
+        if (Y.deno[size_t(r)] > 1) h.magicY[size_t(r)] = uint32_t((1ull << 32) / uint64_t(Y.deno[size_t(r)]) + 1);
+    h.borderX.clear();
+    for (int64_t d = 0; d < X.D; ++d) {
+        if (d >= X.mainBegin && d < X.mainEnd) continue;
+        const int32_t *c = &X.coef[size_t(X.row[d]) * NX];
+        long long sum = 0;
+        for (int i = 0; i < h.NWX; ++i) {
+            const int ta = 2 * i - 1, tb = 2 * i;
+            h.borderX.push_back(int32_t(pairWord(ta >= 0 ? c[ta] : 0, tb < NX ? c[tb] : 0)));
+        }
+        for (int i = h.NWX; i < 7; ++i) h.borderX.push_back(0);
+        for (int i = 0; i < NX; ++i) sum += c[i];
+        h.borderX.push_back(int32_t(X.deno[size_t(X.row[d])] * 64));
+        h.borderX.push_back(int32_t((1ll << (p.shift - 1)) - (long long)h.workBias * sum));
+    }
     h.eligible = true;
 }
 

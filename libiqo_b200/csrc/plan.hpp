@@ -88,6 +88,12 @@ struct HalfPlan {
     uint32_t cwX[7];          // general form, per pair word: bytes (lo(c_a), lo(c_b), hi(c_a), hi(c_b))
     uint32_t cwXs[4];         // symmetric form: [0..m-2] summed pairs, [m-1] centre, [m] the two end taps
     int accInit;              // rounding constant minus the bias contribution
+    // border rows: floor(2^32 / deno) + 1 per coefficient row (0 for ordinary rows): the truncating
+    // division by the small denominator becomes a multiply-high (exact for |numerator| <= 2^21)
+    std::vector<uint32_t> magicY;
+    // border columns in order (left ones, then right ones), 9 words each:
+    // [0..6] pair words of the masked taps (general form), [7] denominator * 64, [8] accumulator init
+    std::vector<int32_t> borderX;
 };
 
 void buildHalfPlan(const Plan &plan, HalfPlan &h);

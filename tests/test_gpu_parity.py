@@ -221,15 +221,17 @@ HALF_CASES = [
 ]
 
 
+@pytest.mark.parametrize("path", [iqo.PATH_AUTO, iqo.PATH_NO_TMA])
 @pytest.mark.parametrize("case", HALF_CASES)
-def test_half_kernel(case):
+def test_half_kernel(case, path):
     deg, px, sw, sh, spad, dpad, kname = case
     dw, dh = sw // 2, sh // 2
     src = lcg_image(sh, sw + spad, seed=11)
     rc, want = oracle_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
     assert rc == 0
-    got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
-    assert kernel == kname
+    got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad, path=path)
+    # host images are staged on the device with a 16-byte aligned pitch, so AUTO feeds the tile by TMA
+    assert kernel == (kname + "_tma" if path == iqo.PATH_AUTO and kname != "generic" else kname)
     assert iqo.plan_kernel(LANCZOS, deg, sw, sh, dw, dh, px)[0] == kname
     bad = np.argwhere(got != want)
     assert bad.size == 0, (len(bad), bad[:8].tolist())
@@ -250,3 +252,20 @@ def test_half_kernel_extreme_values():
             got, kernel = gpu_resize(LANCZOS, src, sw // 2, sh // 2, deg, px)
             assert kernel.startswith("half")
             assert np.array_equal(got, want), (name, deg, px)
+
+
+def test_half_kernel_device_pitches():
+    """Device-resident frames: a 16-byte aligned pitch takes the TMA variant, a pitch that is only
+    4-byte aligned takes the global-load variant, an odd pitch falls back to the generic kernel."""
+    torch = pytest.importorskip("torch")
+    sw, sh, dw, dh, n = 488, 250, 244, 125, 3
+    for pitch, expect in ((496, "half_sym_tma"), (492, "half_sym"), (489, "generic")):
+        host = np.stack([lcg_image(sh, pitch, seed=40 + f) for f in range(n)])
+        want = np.stack([oracle_resize(LANCZOS, host[f], dw, dh, 3, sw=sw)[1] for f in range(n)])
+        dsrc = torch.from_numpy(host).cuda()
+        ddst = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
+        with iqo.LanczosResizer(3, sw, sh, dw, dh) as r:
+            r.resize_batch(n, pitch, pitch * sh, dsrc, dw, dw * dh, ddst, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert r.last_kernel() == expect
+        assert np.array_equal(ddst.cpu().numpy(), want), pitch

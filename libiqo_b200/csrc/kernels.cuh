@@ -60,6 +60,7 @@ struct HalfArgs {
     int workBias;
     // horizontal
     int NWX, symmetric;
+    int endsHi;               // symmetric form: the end-tap pair word has a non-zero high byte plane
     uint32_t cwX[7];
     uint32_t cwXs[4];
     int accInit;

@@ -2,7 +2,7 @@
  * iqo_cuda.h -- C ABI of the B200 (sm_100a) backend for libiqo's one-channel U8 resizers.
  *
  * This is the drop-in boundary.  libiqo's public classes keep their signatures
- * (include/libiqo/*.hpp in this repo); where the reference's constructors probe CPUID and
+ * (the headers under include/libiqo/ in this repo); where the reference's constructors probe CPUID and
  * pick `LanczosResizerImpl_new<ArchAVX512|AVX2FMA|SSE4_1|NEON|Generic>()`
  * (reference src/IQOLanczosResizer.cpp:15-36, src/IQOAreaResizer.cpp:13-34,
  * src/IQOLinearResizer.cpp:13-34) there is now exactly one backend, reached through the
@@ -127,6 +127,24 @@ IQO_CUDA_API int iqo_cuda_resize_batch_multi(int kind, unsigned degree,
                                              size_t dstSt, size_t dstFrameStride, uint8_t *dst,
                                              int nDevices, const int *devices);
 
+/* ---- planar YUV420 frames ----
+ * Frame layout of the reference's sample program (sample/resize_yuv420p.cpp:66-75,117-123):
+ * strides rounded up to even (stX = W + W%2, stY = H + H%2), Y plane stX*stY bytes, then U and V
+ * of (stX/2)*(stY/2) bytes each.  Luma is resized W x H -> dstW x dstH with pxScale 1, both
+ * chroma planes stX/2 x stY/2 -> dstStX/2 x dstStY/2 with pxScale 2 (:150-163; pxScale only
+ * matters for Lanczos). */
+typedef struct iqo_cuda_yuv420 iqo_cuda_yuv420;
+IQO_CUDA_API int iqo_cuda_yuv420_create(iqo_cuda_yuv420 **out, int kind, unsigned degree,
+                                        size_t srcW, size_t srcH, size_t dstW, size_t dstH);
+IQO_CUDA_API void iqo_cuda_yuv420_destroy(iqo_cuda_yuv420 *h);
+/* bytes of one source / destination frame in the layout above */
+IQO_CUDA_API int iqo_cuda_yuv420_frame_bytes(const iqo_cuda_yuv420 *h, size_t *srcBytes, size_t *dstBytes);
+/* nFrames consecutive frames.  Device pointers: three launches (Y, U, V planes of the whole
+ * batch) enqueued on `stream`, asynchronous.  Host pointers: chunks of frames go through a
+ * double-buffered H2D / kernels / D2H pipeline and the call returns when dst is complete. */
+IQO_CUDA_API int iqo_cuda_yuv420_resize(iqo_cuda_yuv420 *h, size_t nFrames, const uint8_t *src, uint8_t *dst,
+                                        void *stream);
+
 /* ---- introspection (tests, benchmarks) ---- */
 
 /* Coefficient tables as the reference would hold them in m_TablesX / m_TablesY
@@ -158,6 +176,11 @@ IQO_CUDA_API const char *iqo_cuda_last_kernel(const iqo_cuda_resizer *r);
 IQO_CUDA_API unsigned long long iqo_cuda_launch_count(void);
 /* synchronise the handle's streams */
 IQO_CUDA_API int iqo_cuda_sync(iqo_cuda_resizer *r);
+
+/* Plans (coefficient tables on the device) are cached per (device, kind, degree, sizes, pxScale)
+ * and stream/staging workspaces are pooled, so that create + resize + destroy in a loop -- what
+ * the reference's benchmark does (benchmark/benchmark.cpp:214-227) -- is cheap.  This drops both. */
+IQO_CUDA_API void iqo_cuda_clear_cache(void);
 
 /* pinned host memory helpers (for callers that want overlap-capable host buffers) */
 IQO_CUDA_API void *iqo_cuda_host_alloc(size_t bytes);

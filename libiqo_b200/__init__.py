@@ -17,7 +17,7 @@ There is NO CPU fallback: importing works anywhere, but the first use raises
 import ctypes as C
 import os
 
-__all__ = ["LanczosResizer", "AreaResizer", "LinearResizer", "IqoCudaError", "lib", "build",
+__all__ = ["LanczosResizer", "AreaResizer", "LinearResizer", "Yuv420Resizer", "IqoCudaError", "lib", "build",
            "LANCZOS", "AREA", "LINEAR", "PATH_AUTO", "PATH_GENERIC", "PATH_NO_TMA", "exported_symbols"]
 
 LANCZOS, AREA, LINEAR = 0, 1, 2
@@ -49,6 +49,10 @@ _SIGNATURES = {
                                               C.c_int, C.POINTER(C.c_int)]),
     "iqo_cuda_resize_batch_multi": (C.c_int, [C.c_int, C.c_uint, _sz, _sz, _sz, _sz, _sz, _sz,
                                               _sz, _sz, _vp, _sz, _sz, _vp, C.c_int, C.POINTER(C.c_int)]),
+    "iqo_cuda_yuv420_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_uint, _sz, _sz, _sz, _sz]),
+    "iqo_cuda_yuv420_destroy": (None, [_vp]),
+    "iqo_cuda_yuv420_frame_bytes": (C.c_int, [_vp, C.POINTER(_sz), C.POINTER(_sz)]),
+    "iqo_cuda_yuv420_resize": (C.c_int, [_vp, _sz, _vp, _vp, _vp]),
     "iqo_cuda_get_table": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _vp, _sz]),
     "iqo_cuda_plan_query": (C.c_int, [C.c_int, C.c_uint, _sz, _sz, _sz, _sz, _sz, C.c_int,
                                       C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int),
@@ -59,6 +63,7 @@ _SIGNATURES = {
     "iqo_cuda_last_kernel": (C.c_char_p, [_vp]),
     "iqo_cuda_launch_count": (C.c_ulonglong, []),
     "iqo_cuda_sync": (C.c_int, [_vp]),
+    "iqo_cuda_clear_cache": (None, []),
     "iqo_cuda_host_alloc": (_vp, [_sz]),
     "iqo_cuda_host_free": (None, [_vp]),
     "iqo_cuda_last_error": (C.c_char_p, []),
@@ -211,6 +216,35 @@ class LinearResizer(_Resizer):
 
     def __init__(self, srcW, srcH, dstW, dstH, device=None):
         _Resizer.__init__(self, 0, srcW, srcH, dstW, dstH, 1, device)
+
+
+class Yuv420Resizer(object):
+    """Planar YUV420 frames in the layout of the reference's sample/resize_yuv420p.cpp:66-163
+    (even-rounded strides; Y, U, V planes; chroma resized with pxScale 2)."""
+
+    def __init__(self, kind, degree, srcW, srcH, dstW, dstH):
+        self._h = _vp()
+        _check(lib().iqo_cuda_yuv420_create(C.byref(self._h), kind, degree, srcW, srcH, dstW, dstH))
+        a, b = _sz(0), _sz(0)
+        _check(lib().iqo_cuda_yuv420_frame_bytes(self._h, C.byref(a), C.byref(b)))
+        self.src_frame_bytes, self.dst_frame_bytes = a.value, b.value
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().iqo_cuda_yuv420_destroy(self._h)
+            self._h = _vp()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def resize(self, nFrames, src, dst, stream=None):
+        """Host buffers: synchronous pipelined path.  Device buffers: asynchronous on `stream`."""
+        _check(lib().iqo_cuda_yuv420_resize(self._h, nFrames, _address(src), _address(dst), stream))
 
 
 def make_resizer(kind, degree, srcW, srcH, dstW, dstH, pxScale=1, device=None):

@@ -9,8 +9,12 @@
 #include <string.h>
 
 #include <algorithm>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
+#include <tuple>
 #include <vector>
 
 #include "kernels.cuh"
@@ -87,31 +91,60 @@ size_t alignUp(size_t v, size_t a)
 
 }  // namespace
 
-struct iqo_cuda_resizer {
+// Everything that depends only on (device, kind, degree, sizes, pxScale): host plan and device
+// tables.  Immutable after construction, shared by every handle of that shape and kept in a small
+// cache, so that constructing a resizer again (the reference's benchmark builds its resizers
+// inside the timed loop, benchmark/benchmark.cpp:214-227) costs a map lookup.
+struct SharedPlan {
     Plan plan;
+    HalfPlan half;
+    GenericGeom geom;
     int device;
     AxisTables tx, ty;
-    GenericGeom geom;
-    HalfPlan half;
     uint32_t *dBorderY, *dMagicY;
     int32_t *dBorderX;
-    bool useTma;
-    int path;
-    const char *lastKernel;
-    cudaStream_t stream[2];
-    cudaEvent_t evUp[2], evDone[2];
-    // staging for host-pointer calls: two slots of `slotFrames` frames each
-    uint8_t *dSrc[2], *dDst[2];
-    size_t srcPitch, dstPitch;  // device pitches of the staging frames
-    size_t slotFrames;
+    SharedPlan() : device(0), dBorderY(0), dMagicY(0), dBorderX(0) {}
+    ~SharedPlan();
+};
 
-    iqo_cuda_resizer() : device(0), dBorderY(0), dMagicY(0), dBorderX(0), useTma(true), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
+// Per-handle mutable resources (streams, staging buffers); recycled through a pool on destroy.
+struct Workspace {
+    int device;
+    cudaStream_t stream[2];
+    uint8_t *dSrc[2], *dDst[2];
+    size_t srcCap, dstCap;  // bytes per slot
+    Workspace() : device(0), srcCap(0), dstCap(0)
     {
         for (int i = 0; i < 2; ++i) {
             stream[i] = 0;
-            evUp[i] = evDone[i] = 0;
             dSrc[i] = dDst[i] = 0;
         }
+    }
+};
+
+struct iqo_cuda_resizer {
+    std::shared_ptr<SharedPlan> sp;
+    Workspace *ws;
+    Plan &plan;
+    HalfPlan &half;
+    AxisTables &tx, &ty;
+    GenericGeom &geom;
+    uint32_t *&dBorderY, *&dMagicY;
+    int32_t *&dBorderX;
+    cudaStream_t *stream;
+    uint8_t **dSrc, **dDst;
+    int device;
+    bool useTma;
+    int path;
+    const char *lastKernel;
+    size_t srcPitch, dstPitch;  // device pitches of the staging frames
+    size_t slotFrames;          // frames each staging slot currently holds
+
+    iqo_cuda_resizer(const std::shared_ptr<SharedPlan> &s, Workspace *w)
+        : sp(s), ws(w), plan(s->plan), half(s->half), tx(s->tx), ty(s->ty), geom(s->geom), dBorderY(s->dBorderY),
+          dMagicY(s->dMagicY), dBorderX(s->dBorderX), stream(w->stream), dSrc(w->dSrc), dDst(w->dDst), device(s->device),
+          useTma(true), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
+    {
     }
 };
 
@@ -137,6 +170,21 @@ void freeAxis(AxisTables &t)
     cudaFree(t.coef);
     cudaFree(t.deno);
 }
+
+}  // namespace
+
+SharedPlan::~SharedPlan()
+{
+    DeviceGuard guard(device);
+    freeAxis(tx);
+    freeAxis(ty);
+    cudaFree(dBorderY);
+    cudaFree(dMagicY);
+    cudaFree(dBorderX);
+    cudaGetLastError();
+}
+
+namespace {
 
 AxisDev axisDev(const AxisPlan &a, const AxisTables &t)
 {
@@ -270,28 +318,137 @@ int checkStrides(const iqo_cuda_resizer *r, size_t srcSt, const void *src, size_
     return IQO_CUDA_OK;
 }
 
-// (re)allocate the two staging slots so that each holds `frames` frames
+// make sure the two staging slots of the handle's workspace hold `frames` frames each
 int ensureStaging(iqo_cuda_resizer *r, size_t frames)
 {
-    if (r->slotFrames >= frames) return IQO_CUDA_OK;
-    for (int i = 0; i < 2; ++i) {
-        cudaFree(r->dSrc[i]);
-        cudaFree(r->dDst[i]);
-        r->dSrc[i] = r->dDst[i] = 0;
-    }
-    r->slotFrames = 0;
     r->srcPitch = alignUp(size_t(r->plan.x.S), 16);
     r->dstPitch = alignUp(size_t(r->plan.x.D), 16);
     const size_t sBytes = r->srcPitch * size_t(r->plan.y.S) * frames;
     const size_t dBytes = r->dstPitch * size_t(r->plan.y.D) * frames;
-    for (int i = 0; i < 2; ++i) {
-        if (cudaMalloc(&r->dSrc[i], sBytes) != cudaSuccess || cudaMalloc(&r->dDst[i], dBytes) != cudaSuccess) {
-            cudaGetLastError();
-            return fail(IQO_CUDA_E_NOMEM, "cannot allocate %zu bytes of device staging", sBytes + dBytes);
+    Workspace *w = r->ws;
+    if (w->srcCap < sBytes) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(w->dSrc[i]);
+            w->dSrc[i] = 0;
         }
+        w->srcCap = 0;
+        for (int i = 0; i < 2; ++i)
+            if (cudaMalloc(&w->dSrc[i], sBytes) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(IQO_CUDA_E_NOMEM, "cannot allocate %zu bytes of device staging", sBytes);
+            }
+        w->srcCap = sBytes;
+    }
+    if (w->dstCap < dBytes) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(w->dDst[i]);
+            w->dDst[i] = 0;
+        }
+        w->dstCap = 0;
+        for (int i = 0; i < 2; ++i)
+            if (cudaMalloc(&w->dDst[i], dBytes) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(IQO_CUDA_E_NOMEM, "cannot allocate %zu bytes of device staging", dBytes);
+            }
+        w->dstCap = dBytes;
     }
     r->slotFrames = frames;
     return IQO_CUDA_OK;
+}
+
+// ---- plan cache and workspace pool (process wide, never destroyed: no static-destruction
+// order problems with the CUDA runtime) ----
+struct PlanKey {
+    int device, kind;
+    unsigned degree;
+    size_t sw, sh, dw, dh, px;
+    bool operator<(const PlanKey &o) const
+    {
+        return std::tie(device, kind, degree, sw, sh, dw, dh, px) < std::tie(o.device, o.kind, o.degree, o.sw, o.sh, o.dw, o.dh, o.px);
+    }
+};
+
+struct Registry {
+    std::mutex mu;
+    std::map<PlanKey, std::shared_ptr<SharedPlan> > plans;
+    std::vector<PlanKey> order;  // insertion order, for eviction
+    std::vector<Workspace *> freeWs;
+};
+
+Registry &registry()
+{
+    static Registry *g = new Registry();
+    return *g;
+}
+
+const size_t kMaxCachedPlans = 32, kMaxPooledWorkspaces = 16;
+
+int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsigned degree, size_t srcW, size_t srcH,
+                    size_t dstW, size_t dstH, size_t pxScale)
+{
+    std::shared_ptr<SharedPlan> sp(new SharedPlan());
+    sp->device = device;
+    int rc = buildPlan(sp->plan, kind, degree, srcW, srcH, dstW, dstH, pxScale);
+    if (rc != kPlanOk) return fail(rc, "%s", sp->plan.error.c_str());  // PlanError values equal the IQO_CUDA_E_* codes
+    {
+        cudaError_t e = initKernels();
+        if (e != cudaSuccess) return fail(IQO_CUDA_E_CUDA, "kernel setup failed: %s", cudaGetErrorString(e));
+    }
+    rc = uploadAxis(sp->plan.x, sp->tx);
+    if (rc == IQO_CUDA_OK) rc = uploadAxis(sp->plan.y, sp->ty);
+    if (rc != IQO_CUDA_OK) return rc;
+    buildHalfPlan(sp->plan, sp->half);
+    if (sp->half.eligible) {
+        const HalfPlan &hp = sp->half;
+        const size_t b0 = hp.borderY.size() * 4, b1 = hp.magicY.size() * 4, b2 = std::max<size_t>(4, hp.borderX.size() * 4);
+        if (cudaMalloc(&sp->dBorderY, b0) != cudaSuccess || cudaMalloc(&sp->dMagicY, b1) != cudaSuccess ||
+            cudaMalloc(&sp->dBorderX, b2) != cudaSuccess ||
+            cudaMemcpy(sp->dBorderY, hp.borderY.data(), b0, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(sp->dMagicY, hp.magicY.data(), b1, cudaMemcpyHostToDevice) != cudaSuccess ||
+            cudaMemcpy(sp->dBorderX, hp.borderX.data(), hp.borderX.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+            cudaGetLastError();
+            sp->half.eligible = false;
+        }
+    }
+    sp->geom = chooseGenericGeom(sp->plan.x.first.data(), sp->plan.x.N, int(sp->plan.x.S), int(sp->plan.x.D));
+    out = sp;
+    return IQO_CUDA_OK;
+}
+
+int acquireWorkspace(Workspace *&out, int device)
+{
+    Registry &g = registry();
+    {
+        std::lock_guard<std::mutex> lock(g.mu);
+        for (size_t i = 0; i < g.freeWs.size(); ++i)
+            if (g.freeWs[i]->device == device) {
+                out = g.freeWs[i];
+                g.freeWs.erase(g.freeWs.begin() + i);
+                return IQO_CUDA_OK;
+            }
+    }
+    Workspace *w = new Workspace();
+    w->device = device;
+    for (int i = 0; i < 2; ++i)
+        if (cudaStreamCreateWithFlags(&w->stream[i], cudaStreamNonBlocking) != cudaSuccess) {
+            const char *msg = cudaGetErrorString(cudaGetLastError());
+            for (int j = 0; j < i; ++j) cudaStreamDestroy(w->stream[j]);
+            delete w;
+            return fail(IQO_CUDA_E_CUDA, "stream creation failed: %s", msg);
+        }
+    out = w;
+    return IQO_CUDA_OK;
+}
+
+void destroyWorkspace(Workspace *w)
+{
+    for (int i = 0; i < 2; ++i) {
+        if (w->stream[i]) cudaStreamDestroy(w->stream[i]);
+        cudaFree(w->dSrc[i]);
+        cudaFree(w->dDst[i]);
+    }
+    cudaGetLastError();
+    delete w;
 }
 
 }  // namespace
@@ -346,64 +503,63 @@ int iqo_cuda_create_on(iqo_cuda_resizer **out, int device, int kind, unsigned de
 {
     if (!out) return fail(IQO_CUDA_E_ARG, "NULL output handle");
     *out = 0;
-    iqo_cuda_resizer *r = new iqo_cuda_resizer();
-    int rc = buildPlan(r->plan, kind, degree, srcW, srcH, dstW, dstH, pxScale);
-    if (rc != kPlanOk) {
-        std::string msg = r->plan.error;
-        delete r;
-        return fail(rc, "%s", msg.c_str());  // PlanError values equal the IQO_CUDA_E_* codes
+    if (kind != IQO_CUDA_LANCZOS) {
+        degree = 0;  // ignored by Area / Linear: do not let it split the plan cache
+        pxScale = 1;
+    }
+    {
+        // argument errors first, so that they are reported as such even without a device
+        Plan probe;
+        if (kind < 0 || kind > 2 || !srcW || !srcH || !dstW || !dstH || (kind == IQO_CUDA_LANCZOS && (!degree || !pxScale))) {
+            int rc = buildPlan(probe, kind, degree, srcW, srcH, dstW, dstH, pxScale);
+            return fail(rc, "%s", probe.error.c_str());
+        }
     }
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
         cudaGetLastError();
-        delete r;
+        Plan probe;
+        int rc = buildPlan(probe, kind, degree, srcW, srcH, dstW, dstH, pxScale);
+        if (rc != kPlanOk) return fail(rc, "%s", probe.error.c_str());
         return fail(IQO_CUDA_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
     }
-    if (device < 0 || device >= ndev) {
-        delete r;
-        return fail(IQO_CUDA_E_ARG, "device %d out of range (0..%d)", device, ndev - 1);
-    }
-    r->device = device;
+    if (device < 0 || device >= ndev) return fail(IQO_CUDA_E_ARG, "device %d out of range (0..%d)", device, ndev - 1);
     DeviceGuard guard(device);
-    if (!guard.ok) {
-        delete r;
-        return fail(IQO_CUDA_E_CUDA, "cannot select device %d", device);
-    }
-    rc = IQO_CUDA_OK;
+    if (!guard.ok) return fail(IQO_CUDA_E_CUDA, "cannot select device %d", device);
+
+    Registry &g = registry();
+    const PlanKey key = {device, kind, degree, srcW, srcH, dstW, dstH, pxScale};
+    std::shared_ptr<SharedPlan> sp;
     {
-        cudaError_t e = initKernels();
-        if (e != cudaSuccess) rc = fail(IQO_CUDA_E_CUDA, "kernel setup failed: %s", cudaGetErrorString(e));
+        std::lock_guard<std::mutex> lock(g.mu);
+        std::map<PlanKey, std::shared_ptr<SharedPlan> >::iterator it = g.plans.find(key);
+        if (it != g.plans.end()) sp = it->second;
     }
-    if (rc == IQO_CUDA_OK) rc = uploadAxis(r->plan.x, r->tx);
-    if (rc == IQO_CUDA_OK) rc = uploadAxis(r->plan.y, r->ty);
-    for (int i = 0; i < 2 && rc == IQO_CUDA_OK; ++i) {
-        if (cudaStreamCreateWithFlags(&r->stream[i], cudaStreamNonBlocking) != cudaSuccess ||
-            cudaEventCreateWithFlags(&r->evUp[i], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&r->evDone[i], cudaEventDisableTiming) != cudaSuccess)
-            rc = fail(IQO_CUDA_E_CUDA, "stream/event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
-    }
-    if (rc != IQO_CUDA_OK) {
-        std::string keep = t_lastError;
-        iqo_cuda_destroy(r);
-        t_lastError = keep;
-        return rc;
-    }
-    buildHalfPlan(r->plan, r->half);
-    if (r->half.eligible) {
-        DeviceGuard g2(device);
-        const HalfPlan &hp = r->half;
-        const size_t b0 = hp.borderY.size() * 4, b1 = hp.magicY.size() * 4, b2 = std::max<size_t>(4, hp.borderX.size() * 4);
-        if (cudaMalloc(&r->dBorderY, b0) != cudaSuccess || cudaMalloc(&r->dMagicY, b1) != cudaSuccess ||
-            cudaMalloc(&r->dBorderX, b2) != cudaSuccess ||
-            cudaMemcpy(r->dBorderY, hp.borderY.data(), b0, cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(r->dMagicY, hp.magicY.data(), b1, cudaMemcpyHostToDevice) != cudaSuccess ||
-            cudaMemcpy(r->dBorderX, hp.borderX.data(), hp.borderX.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
-            cudaGetLastError();
-            r->half.eligible = false;
+    if (!sp) {
+        int rc = buildSharedPlan(sp, device, kind, degree, srcW, srcH, dstW, dstH, pxScale);
+        if (rc != IQO_CUDA_OK) return rc;
+        std::lock_guard<std::mutex> lock(g.mu);
+        if (g.plans.find(key) == g.plans.end()) {
+            // evict the oldest plans that no handle uses any more
+            for (size_t i = 0; g.plans.size() >= kMaxCachedPlans && i < g.order.size();) {
+                std::map<PlanKey, std::shared_ptr<SharedPlan> >::iterator old = g.plans.find(g.order[i]);
+                if (old != g.plans.end() && old->second.use_count() == 1) {
+                    g.plans.erase(old);
+                    g.order.erase(g.order.begin() + i);
+                } else {
+                    ++i;
+                }
+            }
+            g.plans[key] = sp;
+            g.order.push_back(key);
+        } else {
+            sp = g.plans[key];  // another thread built it meanwhile
         }
     }
-    r->geom = chooseGenericGeom(r->plan.x.first.data(), r->plan.x.N, int(r->plan.x.S), int(r->plan.x.D));
-    *out = r;
+    Workspace *ws = 0;
+    int rc = acquireWorkspace(ws, device);
+    if (rc != IQO_CUDA_OK) return rc;
+    *out = new iqo_cuda_resizer(sp, ws);
     return IQO_CUDA_OK;
 }
 
@@ -413,11 +569,7 @@ int iqo_cuda_create(iqo_cuda_resizer **out, int kind, unsigned degree,
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) {
         cudaGetLastError();
-        // still run the planner so that argument errors are reported as such
-        Plan p;
-        int rc = buildPlan(p, kind, degree, srcW, srcH, dstW, dstH, pxScale);
-        if (rc != kPlanOk) return fail(rc, "%s", p.error.c_str());
-        return fail(IQO_CUDA_E_CUDA, "no CUDA device available (this library has no CPU fallback)");
+        dev = 0;  // create_on reports the missing device (after argument errors)
     }
     return iqo_cuda_create_on(out, dev, kind, degree, srcW, srcH, dstW, dstH, pxScale);
 }
@@ -426,23 +578,38 @@ void iqo_cuda_destroy(iqo_cuda_resizer *r)
 {
     if (!r) return;
     DeviceGuard guard(r->device);
-    for (int i = 0; i < 2; ++i) {
-        if (r->stream[i]) {
-            cudaStreamSynchronize(r->stream[i]);
-            cudaStreamDestroy(r->stream[i]);
-        }
-        if (r->evUp[i]) cudaEventDestroy(r->evUp[i]);
-        if (r->evDone[i]) cudaEventDestroy(r->evDone[i]);
-        cudaFree(r->dSrc[i]);
-        cudaFree(r->dDst[i]);
-    }
-    freeAxis(r->tx);
-    freeAxis(r->ty);
-    cudaFree(r->dBorderY);
-    cudaFree(r->dMagicY);
-    cudaFree(r->dBorderX);
+    Workspace *w = r->ws;
+    for (int i = 0; i < 2; ++i) cudaStreamSynchronize(w->stream[i]);
     cudaGetLastError();
+    Registry &g = registry();
+    bool pooled = false;
+    {
+        std::lock_guard<std::mutex> lock(g.mu);
+        // huge staging buffers are not worth keeping around
+        if (g.freeWs.size() < kMaxPooledWorkspaces && w->srcCap + w->dstCap <= (size_t(256) << 20)) {
+            g.freeWs.push_back(w);
+            pooled = true;
+        }
+    }
+    if (!pooled) destroyWorkspace(w);
     delete r;
+}
+
+// Drop every cached plan and pooled workspace (tests; before cudaDeviceReset).
+void iqo_cuda_clear_cache(void)
+{
+    Registry &g = registry();
+    std::vector<Workspace *> ws;
+    {
+        std::lock_guard<std::mutex> lock(g.mu);
+        ws.swap(g.freeWs);
+        g.plans.clear();
+        g.order.clear();
+    }
+    for (size_t i = 0; i < ws.size(); ++i) {
+        DeviceGuard guard(ws[i]->device);
+        destroyWorkspace(ws[i]);
+    }
 }
 
 int iqo_cuda_sync(iqo_cuda_resizer *r)
@@ -647,6 +814,131 @@ int iqo_cuda_resize(iqo_cuda_resizer *r, size_t srcSt, const uint8_t *src, size_
     if (rc) return rc;
     if (!dstDev) CUDA_TRY(cudaMemcpy2DAsync(dst, dstSt, r->dDst[0], r->dstPitch, DW, DH, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    return IQO_CUDA_OK;
+}
+
+// ---- planar YUV420 ----
+
+}  // extern "C" (the struct below is C++)
+
+struct iqo_cuda_yuv420 {
+    iqo_cuda_resizer *luma, *chroma;
+    size_t srcStX, srcStY, dstStX, dstStY;
+    size_t srcSizeY, srcSizeU, srcSize, dstSizeY, dstSizeU, dstSize;
+    uint8_t *dIn[2], *dOut[2];
+    size_t slotFrames;
+};
+
+namespace {
+
+int yuvLaunch(iqo_cuda_yuv420 *h, size_t n, const uint8_t *src, uint8_t *dst, cudaStream_t s)
+{
+    iqo_cuda_resizer *y = h->luma, *c = h->chroma;
+    int rc = launch(y, n, 0, size_t(y->plan.y.D), 0, size_t(y->plan.y.S), h->srcStX, h->srcSize, src, h->dstStX, h->dstSize, dst, s);
+    for (int p = 0; p < 2 && rc == IQO_CUDA_OK; ++p)
+        rc = launch(c, n, 0, size_t(c->plan.y.D), 0, size_t(c->plan.y.S), h->srcStX / 2, h->srcSize,
+                    src + h->srcSizeY + p * h->srcSizeU, h->dstStX / 2, h->dstSize, dst + h->dstSizeY + p * h->dstSizeU, s);
+    return rc;
+}
+
+}  // namespace
+
+extern "C" {
+
+int iqo_cuda_yuv420_create(iqo_cuda_yuv420 **out, int kind, unsigned degree, size_t srcW, size_t srcH, size_t dstW, size_t dstH)
+{
+    if (!out) return fail(IQO_CUDA_E_ARG, "NULL output handle");
+    *out = 0;
+    if (!srcW || !srcH || !dstW || !dstH) return fail(IQO_CUDA_E_ARG, "image sizes must be non-zero");
+    iqo_cuda_yuv420 *h = new iqo_cuda_yuv420();
+    memset(h, 0, sizeof *h);
+    h->srcStX = srcW + srcW % 2;
+    h->srcStY = srcH + srcH % 2;
+    h->dstStX = dstW + dstW % 2;
+    h->dstStY = dstH + dstH % 2;
+    h->srcSizeY = h->srcStX * h->srcStY;
+    h->srcSizeU = h->srcSizeY / 4;
+    h->srcSize = h->srcSizeY + 2 * h->srcSizeU;
+    h->dstSizeY = h->dstStX * h->dstStY;
+    h->dstSizeU = h->dstSizeY / 4;
+    h->dstSize = h->dstSizeY + 2 * h->dstSizeU;
+    int rc = iqo_cuda_create(&h->luma, kind, degree, srcW, srcH, dstW, dstH, 1);
+    if (rc == IQO_CUDA_OK)
+        rc = iqo_cuda_create(&h->chroma, kind, degree, h->srcStX / 2, h->srcStY / 2, h->dstStX / 2, h->dstStY / 2, 2);
+    if (rc != IQO_CUDA_OK) {
+        std::string keep = t_lastError;
+        iqo_cuda_yuv420_destroy(h);
+        t_lastError = keep;
+        return rc;
+    }
+    *out = h;
+    return IQO_CUDA_OK;
+}
+
+void iqo_cuda_yuv420_destroy(iqo_cuda_yuv420 *h)
+{
+    if (!h) return;
+    if (h->luma) {
+        DeviceGuard guard(h->luma->device);
+        cudaStreamSynchronize(h->luma->stream[0]);
+        cudaStreamSynchronize(h->luma->stream[1]);
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(h->dIn[i]);
+            cudaFree(h->dOut[i]);
+        }
+        cudaGetLastError();
+    }
+    iqo_cuda_destroy(h->luma);
+    iqo_cuda_destroy(h->chroma);
+    delete h;
+}
+
+int iqo_cuda_yuv420_frame_bytes(const iqo_cuda_yuv420 *h, size_t *srcBytes, size_t *dstBytes)
+{
+    if (!h) return fail(IQO_CUDA_E_ARG, "NULL handle");
+    if (srcBytes) *srcBytes = h->srcSize;
+    if (dstBytes) *dstBytes = h->dstSize;
+    return IQO_CUDA_OK;
+}
+
+int iqo_cuda_yuv420_resize(iqo_cuda_yuv420 *h, size_t nFrames, const uint8_t *src, uint8_t *dst, void *stream)
+{
+    if (!h) return fail(IQO_CUDA_E_ARG, "NULL handle");
+    if (!src || !dst) return fail(IQO_CUDA_E_ARG, "NULL image pointer");
+    if (nFrames == 0) return IQO_CUDA_OK;
+    DeviceGuard guard(h->luma->device);
+    const bool srcDev = isDevicePointer(src), dstDev = isDevicePointer(dst);
+    if (srcDev && dstDev) return yuvLaunch(h, nFrames, src, dst, (cudaStream_t)stream);
+    if (srcDev != dstDev) return fail(IQO_CUDA_E_ARG, "src and dst must both be host or both be device memory");
+    // host frames: double-buffered chunks on the luma handle's two streams
+    size_t chunk = std::max<size_t>(1, (size_t(96) << 20) / (h->srcSize + h->dstSize));
+    chunk = std::min(chunk, nFrames);
+    if (h->slotFrames < chunk) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(h->dIn[i]);
+            cudaFree(h->dOut[i]);
+            h->dIn[i] = h->dOut[i] = 0;
+        }
+        h->slotFrames = 0;
+        for (int i = 0; i < 2; ++i)
+            if (cudaMalloc(&h->dIn[i], chunk * h->srcSize) != cudaSuccess || cudaMalloc(&h->dOut[i], chunk * h->dstSize) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(IQO_CUDA_E_NOMEM, "cannot allocate YUV staging for %zu frames", chunk);
+            }
+        h->slotFrames = chunk;
+    }
+    int slot = 0;
+    for (size_t done = 0; done < nFrames; slot ^= 1) {
+        const size_t n = std::min(chunk, nFrames - done);
+        cudaStream_t s = h->luma->stream[slot];
+        CUDA_TRY(cudaMemcpyAsync(h->dIn[slot], src + done * h->srcSize, n * h->srcSize, cudaMemcpyHostToDevice, s));
+        int rc = yuvLaunch(h, n, h->dIn[slot], h->dOut[slot], s);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpyAsync(dst + done * h->dstSize, h->dOut[slot], n * h->dstSize, cudaMemcpyDeviceToHost, s));
+        done += n;
+    }
+    CUDA_TRY(cudaStreamSynchronize(h->luma->stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(h->luma->stream[1]));
     return IQO_CUDA_OK;
 }
 

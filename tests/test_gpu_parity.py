@@ -269,3 +269,106 @@ def test_half_kernel_device_pitches():
             torch.cuda.synchronize()
             assert r.last_kernel() == expect
         assert np.array_equal(ddst.cpu().numpy(), want), pitch
+
+
+# ---------------------------------------------------------------------------------------------
+# YUV420 frames, command line tools, plan cache
+# ---------------------------------------------------------------------------------------------
+import os
+import subprocess
+
+BIN = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "build", "bin")
+
+
+def yuv_layout(w, h):
+    stx, sty = w + w % 2, h + h % 2
+    return stx, sty, stx * sty, stx * sty // 4
+
+
+def oracle_yuv420(kind, deg, frame, sw, sh, dw, dh):
+    """Per-plane oracle of one planar frame, exactly as sample/resize_yuv420p.cpp:125-163 calls the classes."""
+    sx, sy, ssy, ssu = yuv_layout(sw, sh)
+    dx, dy, dsy, dsu = yuv_layout(dw, dh)
+    out = np.zeros(dsy + 2 * dsu, dtype=np.uint8)
+    rc, y = oracle_resize(kind, frame[:ssy].reshape(sy, sx), dw, dh, deg, 1, sw=sw, dst_stride=dx)
+    assert rc == 0
+    out[:dh * dx] = y.ravel()
+    for p in range(2):
+        plane = frame[ssy + p * ssu: ssy + (p + 1) * ssu].reshape(sy // 2, sx // 2)
+        rc, c = oracle_resize(kind, plane, dx // 2, dy // 2, deg, 2, dst_stride=dx // 2)
+        assert rc == 0
+        out[dsy + p * dsu: dsy + (p + 1) * dsu] = c.ravel()
+    return out
+
+
+@pytest.mark.parametrize("case", [(LANCZOS, 2, 384, 216, 192, 108), (LANCZOS, 3, 386, 218, 258, 146),
+                                  (AREA, 0, 384, 216, 192, 108), (LINEAR, 0, 128, 72, 384, 216)])
+def test_yuv420_frames(case):
+    torch = pytest.importorskip("torch")
+    kind, deg, sw, sh, dw, dh = case
+    n = 3
+    with iqo.Yuv420Resizer(kind, deg, sw, sh, dw, dh) as r:
+        src = lcg_image(n, r.src_frame_bytes, seed=9)
+        want = np.stack([oracle_yuv420(kind, deg, src[f], sw, sh, dw, dh) for f in range(n)])
+        dst = np.zeros((n, r.dst_frame_bytes), dtype=np.uint8)
+        r.resize(n, src, dst)                       # host frames
+        assert np.array_equal(dst, want)
+        dsrc = torch.from_numpy(src).cuda()         # device frames, three launches on torch's stream
+        ddst = torch.zeros((n, r.dst_frame_bytes), dtype=torch.uint8, device="cuda")
+        r.resize(n, dsrc, ddst, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(ddst.cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("method,kind,deg", [("lanczos2", LANCZOS, 2), ("area", AREA, 0)])
+def test_cli_resize_yuv420p(tmp_path, method, kind, deg):
+    sw, sh, dw, dh = 384, 216, 192, 108
+    sx, sy, ssy, ssu = yuv_layout(sw, sh)
+    frame = lcg_image(1, ssy + 2 * ssu, seed=21)[0]
+    want = oracle_yuv420(kind, deg, frame, sw, sh, dw, dh)
+    fin = tmp_path / "in.yuv"
+    frame.tofile(fin)
+    tools = ["resize_yuv420p"]
+    if os.path.exists(os.path.join(BIN, "ref_resize_yuv420p")):
+        tools.append("ref_resize_yuv420p")   # the reference's own sample source, linked to this backend
+    for tool in tools:
+        fout = tmp_path / (tool + ".yuv")
+        out = subprocess.run([os.path.join(BIN, tool), "-m", method, "-i", str(fin), "-iw", str(sw), "-ih", str(sh),
+                              "-o", str(fout), "-ow", str(dw), "-oh", str(dh)], capture_output=True, text=True)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "size: %dx%d" % (sw, sh) in out.stdout
+        got = np.fromfile(fout, dtype=np.uint8)
+        assert np.array_equal(got, want), tool
+
+
+def test_cli_benchmark_runs():
+    for tool in ("benchmark", "ref_benchmark"):
+        exe = os.path.join(BIN, tool)
+        if not os.path.exists(exe):
+            continue
+        out = subprocess.run([exe, "-m", "lanczos3", "-iw", "640", "-ih", "360", "-ow", "320", "-oh", "180"],
+                             capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stdout + out.stderr
+        assert "elapsed time:" in out.stdout and "ms/cycle" in out.stdout
+
+
+def test_plan_cache_and_workspace_pool():
+    import time
+    src = lcg_image(108, 192, seed=5)
+    rc, want = oracle_resize(LANCZOS, src, 96, 54, 3)
+    dst = np.zeros((54, 96), dtype=np.uint8)
+    with iqo.LanczosResizer(3, 192, 108, 96, 54) as r:   # builds and caches the plan
+        r.resize(192, src, 96, dst)
+    t0 = time.perf_counter()
+    for _ in range(200):                                  # the reference benchmark's pattern
+        dst[:] = 0
+        with iqo.LanczosResizer(3, 192, 108, 96, 54) as r:
+            r.resize(192, src, 96, dst)
+        assert np.array_equal(dst, want)
+    per_cycle = (time.perf_counter() - t0) / 200
+    assert per_cycle < 5e-3, per_cycle
+    iqo.lib().iqo_cuda_clear_cache()
+    with iqo.LanczosResizer(3, 192, 108, 96, 54) as r:
+        dst[:] = 0
+        r.resize(192, src, 96, dst)
+    assert np.array_equal(dst, want)

@@ -54,6 +54,8 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--path", default="auto", choices=["auto", "generic"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every GPU gets the workload's frame count; strong: that count is sharded over the GPUs")
     return ap.parse_args()
 
 
@@ -208,6 +210,16 @@ def visible_physical_index(local_rank):
 # ----------------------------------------------------------------------------- CUDA arm
 
 def run_cuda(args):
+    # libraries (NCCL's version banner, ...) may print to stdout: keep fd 1 for the JSON line only
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        return _run_cuda(args, json_fd)
+    finally:
+        os.close(json_fd)
+
+
+def _run_cuda(args, json_fd):
     import numpy as np
     import torch
     import libiqo_b200 as iqo
@@ -227,6 +239,9 @@ def run_cuda(args):
     work = WORKLOADS[args.workload]
     kind, deg, px, sw, sh, dw, dh, default_frames = work
     frames = args.frames or default_frames
+    if args.scaling == "strong":
+        from libiqo_b200.sharding import frame_shard
+        frames = frame_shard(frames, world, rank)[1]
     dev = torch.device("cuda", local)
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
@@ -268,7 +283,10 @@ def run_cuda(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     ms_step = ms_total / args.steps
-    total_px = float(frames) * dw * dh * world
+    nframes_all = torch.tensor([float(frames)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(nframes_all)
+    total_px = float(nframes_all.item()) * dw * dh
     value = total_px / (ms_step * 1e-3) / 1e6
     kernel_name = r.last_kernel()
 
@@ -354,7 +372,7 @@ def run_cuda(args):
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
         "config": {"workload": args.workload, "frames_per_gpu": frames, "src": [sw, sh], "dst": [dw, dh],
                    "kernel": kernel_name, "sharding": "independent frames per GPU, no collective",
@@ -364,7 +382,7 @@ def run_cuda(args):
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary() if sampler else None, "parity": parity,
     }
-    print(json.dumps(line), flush=True)
+    os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
     return 0

@@ -98,12 +98,21 @@ size_t alignUp(size_t v, size_t a)
 struct SharedPlan {
     Plan plan;
     HalfPlan half;
+    PackedPlan packed;
     GenericGeom geom;
+    PackedGeom pgeom;
     int device;
     AxisTables tx, ty;
     uint32_t *dBorderY, *dMagicY;
     int32_t *dBorderX;
-    SharedPlan() : device(0), dBorderY(0), dMagicY(0), dBorderX(0) {}
+    // packed kernel tables
+    int32_t *pFirstY, *pNtapY, *pCoefOffY, *pFirstX, *pAccInitX, *pDivX;
+    uint32_t *pMagicY, *pCwX;
+    SharedPlan()
+        : device(0), dBorderY(0), dMagicY(0), dBorderX(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pFirstX(0), pAccInitX(0),
+          pDivX(0), pMagicY(0), pCwX(0)
+    {
+    }
     ~SharedPlan();
 };
 
@@ -181,10 +190,26 @@ SharedPlan::~SharedPlan()
     cudaFree(dBorderY);
     cudaFree(dMagicY);
     cudaFree(dBorderX);
+    cudaFree(pFirstY);
+    cudaFree(pNtapY);
+    cudaFree(pCoefOffY);
+    cudaFree(pFirstX);
+    cudaFree(pAccInitX);
+    cudaFree(pDivX);
+    cudaFree(pMagicY);
+    cudaFree(pCwX);
     cudaGetLastError();
 }
 
 namespace {
+
+template <typename T>
+bool uploadVec(T *&dptr, const std::vector<T> &v)
+{
+    const size_t bytes = std::max<size_t>(sizeof(T), v.size() * sizeof(T));
+    if (cudaMalloc(&dptr, bytes) != cudaSuccess) return false;
+    return v.empty() || cudaMemcpy(dptr, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice) == cudaSuccess;
+}
 
 AxisDev axisDev(const AxisPlan &a, const AxisTables &t)
 {
@@ -304,6 +329,50 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         }
         return IQO_CUDA_OK;
     }
+    const SharedPlan &sp = *r->sp;
+    if (r->path == IQO_CUDA_PATH_AUTO && sp.packed.eligible && ((uintptr_t)src % 4) == 0 && srcSt % 4 == 0 &&
+        srcFrameStride % 4 == 0 && dstRows <= size_t(65535) * sp.pgeom.tileH) {
+        PackedArgs q;
+        q.srcPitch = (long long)srcSt;
+        q.dstPitch = (long long)dstSt;
+        q.srcFrameStride = (long long)srcFrameStride;
+        q.dstFrameStride = (long long)dstFrameStride;
+        q.SW = int(r->plan.x.S);
+        q.SH = int(r->plan.y.S);
+        q.DW = int(r->plan.x.D);
+        q.DH = int(r->plan.y.D);
+        q.srcRow0 = int(srcRow0);
+        q.dstRow0 = int(dstRow0);
+        q.dstRows = int(dstRows);
+        q.tileW = sp.pgeom.tileW;
+        q.tileH = sp.pgeom.tileH;
+        q.wordsPerRow = sp.pgeom.wordsPerRow;
+        q.shift = r->plan.shift;
+        q.isSigned = r->plan.workSigned;
+        q.workBias = sp.packed.workBias;
+        q.firstY = sp.pFirstY;
+        q.ntapY = sp.pNtapY;
+        q.coefOffY = sp.pCoefOffY;
+        q.coefY = sp.ty.coef;
+        q.rowY = sp.ty.row;
+        q.denoY = sp.ty.deno;
+        q.magicY = sp.pMagicY;
+        q.firstX = sp.pFirstX;
+        q.rowX = sp.tx.row;
+        q.accInitX = sp.pAccInitX;
+        q.divX = sp.pDivX;
+        q.cwX = sp.pCwX;
+        q.NX = r->plan.x.N;
+        q.NP = sp.packed.NP;
+        r->lastKernel = "packed";
+        for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
+            q.nFrames = int(std::min<size_t>(65535, nFrames - f0));
+            q.src = src + f0 * srcFrameStride;
+            q.dst = dst + f0 * dstFrameStride;
+            CUDA_TRY(launchPacked(q, stream));
+        }
+        return IQO_CUDA_OK;
+    }
     r->lastKernel = "generic";
     CUDA_TRY(launchGeneric(a, r->geom, stream));
     return IQO_CUDA_OK;
@@ -411,6 +480,18 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
         }
     }
     sp->geom = chooseGenericGeom(sp->plan.x.first.data(), sp->plan.x.N, int(sp->plan.x.S), int(sp->plan.x.D));
+    buildPackedPlan(sp->plan, sp->packed);
+    if (sp->packed.eligible) {
+        const PackedPlan &q = sp->packed;
+        if (!uploadVec(sp->pFirstY, q.firstY) || !uploadVec(sp->pNtapY, q.ntapY) || !uploadVec(sp->pCoefOffY, q.coefOffY) ||
+            !uploadVec(sp->pMagicY, q.magicY) || !uploadVec(sp->pFirstX, q.firstX) || !uploadVec(sp->pCwX, q.cwX) ||
+            !uploadVec(sp->pAccInitX, q.accInitX) || !uploadVec(sp->pDivX, q.divX)) {
+            cudaGetLastError();
+            sp->packed.eligible = false;
+        } else {
+            sp->pgeom = choosePackedGeom(q.firstX.data(), sp->plan.x.N, int(sp->plan.x.S), int(sp->plan.x.D));
+        }
+    }
     out = sp;
     return IQO_CUDA_OK;
 }
@@ -678,8 +759,11 @@ int iqo_cuda_plan_kernel(int kind, unsigned degree, size_t srcW, size_t srcH, si
     if (rc != kPlanOk) return fail(rc, "%s", p.error.c_str());
     HalfPlan h;
     buildHalfPlan(p, h);
-    if (kernel && kernelCap) snprintf(kernel, kernelCap, "%s", h.eligible ? (h.symmetric ? "half_sym" : "half") : "generic");
-    if (why && whyCap) snprintf(why, whyCap, "%s", h.why.c_str());
+    PackedPlan q;
+    buildPackedPlan(p, q);
+    if (kernel && kernelCap)
+        snprintf(kernel, kernelCap, "%s", h.eligible ? (h.symmetric ? "half_sym" : "half") : q.eligible ? "packed" : "generic");
+    if (why && whyCap) snprintf(why, whyCap, "%s%s%s", h.why.c_str(), q.eligible ? "" : "; packed: ", q.eligible ? "" : q.why.c_str());
     return IQO_CUDA_OK;
 }
 

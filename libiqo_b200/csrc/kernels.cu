@@ -635,6 +635,130 @@ cudaError_t launchHalfT(const HalfArgs &a, const CUtensorMap *tmap, int boxRows,
     return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------
+// General packed kernel: any kind, ratio, phase count (plan.hpp PackedPlan).
+//
+//  vertical pass   a thread owns 4 adjacent source columns (one aligned 32-bit word per source
+//                  row) of one destination row.  The four bytes are spread into two registers of
+//                  two 16-bit lanes (2 PRMT) and each tap is ONE multiply-add per register:
+//                  (b1 * 2^16 + b0) * c accumulates both columns at once.  The planner proves that
+//                  every partial sum, after a bias, stays inside [0, 65535], so no carry or
+//                  borrow ever crosses the lanes and the arithmetic equals two independent
+//                  16-bit sums -- which is exactly the packed layout the horizontal pass wants.
+//                  Out-of-image taps were trimmed by the planner: no index is clamped.
+//  horizontal pass one pixel per lane: dp2a over the 16-bit pairs of its window against
+//                  planner-packed coefficient words (low / high byte planes, one variant per
+//                  parity of the window start), one shift, clamp, byte store (a warp writes 32
+//                  consecutive bytes).  Lanczos border columns divide instead of shifting.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int dp2a_hi_uu(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp2a.hi.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+template <bool SIGNED>
+__global__ void __launch_bounds__(256) resizePackedKernel(const __grid_constant__ PackedArgs a)
+{
+    extern __shared__ __align__(16) uint32_t Wp[];
+    const int tx0 = blockIdx.x * a.tileW;
+    const int ty0 = blockIdx.y * a.tileH;
+    const int tw = min(a.tileW, a.DW - tx0);
+    const int th = min(a.tileH, a.dstRows - ty0);
+    const uint8_t *__restrict__ src = a.src + (long long)blockIdx.z * a.srcFrameStride;
+    uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int B = a.workBias;
+
+    // source column window of the tile; firstX is non-decreasing and >= 0
+    const int x0 = __ldg(a.firstX + tx0) & ~3;
+    const int x1 = min(__ldg(a.firstX + tx0 + tw - 1) + a.NX - 1, a.SW - 1);
+    const int words = ((x1 - x0) >> 2) + 1;  // 4-column words this tile reads per source row
+
+    // ================= vertical pass =================
+    for (int r = warp; r < th; r += 8) {
+        const int y = a.dstRow0 + ty0 + r;
+        const int fy = __ldg(a.firstY + y) - a.srcRow0;
+        const int nt = __ldg(a.ntapY + y);
+        const int32_t *__restrict__ cy = a.coefY + __ldg(a.coefOffY + y);
+        int deno = 0;
+        uint32_t magic = 0;
+        if (SIGNED) {
+            const int row = __ldg(a.rowY + y);
+            deno = __ldg(a.denoY + row);
+            magic = __ldg(a.magicY + row);
+        }
+        const uint32_t init = deno ? 0u : ((uint32_t)B | ((uint32_t)B << 16));
+        for (int cw = lane; cw < words; cw += 32) {
+            const uint8_t *ptr = src + (long long)fy * a.srcPitch + (x0 + 4 * cw);
+            uint32_t acc01 = init, acc23 = init;
+            for (int i = 0; i < nt; ++i) {
+                const uint32_t word = __ldg(reinterpret_cast<const uint32_t *>(ptr));
+                ptr += a.srcPitch;
+                const uint32_t c = (uint32_t)__ldg(cy + i);
+                acc01 += prmt(word, 0u, 0x4140) * c;  // lanes (col 0, col 1)
+                acc23 += prmt(word, 0u, 0x4342) * c;  // lanes (col 2, col 3)
+            }
+            if (SIGNED && deno) {
+                // resizeYborder: the numerator lanes are genuine int16 sums here (no bias was
+                // added); work = int16(nume * 64 / deno), C division via multiply-high
+                auto bdiv = [&](uint32_t lanes) -> uint32_t {
+                    uint32_t out = 0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int n = (int)(short)(lanes >> (16 * h)) * 64;
+                        const uint32_t m = (uint32_t)abs(n);
+                        const int qv = magic ? (int)__umulhi(m, magic) : (int)m;
+                        const int w = (int)(short)(n < 0 ? -qv : qv) + B;
+                        out |= ((uint32_t)w & 0xffffu) << (16 * h);
+                    }
+                    return out;
+                };
+                // un-bias is not needed (init was 0 for this row) but negative lanes borrowed from
+                // their neighbour: redo the two lanes separately from the packed sum
+                const uint32_t lo0 = acc01 & 0xffffu, hi0 = (acc01 >> 16) + ((lo0 & 0x8000u) ? 1u : 0u);
+                const uint32_t lo1 = acc23 & 0xffffu, hi1 = (acc23 >> 16) + ((lo1 & 0x8000u) ? 1u : 0u);
+                acc01 = bdiv(lo0 | (hi0 << 16));
+                acc23 = bdiv(lo1 | (hi1 << 16));
+            }
+            *reinterpret_cast<uint2 *>(Wp + r * a.wordsPerRow + 2 * cw) = make_uint2(acc01, acc23);
+        }
+    }
+    __syncthreads();
+
+    // ================= horizontal pass =================
+    const int half = 1 << (a.shift - 1);
+    (void)half;
+    for (int r = warp; r < th; r += 8) {
+        const uint32_t *wr = Wp + r * a.wordsPerRow;
+        uint8_t *out = dst + (long long)(ty0 + r) * a.dstPitch + tx0;
+        for (int dx = lane; dx < tw; dx += 32) {
+            const int d = tx0 + dx;
+            const int e0 = __ldg(a.firstX + d) - x0;
+            const int row = __ldg(a.rowX + d);
+            const uint32_t *__restrict__ cw = a.cwX + (long long)(row * 2 + (e0 & 1)) * a.NP;
+            const uint32_t *wp = wr + (e0 >> 1);
+            int lo = __ldg(a.accInitX + row), hi = 0;
+            for (int j = 0; j < a.NP; ++j) {
+                const uint32_t c = __ldg(cw + j);
+                const uint32_t w = wp[j];
+                lo = dp2a_lo_uu(w, c, lo);
+                hi = SIGNED ? dp2a_hi_us(w, c, hi) : dp2a_hi_uu(w, c, hi);
+            }
+            const int total = lo + (hi << 8);
+            int v = total >> a.shift;
+            if (SIGNED) {
+                const int div = __ldg(a.divX + row);
+                if (div != 0) v = total / div;  // resizeXborder: truncating division by deno * 64
+            }
+            v = (int)(short)v;
+            out[dx] = (uint8_t)min(max(v, 0), 255);
+        }
+    }
+}
+
 }  // namespace
 
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D)
@@ -706,6 +830,51 @@ cudaError_t launchHalf(const HalfArgs &a, const CUtensorMap *tmap, int boxRows, 
     IQO_HALF_CASE(1, 7)
 #undef IQO_HALF_CASE
     return cudaErrorInvalidValue;
+}
+
+PackedGeom choosePackedGeom(const int32_t *firstX, int N, int S, int D)
+{
+    PackedGeom g;
+    g.tileW = 128;
+    g.tileH = 16;
+    for (;;) {
+        int widest = 1;
+        for (int t0 = 0; t0 < D; t0 += g.tileW) {
+            const int t1 = std::min(D, t0 + g.tileW) - 1;
+            const int lo = firstX[t0] & ~3;
+            const int hi = std::min(firstX[t1] + N - 1, S - 1);
+            widest = std::max(widest, ((hi - lo) >> 2) + 1);
+        }
+        // two 32-bit words per 4-column source word, plus slack for the zero-weight pair words
+        // the horizontal pass may touch beyond the last written column
+        g.wordsPerRow = (2 * widest + N / 2 + 4 + 1) & ~1;  // even: rows start 8-byte aligned
+        g.smemBytes = size_t(g.tileH) * g.wordsPerRow * 4;
+        if (g.smemBytes <= 64 * 1024 || g.tileW <= 8) break;
+        g.tileW /= 2;
+    }
+    return g;
+}
+
+cudaError_t launchPacked(const PackedArgs &a, cudaStream_t stream)
+{
+    static bool attrSet = false;
+    if (!attrSet) {
+        cudaError_t e = cudaFuncSetAttribute(resizePackedKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(resizePackedKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        if (e != cudaSuccess) return e;
+        attrSet = true;
+    }
+    const int tilesX = (a.DW + a.tileW - 1) / a.tileW;
+    const int tilesY = (a.dstRows + a.tileH - 1) / a.tileH;
+    if (tilesY > 65535) return cudaErrorInvalidConfiguration;
+    dim3 grid(tilesX, tilesY, a.nFrames);
+    const size_t smem = size_t(a.tileH) * a.wordsPerRow * 4;
+    if (a.isSigned)
+        resizePackedKernel<true><<<grid, 256, smem, stream>>>(a);
+    else
+        resizePackedKernel<false><<<grid, 256, smem, stream>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
 }
 
 int halfSourceRowsMax()

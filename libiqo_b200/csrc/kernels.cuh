@@ -76,6 +76,34 @@ struct HalfArgs {
 cudaError_t launchHalf(const HalfArgs &a, const CUtensorMap *tmap, int boxRows, cudaStream_t stream);
 int halfSourceRowsMax();
 
+// Arguments of the general packed kernel (see plan.hpp PackedPlan).
+struct PackedArgs {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long srcPitch, dstPitch, srcFrameStride, dstFrameStride;
+    int SW, SH, DW, DH;
+    int nFrames;
+    int srcRow0, dstRow0, dstRows;  // row-band mode (else 0, 0, DH)
+    int tileW, tileH, wordsPerRow;  // destination tile and the 32-bit words of one shared W row
+    int shift;                      // 20 or 23
+    int isSigned;                   // Lanczos: signed high coefficient plane, border divisions
+    int workBias;
+    // vertical
+    const int32_t *firstY, *ntapY, *coefOffY, *coefY, *rowY, *denoY;
+    const uint32_t *magicY;
+    // horizontal
+    const int32_t *firstX, *rowX, *accInitX, *divX;
+    const uint32_t *cwX;
+    int NX, NP;
+};
+
+struct PackedGeom {
+    int tileW, tileH, wordsPerRow;
+    size_t smemBytes;
+};
+PackedGeom choosePackedGeom(const int32_t *firstXClamped, int N, int S, int D);
+cudaError_t launchPacked(const PackedArgs &a, cudaStream_t stream);
+
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D);
 cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_t stream);
 cudaError_t initKernels();  // sets function attributes once per device

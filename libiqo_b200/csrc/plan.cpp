@@ -490,3 +490,117 @@ void buildHalfPlan(const Plan &p, HalfPlan &h)
 }
 
 }  // namespace iqo_b200
+
+// ---------------------------------------------------------------------------------------------
+// Plan of the general packed kernel
+// ---------------------------------------------------------------------------------------------
+namespace iqo_b200 {
+
+void buildPackedPlan(const Plan &p, PackedPlan &q)
+{
+    q.eligible = false;
+    q.why.clear();
+    const AxisPlan &X = p.x, &Y = p.y;
+    const bool isSigned = p.workSigned;
+
+    // ---- vertical: every out-of-image tap must be weightless; trim them off ----
+    q.firstY.assign(size_t(Y.D), 0);
+    q.ntapY.assign(size_t(Y.D), 0);
+    q.coefOffY.assign(size_t(Y.D), 0);
+    for (int64_t y = 0; y < Y.D; ++y) {
+        const int32_t *c = &Y.coef[size_t(Y.row[y]) * Y.N];
+        int lo = 0, hi = Y.N;  // taps [lo, hi) are inside the image
+        const int64_t f = Y.first[y];
+        if (f < 0) lo = int(std::min<int64_t>(-f, Y.N));
+        if (f + Y.N > Y.S) hi = int(std::max<int64_t>(Y.S - f, lo));
+        for (int i = 0; i < Y.N; ++i)
+            if ((i < lo || i >= hi) && c[i] != 0) { q.why = "vertical tap outside the image with non-zero weight"; return; }
+        while (lo < hi && c[lo] == 0) ++lo;            // leading / trailing zero taps cost nothing
+        while (hi > lo && c[hi - 1] == 0) --hi;
+        if (hi == lo) { lo = 0; hi = 0; }
+        q.firstY[size_t(y)] = int32_t(f + lo);
+        q.ntapY[size_t(y)] = hi - lo;
+        q.coefOffY[size_t(y)] = int32_t(size_t(Y.row[y]) * Y.N + lo);
+        if (hi == lo) q.firstY[size_t(y)] = 0;
+    }
+    // 16-bit lane range of the intermediate (border rows are rescaled by 64/deno)
+    long long wmin = 0, wmax = 0, laneMin = 0, laneMax = 0;
+    q.magicY.assign(size_t(Y.numRows), 0);
+    for (int r = 0; r < Y.numRows; ++r) {
+        long long pos = 0, neg = 0;
+        for (int i = 0; i < Y.N; ++i) {
+            const int c = Y.coef[size_t(r) * Y.N + i];
+            (c > 0 ? pos : neg) += c;
+        }
+        long long lo = 255 * neg, hi = 255 * pos;
+        laneMin = std::min(laneMin, lo);   // partial sums of the packed multiply-adds
+        laneMax = std::max(laneMax, hi);
+        if (isSigned ? (lo < -32768 || hi > 32767) : (hi > 65535)) { q.why = "vertical sum may wrap 16 bits"; return; }
+        const int den = Y.deno[size_t(r)];
+        if (den != 0) {
+            if (den < 0 || den > 255) { q.why = "border denominator out of range"; return; }
+            lo = lo * 64 / den - 1;
+            hi = hi * 64 / den + 1;
+            if (den > 1) q.magicY[size_t(r)] = uint32_t((1ull << 32) / uint64_t(den) + 1);
+        }
+        wmin = std::min(wmin, lo);
+        wmax = std::max(wmax, hi);
+    }
+    q.workBias = int(-std::min(wmin, laneMin));
+    if (std::max(wmax, laneMax) + q.workBias > 65535) { q.why = "intermediate range wider than a 16-bit lane"; return; }
+
+    // ---- horizontal ----
+    q.firstX.assign(size_t(X.D), 0);
+    q.NP = X.N / 2 + 1;
+    std::vector<int> rowShift(size_t(X.numRows), 0);  // leading taps dropped because they lie left of column 0
+    for (int64_t d = 0; d < X.D; ++d) {
+        const int r = X.row[d];
+        const int32_t *c = &X.coef[size_t(r) * X.N];
+        const int64_t f = X.first[d];
+        const int shift = f < 0 ? int(std::min<int64_t>(-f, X.N)) : 0;
+        for (int i = 0; i < X.N; ++i) {
+            const bool outside = (f + i < 0) || (f + i >= X.S);
+            if (outside && c[i] != 0) { q.why = "horizontal tap outside the image with non-zero weight"; return; }
+        }
+        if (shift != 0 && r < int(X.rD) && X.rD != X.D) {
+            // a phase row shared by several columns cannot be re-based; only planner-made
+            // per-column rows (Lanczos borders) or one-row-per-column tables get here
+            bool shared = false;
+            for (int64_t e = 0; e < X.D && !shared; ++e) shared = (e != d && X.row[e] == r);
+            if (shared) { q.why = "shared phase row starts left of the image"; return; }
+        }
+        rowShift[size_t(r)] = shift;
+        q.firstX[size_t(d)] = int32_t(f + shift);
+    }
+    q.cwX.assign(size_t(X.numRows) * 2 * q.NP, 0);
+    q.accInitX.assign(size_t(X.numRows), 0);
+    q.divX.assign(size_t(X.numRows), 0);
+    for (int r = 0; r < X.numRows; ++r) {
+        const int32_t *c = &X.coef[size_t(r) * X.N];
+        const int shift = rowShift[size_t(r)];
+        long long sum = 0;
+        for (int i = 0; i < X.N; ++i) sum += c[i];
+        for (int par = 0; par < 2; ++par) {
+            // window element i (coefficient c[shift + i]) sits in half (par + i) & 1 of word (par + i) >> 1
+            for (int w = 0; w < q.NP; ++w) {
+                const int ia = 2 * w - par, ib = 2 * w + 1 - par;  // taps in the low / high half
+                const int ca = (ia >= 0 && shift + ia < X.N) ? c[shift + ia] : 0;
+                const int cb = (ib >= 0 && shift + ib < X.N) ? c[shift + ib] : 0;
+                uint32_t la, ha, lb, hb;
+                if (isSigned) {
+                    splitPlanes(ca, la, ha);
+                    splitPlanes(cb, lb, hb);
+                } else {
+                    la = uint32_t(ca) & 0xff; ha = (uint32_t(ca) >> 8) & 0xff;
+                    lb = uint32_t(cb) & 0xff; hb = (uint32_t(cb) >> 8) & 0xff;
+                }
+                q.cwX[(size_t(r) * 2 + par) * q.NP + w] = la | (lb << 8) | (ha << 16) | (hb << 24);
+            }
+        }
+        q.accInitX[size_t(r)] = int32_t((1ll << (p.shift - 1)) - (long long)q.workBias * sum);
+        q.divX[size_t(r)] = X.deno[size_t(r)] * 64;
+    }
+    q.eligible = true;
+}
+
+}  // namespace iqo_b200

@@ -99,3 +99,28 @@ struct HalfPlan {
 void buildHalfPlan(const Plan &plan, HalfPlan &h);
 
 }  // namespace iqo_b200
+
+namespace iqo_b200 {
+
+// Parameters of the general "packed" kernel (kernels.cu: resizePackedKernel): any kind, ratio and
+// phase count, as long as no out-of-image tap carries a non-zero coefficient (true for every
+// input the reference defines) and the vertical sums fit 16-bit lanes.
+struct PackedPlan {
+    bool eligible;
+    std::string why;
+    int workBias;                   // added to every intermediate: lanes stay in [0, 65535]
+    // vertical pass, per destination row: taps [0, ntapY) of coefficient slice coefOffY apply to
+    // source rows firstY .. firstY+ntapY-1 (all inside the image)
+    std::vector<int32_t> firstY, ntapY, coefOffY;
+    std::vector<uint32_t> magicY;   // per coefficient row: multiply-high constant of the border division
+    // horizontal pass, per destination column: first source column (>= 0) and coefficient row
+    std::vector<int32_t> firstX;
+    int NP;                         // pair words per packed row
+    std::vector<uint32_t> cwX;      // [numRowsX][2 (parity of the window start)][NP]: bytes lo_a, lo_b, hi_a, hi_b
+    std::vector<int32_t> accInitX;  // [numRowsX]: rounding constant minus bias * (sum of the row)
+    std::vector<int32_t> divX;      // [numRowsX]: 0, or denominator * 64 of a Lanczos border column
+};
+
+void buildPackedPlan(const Plan &plan, PackedPlan &q);
+
+}  // namespace iqo_b200

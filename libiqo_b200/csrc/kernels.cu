@@ -250,75 +250,80 @@ __device__ __forceinline__ void halfVerticalStrip(const HalfArgs &a, const uint8
     }
     fetch();
 
-    for (int k = k0; k < k1; k += NG) {
+    // one destination row pair: `s` (compile-time after unrolling) is the ring position of the window
+    auto step = [&](const int s, const int kk) {
+        win[(s + NG - 1) % NG] = transposed();
+        fetch();  // prefetch the next pair's newest group (overshoots by one group at the strip end)
 #pragma unroll
-        for (int s = 0; s < NG; ++s) {
-            if (s == 0 || k + s < k1) {
-                win[(s + NG - 1) % NG] = transposed();
-                fetch();  // prefetch the next pair's newest group (overshoots by one group at the strip end)
-#pragma unroll
-                for (int par = 0; par < 2; ++par) {
-                    const int rl = 2 * (k + s) + par;  // local destination row
-                    uint32_t c0 = a.cwY[par][0], c1 = NG > 1 ? a.cwY[par][1] : 0u, c2 = NG > 2 ? a.cwY[par][2] : 0u;
-                    int deno = 0;
-                    uint32_t magic = 0;
-                    if (EDGE) {
-                        const int y = ty0 + rl;
-                        if (y < a.DH && (y < a.mbY || y >= a.meY)) {
-                            const int row = __ldg(a.rowY + y);
-                            deno = __ldg(a.denoY + row);
-                            magic = __ldg(a.magicY + row);
-                            c0 = __ldg(a.borderY + row * 3);
-                            c1 = __ldg(a.borderY + row * 3 + 1);
-                            c2 = __ldg(a.borderY + row * 3 + 2);
-                        }
-                    }
-                    const int init = (EDGE && deno) ? 0 : B;
-                    int v0 = init, v1 = init, v2 = init, v3 = init;
-                    {
-                        const uint4 q = win[s % NG];
-                        v0 = dp4a_us(q.x, c0, v0);
-                        v1 = dp4a_us(q.y, c0, v1);
-                        v2 = dp4a_us(q.z, c0, v2);
-                        v3 = dp4a_us(q.w, c0, v3);
-                    }
-                    if (NG > 1) {
-                        const uint4 q = win[(s + 1) % NG];
-                        v0 = dp4a_us(q.x, c1, v0);
-                        v1 = dp4a_us(q.y, c1, v1);
-                        v2 = dp4a_us(q.z, c1, v2);
-                        v3 = dp4a_us(q.w, c1, v3);
-                    }
-                    if (NG > 2) {
-                        const uint4 q = win[(s + 2) % NG];
-                        v0 = dp4a_us(q.x, c2, v0);
-                        v1 = dp4a_us(q.y, c2, v1);
-                        v2 = dp4a_us(q.z, c2, v2);
-                        v3 = dp4a_us(q.w, c2, v3);
-                    }
-                    if (EDGE && deno) {
-                        // resizeYborder: int16 numerator * 64 / denominator, C (truncating) division;
-                        // |numerator * 64| <= 2^21 and 1 <= deno <= 127, so floor(n / deno) is the
-                        // multiply-high by floor(2^32 / deno) + 1 (deno == 1: magic == 0, identity)
-                        auto bdiv = [&](int v) -> int {
-                            const int n = (int)(short)v * 64;
-                            const uint32_t m = (uint32_t)abs(n);
-                            const int q = magic ? (int)__umulhi(m, magic) : (int)m;
-                            return (int)(short)(n < 0 ? -q : q) + B;
-                        };
-                        v0 = bdiv(v0);
-                        v1 = bdiv(v1);
-                        v2 = bdiv(v2);
-                        v3 = bdiv(v3);
-                    }
-                    uint2 o;
-                    o.x = prmt((uint32_t)v0, (uint32_t)v1, 0x5410);
-                    o.y = prmt((uint32_t)v2, (uint32_t)v3, 0x5410);
-                    *reinterpret_cast<uint2 *>(wout + rl * kHalfRowWords) = o;
+        for (int par = 0; par < 2; ++par) {
+            const int rl = 2 * kk + par;  // local destination row
+            uint32_t c0 = a.cwY[par][0], c1 = NG > 1 ? a.cwY[par][1] : 0u, c2 = NG > 2 ? a.cwY[par][2] : 0u;
+            int deno = 0;
+            uint32_t magic = 0;
+            if (EDGE) {
+                const int y = ty0 + rl;
+                if (y < a.DH && (y < a.mbY || y >= a.meY)) {
+                    const int row = __ldg(a.rowY + y);
+                    deno = __ldg(a.denoY + row);
+                    magic = __ldg(a.magicY + row);
+                    c0 = __ldg(a.borderY + row * 3);
+                    c1 = __ldg(a.borderY + row * 3 + 1);
+                    c2 = __ldg(a.borderY + row * 3 + 2);
                 }
             }
+            const int init = (EDGE && deno) ? 0 : B;
+            int v0 = init, v1 = init, v2 = init, v3 = init;
+            {
+                const uint4 q = win[s % NG];
+                v0 = dp4a_us(q.x, c0, v0);
+                v1 = dp4a_us(q.y, c0, v1);
+                v2 = dp4a_us(q.z, c0, v2);
+                v3 = dp4a_us(q.w, c0, v3);
+            }
+            if (NG > 1) {
+                const uint4 q = win[(s + 1) % NG];
+                v0 = dp4a_us(q.x, c1, v0);
+                v1 = dp4a_us(q.y, c1, v1);
+                v2 = dp4a_us(q.z, c1, v2);
+                v3 = dp4a_us(q.w, c1, v3);
+            }
+            if (NG > 2) {
+                const uint4 q = win[(s + 2) % NG];
+                v0 = dp4a_us(q.x, c2, v0);
+                v1 = dp4a_us(q.y, c2, v1);
+                v2 = dp4a_us(q.z, c2, v2);
+                v3 = dp4a_us(q.w, c2, v3);
+            }
+            if (EDGE && deno) {
+                // resizeYborder: int16 numerator * 64 / denominator, C (truncating) division;
+                // |numerator * 64| <= 2^21 and 1 <= deno <= 127, so floor(n / deno) is the
+                // multiply-high by floor(2^32 / deno) + 1 (deno == 1: magic == 0, identity)
+                auto bdiv = [&](int v) -> int {
+                    const int n = (int)(short)v * 64;
+                    const uint32_t m = (uint32_t)abs(n);
+                    const int q = magic ? (int)__umulhi(m, magic) : (int)m;
+                    return (int)(short)(n < 0 ? -q : q) + B;
+                };
+                v0 = bdiv(v0);
+                v1 = bdiv(v1);
+                v2 = bdiv(v2);
+                v3 = bdiv(v3);
+            }
+            uint2 o;
+            o.x = prmt((uint32_t)v0, (uint32_t)v1, 0x5410);
+            o.y = prmt((uint32_t)v2, (uint32_t)v3, 0x5410);
+            *reinterpret_cast<uint2 *>(wout + rl * kHalfRowWords) = o;
         }
+    };
+
+    int k = k0;
+    for (; k + NG <= k1; k += NG) {  // whole turns of the register ring, no per-step checks
+#pragma unroll
+        for (int s = 0; s < NG; ++s) step(s, k + s);
     }
+#pragma unroll
+    for (int s = 0; s < NG - 1; ++s)  // at most NG-1 remaining pairs
+        if (k + s < k1) step(s, k + s);
 }
 
 // Vertical pass of a tile: warps = 2 column halves x (2 or 4) strips of destination row pairs.

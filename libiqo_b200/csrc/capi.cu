@@ -106,11 +106,10 @@ struct SharedPlan {
     uint32_t *dBorderY, *dMagicY;
     int32_t *dBorderX;
     // packed kernel tables
-    int32_t *pFirstY, *pNtapY, *pCoefOffY, *pFirstX, *pAccInitX, *pDivX;
+    int32_t *pFirstY, *pNtapY, *pCoefOffY, *pRecX;
     uint32_t *pMagicY, *pCwX;
     SharedPlan()
-        : device(0), dBorderY(0), dMagicY(0), dBorderX(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pFirstX(0), pAccInitX(0),
-          pDivX(0), pMagicY(0), pCwX(0)
+        : device(0), dBorderY(0), dMagicY(0), dBorderX(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0)
     {
     }
     ~SharedPlan();
@@ -193,9 +192,7 @@ SharedPlan::~SharedPlan()
     cudaFree(pFirstY);
     cudaFree(pNtapY);
     cudaFree(pCoefOffY);
-    cudaFree(pFirstX);
-    cudaFree(pAccInitX);
-    cudaFree(pDivX);
+    cudaFree(pRecX);
     cudaFree(pMagicY);
     cudaFree(pCwX);
     cudaGetLastError();
@@ -357,10 +354,8 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         q.rowY = sp.ty.row;
         q.denoY = sp.ty.deno;
         q.magicY = sp.pMagicY;
-        q.firstX = sp.pFirstX;
-        q.rowX = sp.tx.row;
-        q.accInitX = sp.pAccInitX;
-        q.divX = sp.pDivX;
+        q.ntMax = sp.packed.ntMax;
+        q.recX = reinterpret_cast<const int4 *>(sp.pRecX);
         q.cwX = sp.pCwX;
         q.NX = r->plan.x.N;
         q.NP = sp.packed.NP;
@@ -480,16 +475,16 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
         }
     }
     sp->geom = chooseGenericGeom(sp->plan.x.first.data(), sp->plan.x.N, int(sp->plan.x.S), int(sp->plan.x.D));
-    buildPackedPlan(sp->plan, sp->packed);
+    buildPackedPlan(sp->plan, sp->packed, packedPadNP(sp->plan.x.N / 2 + 1));
     if (sp->packed.eligible) {
         const PackedPlan &q = sp->packed;
         if (!uploadVec(sp->pFirstY, q.firstY) || !uploadVec(sp->pNtapY, q.ntapY) || !uploadVec(sp->pCoefOffY, q.coefOffY) ||
-            !uploadVec(sp->pMagicY, q.magicY) || !uploadVec(sp->pFirstX, q.firstX) || !uploadVec(sp->pCwX, q.cwX) ||
-            !uploadVec(sp->pAccInitX, q.accInitX) || !uploadVec(sp->pDivX, q.divX)) {
+            !uploadVec(sp->pMagicY, q.magicY) || !uploadVec(sp->pCwX, q.cwX) || !uploadVec(sp->pRecX, q.recX)) {
             cudaGetLastError();
             sp->packed.eligible = false;
         } else {
-            sp->pgeom = choosePackedGeom(q.firstX.data(), sp->plan.x.N, int(sp->plan.x.S), int(sp->plan.x.D));
+            sp->pgeom = choosePackedGeom(q.firstX.data(), sp->plan.x.N, int(sp->plan.x.S), int(sp->plan.x.D), q.NP, q.ntMax);
+            if (sp->pgeom.smemBytes > 150 * 1024) sp->packed.eligible = false;  // extreme down-sampling: generic kernel
         }
     }
     out = sp;
@@ -760,7 +755,7 @@ int iqo_cuda_plan_kernel(int kind, unsigned degree, size_t srcW, size_t srcH, si
     HalfPlan h;
     buildHalfPlan(p, h);
     PackedPlan q;
-    buildPackedPlan(p, q);
+    buildPackedPlan(p, q, packedPadNP(p.x.N / 2 + 1));
     if (kernel && kernelCap)
         snprintf(kernel, kernelCap, "%s", h.eligible ? (h.symmetric ? "half_sym" : "half") : q.eligible ? "packed" : "generic");
     if (why && whyCap) snprintf(why, whyCap, "%s%s%s", h.why.c_str(), q.eligible ? "" : "; packed: ", q.eligible ? "" : q.why.c_str());

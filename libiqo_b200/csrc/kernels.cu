@@ -664,30 +664,31 @@ __device__ __forceinline__ int dp2a_hi_uu(uint32_t a, uint32_t b, int c)
     return d;
 }
 
-template <bool SIGNED>
+constexpr int kPackedTileW = 128;  // destination columns per tile = threads per row half
+constexpr int kPackedTileH = 32;   // destination rows per tile (two halves of 16)
+constexpr int kPackedMaxTapsY = 64;
+
+template <bool SIGNED, int NPT>
 __global__ void __launch_bounds__(256) resizePackedKernel(const __grid_constant__ PackedArgs a)
 {
-    extern __shared__ __align__(16) uint32_t Wp[];
-    const int tx0 = blockIdx.x * a.tileW;
-    const int ty0 = blockIdx.y * a.tileH;
-    const int tw = min(a.tileW, a.DW - tx0);
-    const int th = min(a.tileH, a.dstRows - ty0);
+    extern __shared__ __align__(16) uint32_t Wp[];  // [tileH][wordsPerRow] packed 16-bit pairs
+    __shared__ int sFy[kPackedTileH], sNt[kPackedTileH], sDeno[kPackedTileH];
+    __shared__ uint32_t sMagic[kPackedTileH];
+    int32_t *sCoef = reinterpret_cast<int32_t *>(Wp + a.tileH * a.wordsPerRow);  // [tileH][ntMax]
+
+    const int tx0 = blockIdx.x * kPackedTileW;
+    const int ty0 = blockIdx.y * kPackedTileH;
+    const int tw = min(kPackedTileW, a.DW - tx0);
+    const int th = min(kPackedTileH, a.dstRows - ty0);
     const uint8_t *__restrict__ src = a.src + (long long)blockIdx.z * a.srcFrameStride;
     uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int B = a.workBias;
 
-    // source column window of the tile; firstX is non-decreasing and >= 0
-    const int x0 = __ldg(a.firstX + tx0) & ~3;
-    const int x1 = min(__ldg(a.firstX + tx0 + tw - 1) + a.NX - 1, a.SW - 1);
-    const int words = ((x1 - x0) >> 2) + 1;  // 4-column words this tile reads per source row
-
-    // ================= vertical pass =================
-    for (int r = warp; r < th; r += 8) {
-        const int y = a.dstRow0 + ty0 + r;
-        const int fy = __ldg(a.firstY + y) - a.srcRow0;
-        const int nt = __ldg(a.ntapY + y);
-        const int32_t *__restrict__ cy = a.coefY + __ldg(a.coefOffY + y);
+    // per-row metadata and coefficient slices of this tile -> shared memory
+    if (threadIdx.x < th) {
+        const int y = a.dstRow0 + ty0 + threadIdx.x;
+        sFy[threadIdx.x] = __ldg(a.firstY + y) - a.srcRow0;
+        sNt[threadIdx.x] = __ldg(a.ntapY + y);
         int deno = 0;
         uint32_t magic = 0;
         if (SIGNED) {
@@ -695,25 +696,57 @@ __global__ void __launch_bounds__(256) resizePackedKernel(const __grid_constant_
             deno = __ldg(a.denoY + row);
             magic = __ldg(a.magicY + row);
         }
-        const uint32_t init = deno ? 0u : ((uint32_t)B | ((uint32_t)B << 16));
-        for (int cw = lane; cw < words; cw += 32) {
-            const uint8_t *ptr = src + (long long)fy * a.srcPitch + (x0 + 4 * cw);
-            uint32_t acc01 = init, acc23 = init;
+        sDeno[threadIdx.x] = deno;
+        sMagic[threadIdx.x] = magic;
+    }
+    for (int idx = threadIdx.x; idx < th * a.ntMax; idx += blockDim.x) {
+        const int r = idx / a.ntMax, i = idx - r * a.ntMax;
+        const int y = a.dstRow0 + ty0 + r;
+        sCoef[idx] = (i < __ldg(a.ntapY + y)) ? __ldg(a.coefY + __ldg(a.coefOffY + y) + i) : 0;
+    }
+    // source column window of the tile (firstX is non-decreasing and >= 0), in 8-column units
+    const int x0 = __ldg(&a.recX[tx0].x) & ~7;
+    const int x1 = min(__ldg(&a.recX[tx0 + tw - 1].x) + a.NX - 1, a.SW - 1);
+    const int ncd = ((x1 - x0) >> 3) + 1;
+    const int swWords = (a.SW + 3) >> 2;  // 32-bit words per source row that hold image bytes
+    __syncthreads();
+
+    // ================= vertical pass: item = (row, 8 adjacent source columns) =================
+    {
+        const uint32_t rcp = (65536u + ncd - 1) / ncd;  // items < 32 * 2^9: exact floor division
+        for (int item = threadIdx.x; item < th * ncd; item += blockDim.x) {
+            const int r = (int)(((uint32_t)item * rcp) >> 16);
+            const int cd = item - r * ncd;
+            const int col = x0 + 8 * cd;
+            const bool ok1 = ((col >> 2) + 1) < swWords;  // the second word still holds image bytes
+            const uint8_t *ptr = src + (long long)sFy[r] * a.srcPitch + col;
+            const int nt = sNt[r];
+            const int deno = sDeno[r];
+            const int32_t *cs = sCoef + r * a.ntMax;
+            const uint32_t init = deno ? 0u : ((uint32_t)B | ((uint32_t)B << 16));
+            uint32_t a0 = init, a1 = init, a2 = init, a3 = init;
             for (int i = 0; i < nt; ++i) {
-                const uint32_t word = __ldg(reinterpret_cast<const uint32_t *>(ptr));
+                const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t *>(ptr));
+                const uint32_t w1 = ok1 ? __ldg(reinterpret_cast<const uint32_t *>(ptr + 4)) : 0u;
                 ptr += a.srcPitch;
-                const uint32_t c = (uint32_t)__ldg(cy + i);
-                acc01 += prmt(word, 0u, 0x4140) * c;  // lanes (col 0, col 1)
-                acc23 += prmt(word, 0u, 0x4342) * c;  // lanes (col 2, col 3)
+                const uint32_t c = (uint32_t)cs[i];
+                a0 += prmt(w0, 0u, 0x4140) * c;  // 16-bit lanes (col 0, col 1)
+                a1 += prmt(w0, 0u, 0x4342) * c;  // (col 2, col 3)
+                a2 += prmt(w1, 0u, 0x4140) * c;
+                a3 += prmt(w1, 0u, 0x4342) * c;
             }
             if (SIGNED && deno) {
-                // resizeYborder: the numerator lanes are genuine int16 sums here (no bias was
-                // added); work = int16(nume * 64 / deno), C division via multiply-high
-                auto bdiv = [&](uint32_t lanes) -> uint32_t {
+                // resizeYborder: the lanes are plain int16 sums here (no bias was added; a negative
+                // low lane borrowed one from the high lane); work = int16(nume * 64 / deno), C
+                // division as a multiply-high (|nume * 64| <= 2^21, 1 <= deno <= 255)
+                const uint32_t magic = sMagic[r];
+                auto bdiv = [&](uint32_t packed) -> uint32_t {
+                    const uint32_t lo = packed & 0xffffu;
+                    const uint32_t hi = (packed >> 16) + ((lo & 0x8000u) ? 1u : 0u);
                     uint32_t out = 0;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int n = (int)(short)(lanes >> (16 * h)) * 64;
+                        const int n = (int)(short)(h ? hi : lo) * 64;
                         const uint32_t m = (uint32_t)abs(n);
                         const int qv = magic ? (int)__umulhi(m, magic) : (int)m;
                         const int w = (int)(short)(n < 0 ? -qv : qv) + B;
@@ -721,45 +754,42 @@ __global__ void __launch_bounds__(256) resizePackedKernel(const __grid_constant_
                     }
                     return out;
                 };
-                // un-bias is not needed (init was 0 for this row) but negative lanes borrowed from
-                // their neighbour: redo the two lanes separately from the packed sum
-                const uint32_t lo0 = acc01 & 0xffffu, hi0 = (acc01 >> 16) + ((lo0 & 0x8000u) ? 1u : 0u);
-                const uint32_t lo1 = acc23 & 0xffffu, hi1 = (acc23 >> 16) + ((lo1 & 0x8000u) ? 1u : 0u);
-                acc01 = bdiv(lo0 | (hi0 << 16));
-                acc23 = bdiv(lo1 | (hi1 << 16));
+                a0 = bdiv(a0);
+                a1 = bdiv(a1);
+                a2 = bdiv(a2);
+                a3 = bdiv(a3);
             }
-            *reinterpret_cast<uint2 *>(Wp + r * a.wordsPerRow + 2 * cw) = make_uint2(acc01, acc23);
+            *reinterpret_cast<uint4 *>(Wp + r * a.wordsPerRow + 4 * cd) = make_uint4(a0, a1, a2, a3);
         }
     }
     __syncthreads();
 
-    // ================= horizontal pass =================
-    const int half = 1 << (a.shift - 1);
-    (void)half;
-    for (int r = warp; r < th; r += 8) {
-        const uint32_t *wr = Wp + r * a.wordsPerRow;
-        uint8_t *out = dst + (long long)(ty0 + r) * a.dstPitch + tx0;
-        for (int dx = lane; dx < tw; dx += 32) {
-            const int d = tx0 + dx;
-            const int e0 = __ldg(a.firstX + d) - x0;
-            const int row = __ldg(a.rowX + d);
-            const uint32_t *__restrict__ cw = a.cwX + (long long)(row * 2 + (e0 & 1)) * a.NP;
-            const uint32_t *wp = wr + (e0 >> 1);
-            int lo = __ldg(a.accInitX + row), hi = 0;
-            for (int j = 0; j < a.NP; ++j) {
-                const uint32_t c = __ldg(cw + j);
-                const uint32_t w = wp[j];
-                lo = dp2a_lo_uu(w, c, lo);
-                hi = SIGNED ? dp2a_hi_us(w, c, hi) : dp2a_hi_uu(w, c, hi);
+    // ================= horizontal pass: thread = one destination column, half of the rows ========
+    {
+        const int dx = threadIdx.x & (kPackedTileW - 1);
+        const int rh = threadIdx.x >> 7;  // 0 / 1
+        if (dx < tw) {
+            const int4 rec = __ldg(a.recX + tx0 + dx);  // {first column, coefficient word offset, accumulator init, divisor}
+            uint32_t cw[NPT];
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) cw[j] = __ldg(a.cwX + rec.y + j);
+            const uint32_t *wp = Wp + ((rec.x - x0) >> 1) + rh * (kPackedTileH / 2) * a.wordsPerRow;
+            uint8_t *out = dst + (long long)(ty0 + rh * (kPackedTileH / 2)) * a.dstPitch + tx0 + dx;
+            const int rows = min(kPackedTileH / 2, th - rh * (kPackedTileH / 2));
+            for (int r = 0; r < rows; ++r, wp += a.wordsPerRow, out += a.dstPitch) {
+                int lo = rec.z, hi = 0;
+#pragma unroll
+                for (int j = 0; j < NPT; ++j) {
+                    const uint32_t w = wp[j];
+                    lo = dp2a_lo_uu(w, cw[j], lo);
+                    hi = SIGNED ? dp2a_hi_us(w, cw[j], hi) : dp2a_hi_uu(w, cw[j], hi);
+                }
+                const int total = lo + (hi << 8);
+                int v = total >> a.shift;
+                if (SIGNED && rec.w != 0) v = total / rec.w;  // resizeXborder: truncating division by deno * 64
+                v = (int)(short)v;
+                *out = (uint8_t)min(max(v, 0), 255);
             }
-            const int total = lo + (hi << 8);
-            int v = total >> a.shift;
-            if (SIGNED) {
-                const int div = __ldg(a.divX + row);
-                if (div != 0) v = total / div;  // resizeXborder: truncating division by deno * 64
-            }
-            v = (int)(short)v;
-            out[dx] = (uint8_t)min(max(v, 0), 255);
         }
     }
 }
@@ -837,49 +867,65 @@ cudaError_t launchHalf(const HalfArgs &a, const CUtensorMap *tmap, int boxRows, 
     return cudaErrorInvalidValue;
 }
 
-PackedGeom choosePackedGeom(const int32_t *firstX, int N, int S, int D)
+int packedPadNP(int np)
+{
+    const int sizes[] = {2, 3, 4, 6, 8, 12};
+    for (int i = 0; i < 6; ++i)
+        if (np <= sizes[i]) return sizes[i];
+    return 0;  // longer kernels: not handled by the packed kernel
+}
+
+PackedGeom choosePackedGeom(const int32_t *firstX, int N, int S, int D, int npt, int ntMax)
 {
     PackedGeom g;
-    g.tileW = 128;
-    g.tileH = 16;
-    for (;;) {
-        int widest = 1;
-        for (int t0 = 0; t0 < D; t0 += g.tileW) {
-            const int t1 = std::min(D, t0 + g.tileW) - 1;
-            const int lo = firstX[t0] & ~3;
-            const int hi = std::min(firstX[t1] + N - 1, S - 1);
-            widest = std::max(widest, ((hi - lo) >> 2) + 1);
-        }
-        // two 32-bit words per 4-column source word, plus slack for the zero-weight pair words
-        // the horizontal pass may touch beyond the last written column
-        g.wordsPerRow = (2 * widest + N / 2 + 4 + 1) & ~1;  // even: rows start 8-byte aligned
-        g.smemBytes = size_t(g.tileH) * g.wordsPerRow * 4;
-        if (g.smemBytes <= 64 * 1024 || g.tileW <= 8) break;
-        g.tileW /= 2;
+    g.tileW = kPackedTileW;
+    g.tileH = kPackedTileH;
+    int widest = 1;
+    for (int t0 = 0; t0 < D; t0 += g.tileW) {
+        const int t1 = std::min(D, t0 + g.tileW) - 1;
+        const int lo = firstX[t0] & ~7;
+        const int hi = std::min(firstX[t1] + N - 1, S - 1);
+        widest = std::max(widest, ((hi - lo) >> 3) + 1);
     }
+    // four 32-bit words per 8-column unit, plus slack for the zero-weight pair words the
+    // horizontal pass touches beyond the last written column; multiple of 4 (16-byte rows)
+    g.wordsPerRow = (4 * widest + npt + 4 + 3) & ~3;
+    g.smemBytes = size_t(g.tileH) * g.wordsPerRow * 4 + size_t(g.tileH) * ntMax * 4;
     return g;
+}
+
+template <bool SIGNED, int NPT>
+cudaError_t launchPackedT(const PackedArgs &a, dim3 grid, size_t smem, cudaStream_t stream)
+{
+    static bool attrSet = false;
+    if (!attrSet) {
+        cudaError_t e = cudaFuncSetAttribute(resizePackedKernel<SIGNED, NPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        if (e != cudaSuccess) return e;
+        attrSet = true;
+    }
+    resizePackedKernel<SIGNED, NPT><<<grid, 256, smem, stream>>>(a);
+    return cudaGetLastError();
 }
 
 cudaError_t launchPacked(const PackedArgs &a, cudaStream_t stream)
 {
-    static bool attrSet = false;
-    if (!attrSet) {
-        cudaError_t e = cudaFuncSetAttribute(resizePackedKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(resizePackedKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-        if (e != cudaSuccess) return e;
-        attrSet = true;
-    }
-    const int tilesX = (a.DW + a.tileW - 1) / a.tileW;
-    const int tilesY = (a.dstRows + a.tileH - 1) / a.tileH;
+    const int tilesX = (a.DW + kPackedTileW - 1) / kPackedTileW;
+    const int tilesY = (a.dstRows + kPackedTileH - 1) / kPackedTileH;
     if (tilesY > 65535) return cudaErrorInvalidConfiguration;
     dim3 grid(tilesX, tilesY, a.nFrames);
-    const size_t smem = size_t(a.tileH) * a.wordsPerRow * 4;
-    if (a.isSigned)
-        resizePackedKernel<true><<<grid, 256, smem, stream>>>(a);
-    else
-        resizePackedKernel<false><<<grid, 256, smem, stream>>>(a);
+    const size_t smem = size_t(a.tileH) * a.wordsPerRow * 4 + size_t(a.tileH) * a.ntMax * 4;
     g_launches.fetch_add(1);
-    return cudaGetLastError();
+#define IQO_PACKED_CASE(N)                                                              \
+    if (a.NP == N)                                                                      \
+        return a.isSigned ? launchPackedT<true, N>(a, grid, smem, stream) : launchPackedT<false, N>(a, grid, smem, stream);
+    IQO_PACKED_CASE(2)
+    IQO_PACKED_CASE(3)
+    IQO_PACKED_CASE(4)
+    IQO_PACKED_CASE(6)
+    IQO_PACKED_CASE(8)
+    IQO_PACKED_CASE(12)
+#undef IQO_PACKED_CASE
+    return cudaErrorInvalidValue;
 }
 
 int halfSourceRowsMax()

@@ -91,17 +91,20 @@ struct PackedArgs {
     // vertical
     const int32_t *firstY, *ntapY, *coefOffY, *coefY, *rowY, *denoY;
     const uint32_t *magicY;
-    // horizontal
-    const int32_t *firstX, *rowX, *accInitX, *divX;
+    int ntMax;                      // widest vertical slice (row stride of the staged coefficients)
+    // horizontal: per destination column {first source column, offset of its NP coefficient pair
+    // words in cwX, accumulator init, divisor (0 = shift)}
+    const int4 *recX;
     const uint32_t *cwX;
-    int NX, NP;
+    int NX, NP;                     // NP is already padded to an instantiated size
 };
 
 struct PackedGeom {
     int tileW, tileH, wordsPerRow;
     size_t smemBytes;
 };
-PackedGeom choosePackedGeom(const int32_t *firstXClamped, int N, int S, int D);
+int packedPadNP(int np);  // smallest instantiated pair-word count >= np, 0 if none
+PackedGeom choosePackedGeom(const int32_t *firstXClamped, int N, int S, int D, int npt, int ntMax);
 cudaError_t launchPacked(const PackedArgs &a, cudaStream_t stream);
 
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D);

@@ -496,7 +496,7 @@ void buildHalfPlan(const Plan &p, HalfPlan &h)
 // ---------------------------------------------------------------------------------------------
 namespace iqo_b200 {
 
-void buildPackedPlan(const Plan &p, PackedPlan &q)
+void buildPackedPlan(const Plan &p, PackedPlan &q, int padNP)
 {
     q.eligible = false;
     q.why.clear();
@@ -551,7 +551,11 @@ void buildPackedPlan(const Plan &p, PackedPlan &q)
 
     // ---- horizontal ----
     q.firstX.assign(size_t(X.D), 0);
-    q.NP = X.N / 2 + 1;
+    if (padNP < X.N / 2 + 1) { q.why = "horizontal kernel longer than the packed kernel supports"; return; }
+    q.NP = padNP;
+    q.ntMax = 1;
+    for (int64_t y = 0; y < Y.D; ++y) q.ntMax = std::max(q.ntMax, q.ntapY[size_t(y)]);
+    if (q.ntMax > 64) { q.why = "vertical kernel longer than 64 taps"; return; }
     std::vector<int> rowShift(size_t(X.numRows), 0);  // leading taps dropped because they lie left of column 0
     for (int64_t d = 0; d < X.D; ++d) {
         const int r = X.row[d];
@@ -573,8 +577,7 @@ void buildPackedPlan(const Plan &p, PackedPlan &q)
         q.firstX[size_t(d)] = int32_t(f + shift);
     }
     q.cwX.assign(size_t(X.numRows) * 2 * q.NP, 0);
-    q.accInitX.assign(size_t(X.numRows), 0);
-    q.divX.assign(size_t(X.numRows), 0);
+    std::vector<int32_t> accInit(size_t(X.numRows), 0), divisor(size_t(X.numRows), 0);
     for (int r = 0; r < X.numRows; ++r) {
         const int32_t *c = &X.coef[size_t(r) * X.N];
         const int shift = rowShift[size_t(r)];
@@ -597,8 +600,17 @@ void buildPackedPlan(const Plan &p, PackedPlan &q)
                 q.cwX[(size_t(r) * 2 + par) * q.NP + w] = la | (lb << 8) | (ha << 16) | (hb << 24);
             }
         }
-        q.accInitX[size_t(r)] = int32_t((1ll << (p.shift - 1)) - (long long)q.workBias * sum);
-        q.divX[size_t(r)] = X.deno[size_t(r)] * 64;
+        accInit[size_t(r)] = int32_t((1ll << (p.shift - 1)) - (long long)q.workBias * sum);
+        divisor[size_t(r)] = X.deno[size_t(r)] * 64;
+    }
+    q.recX.assign(size_t(X.D) * 4, 0);
+    for (int64_t d = 0; d < X.D; ++d) {
+        const int r = X.row[d];
+        const int f = q.firstX[size_t(d)];
+        q.recX[size_t(d) * 4 + 0] = f;
+        q.recX[size_t(d) * 4 + 1] = int32_t((size_t(r) * 2 + (f & 1)) * q.NP);
+        q.recX[size_t(d) * 4 + 2] = accInit[size_t(r)];
+        q.recX[size_t(d) * 4 + 3] = divisor[size_t(r)];
     }
     q.eligible = true;
 }

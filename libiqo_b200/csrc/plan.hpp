@@ -115,12 +115,15 @@ struct PackedPlan {
     std::vector<uint32_t> magicY;   // per coefficient row: multiply-high constant of the border division
     // horizontal pass, per destination column: first source column (>= 0) and coefficient row
     std::vector<int32_t> firstX;
-    int NP;                         // pair words per packed row
+    int NP;                         // pair words per packed row (padded to `padNP`)
+    int ntMax;                      // longest vertical slice
     std::vector<uint32_t> cwX;      // [numRowsX][2 (parity of the window start)][NP]: bytes lo_a, lo_b, hi_a, hi_b
-    std::vector<int32_t> accInitX;  // [numRowsX]: rounding constant minus bias * (sum of the row)
-    std::vector<int32_t> divX;      // [numRowsX]: 0, or denominator * 64 of a Lanczos border column
+    // per destination column: {first source column, offset of its row/parity in cwX,
+    // rounding constant minus bias * (sum of the row), 0 or denominator * 64 (Lanczos border)}
+    std::vector<int32_t> recX;      // [D][4]
 };
 
-void buildPackedPlan(const Plan &plan, PackedPlan &q);
+// padNP: pair-word count the kernel is instantiated for (>= N/2 + 1)
+void buildPackedPlan(const Plan &plan, PackedPlan &q, int padNP);
 
 }  // namespace iqo_b200

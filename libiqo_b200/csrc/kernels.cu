@@ -16,6 +16,21 @@ namespace {
 
 std::atomic<unsigned long long> g_launches(0);
 
+// cudaFuncSetAttribute is per device: remember, per kernel instantiation, where it was done
+struct PerDeviceOnce {
+    std::atomic<unsigned long long> mask[2];
+    PerDeviceOnce() { mask[0] = 0; mask[1] = 0; }
+    bool done(int dev) const { return dev >= 0 && dev < 128 && ((mask[dev >> 6].load() >> (dev & 63)) & 1ull); }
+    void set(int dev) { if (dev >= 0 && dev < 128) mask[dev >> 6].fetch_or(1ull << (dev & 63)); }
+};
+
+int currentDevice()
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    return dev;
+}
+
 __device__ __forceinline__ int clampi(int v, int lo, int hi)
 {
     return min(max(v, lo), hi);
@@ -619,12 +634,13 @@ cudaError_t launchHalfT(const HalfArgs &a, const CUtensorMap *tmap, int boxRows,
     dim3 grid(tilesX, tilesY, a.nFrames);
     const int threads = a.tileRows > 32 ? 256 : 128;
     if (tmap) {
-        static bool attrSet = false;  // per instantiation; a benign race sets it twice at worst
-        if (!attrSet) {
+        static PerDeviceOnce attrSet;  // per instantiation; a benign race sets it twice at worst
+        const int dev = currentDevice();
+        if (!attrSet.done(dev)) {
             cudaError_t e = cudaFuncSetAttribute(resizeHalfTmaKernel<NG, NWX, SYM, ENDHI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                  kHalfTileBytes + kHalfWBytes);
             if (e != cudaSuccess) return e;
-            attrSet = true;
+            attrSet.set(dev);
         }
         HalfTmaArgs p;
         p.tmap = *tmap;
@@ -897,11 +913,12 @@ PackedGeom choosePackedGeom(const int32_t *firstX, int N, int S, int D, int npt,
 template <bool SIGNED, int NPT>
 cudaError_t launchPackedT(const PackedArgs &a, dim3 grid, size_t smem, cudaStream_t stream)
 {
-    static bool attrSet = false;
-    if (!attrSet) {
+    static PerDeviceOnce attrSet;
+    const int dev = currentDevice();
+    if (!attrSet.done(dev)) {
         cudaError_t e = cudaFuncSetAttribute(resizePackedKernel<SIGNED, NPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
         if (e != cudaSuccess) return e;
-        attrSet = true;
+        attrSet.set(dev);
     }
     resizePackedKernel<SIGNED, NPT><<<grid, 256, smem, stream>>>(a);
     return cudaGetLastError();

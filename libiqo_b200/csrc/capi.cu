@@ -327,6 +327,23 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         return IQO_CUDA_OK;
     }
     const SharedPlan &sp = *r->sp;
+    // Area 2:1 on both axes: pure streaming kernel (needs whole 16-byte source chunks per 8 pixels)
+    {
+        const AxisPlan &X = r->plan.x, &Y = r->plan.y;
+        if (r->path == IQO_CUDA_PATH_AUTO && r->plan.kind == kArea && whole && X.rD == 1 && X.rS == 2 && Y.rD == 1 && Y.rS == 2 &&
+            X.N == 2 && Y.N == 2 && Y.coef[0] < 256 && Y.coef[1] < 256 && ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 &&
+            srcFrameStride % 16 == 0 && ((uintptr_t)dst % 8) == 0 && dstSt % 8 == 0 && dstFrameStride % 8 == 0 &&
+            X.S % 16 == 0) {
+            r->lastKernel = "area2";
+            for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
+                const int nf = int(std::min<size_t>(65535, nFrames - f0));
+                CUDA_TRY(launchArea2(src + f0 * srcFrameStride, dst + f0 * dstFrameStride, (long long)srcSt, (long long)dstSt,
+                                     (long long)srcFrameStride, (long long)dstFrameStride, int(X.D), int(Y.D), nf, &Y.coef[0],
+                                     &X.coef[0], stream));
+            }
+            return IQO_CUDA_OK;
+        }
+    }
     if (r->path == IQO_CUDA_PATH_AUTO && sp.packed.eligible && ((uintptr_t)src % 4) == 0 && srcSt % 4 == 0 &&
         srcFrameStride % 4 == 0 && dstRows <= size_t(65535) * sp.pgeom.tileH) {
         PackedArgs q;

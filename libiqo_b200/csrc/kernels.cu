@@ -810,6 +810,65 @@ __global__ void __launch_bounds__(256) resizePackedKernel(const __grid_constant_
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Area 2:1 x 2:1 (BASELINE config 2a): every destination pixel is a 2 x 2 block of the source,
+// weights from the planner's single-phase tables (cY = cX = [1/2, 1/2] in 8 / 15 bit fixed point).
+// Pure streaming: a thread reads 16 source bytes of two rows (two 16-byte loads), interleaves
+// the rows (PRMT) so that dp4a(u8 x u8) gives the vertical sums of two columns, applies the two
+// horizontal weights and stores 8 pixels with one 8-byte store.  No shared memory, no halo.
+//   work = u16(cy0*a + cy1*c)   (AreaResizerImpl<Generic>::resizeYmain, ..._Generic.cpp:303-320)
+//   dst  = (cx0*work0 + cx1*work1 + 2^22) >> 23   (resizeXmain, :340-368)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ int dp4a_uu(uint32_t a, uint32_t b, int c)
+{
+    int d;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
+struct Area2Args {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long srcPitch, dstPitch, srcFrameStride, dstFrameStride;
+    int DW, DH;
+    int chunksPerRow;      // ceil(DW / 8)
+    uint32_t rcpChunks;    // ceil(2^32 / chunksPerRow)
+    uint32_t cyLo, cyHi;   // (cy0, cy1, 0, 0) and (0, 0, cy0, cy1) as bytes
+    int cx0, cx1;
+};
+
+__global__ void __launch_bounds__(256) resizeArea2Kernel(const __grid_constant__ Area2Args a)
+{
+    const uint32_t idx = blockIdx.x * 256u + threadIdx.x;
+    const int row = (a.chunksPerRow == 1) ? (int)idx : (int)__umulhi(idx, a.rcpChunks);
+    const int ch = (int)idx - row * a.chunksPerRow;
+    if (row >= a.DH) return;
+    const uint8_t *__restrict__ s0 = a.src + (long long)blockIdx.y * a.srcFrameStride + (long long)(2 * row) * a.srcPitch + 16 * ch;
+    const uint4 ra = __ldg(reinterpret_cast<const uint4 *>(s0));
+    const uint4 rc = __ldg(reinterpret_cast<const uint4 *>(s0 + a.srcPitch));
+    const uint32_t wa[4] = {ra.x, ra.y, ra.z, ra.w}, wc[4] = {rc.x, rc.y, rc.z, rc.w};
+    int v[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint32_t p01 = prmt(wa[j], wc[j], 0x5140);  // (a0, c0, a1, c1)
+        const uint32_t p23 = prmt(wa[j], wc[j], 0x7362);  // (a2, c2, a3, c3)
+        const int w0 = dp4a_uu(p01, a.cyLo, 0), w1 = dp4a_uu(p01, a.cyHi, 0);
+        const int w2 = dp4a_uu(p23, a.cyLo, 0), w3 = dp4a_uu(p23, a.cyHi, 0);
+        v[2 * j] = (w0 * a.cx0 + w1 * a.cx1 + (1 << 22)) >> 23;
+        v[2 * j + 1] = (w2 * a.cx0 + w3 * a.cx1 + (1 << 22)) >> 23;
+    }
+    uint2 o;
+    o.x = packSatU8(v[1], v[0], packSatU8(v[3], v[2], 0u));
+    o.y = packSatU8(v[5], v[4], packSatU8(v[7], v[6], 0u));
+    uint8_t *out = a.dst + (long long)blockIdx.y * a.dstFrameStride + (long long)row * a.dstPitch + 8 * ch;
+    if (8 * ch + 8 <= a.DW) {
+        *reinterpret_cast<uint2 *>(out) = o;
+    } else {
+        for (int p = 0; p < a.DW - 8 * ch; ++p) out[p] = (uint8_t)(((p < 4 ? o.x : o.y) >> (8 * (p & 3))) & 0xffu);
+    }
+}
+
 }  // namespace
 
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D)
@@ -943,6 +1002,32 @@ cudaError_t launchPacked(const PackedArgs &a, cudaStream_t stream)
     IQO_PACKED_CASE(12)
 #undef IQO_PACKED_CASE
     return cudaErrorInvalidValue;
+}
+
+cudaError_t launchArea2(const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch, long long srcFrameStride,
+                        long long dstFrameStride, int DW, int DH, int nFrames, const int32_t cy[2], const int32_t cx[2],
+                        cudaStream_t stream)
+{
+    Area2Args a;
+    a.src = src;
+    a.dst = dst;
+    a.srcPitch = srcPitch;
+    a.dstPitch = dstPitch;
+    a.srcFrameStride = srcFrameStride;
+    a.dstFrameStride = dstFrameStride;
+    a.DW = DW;
+    a.DH = DH;
+    a.chunksPerRow = (DW + 7) / 8;
+    a.rcpChunks = (uint32_t)((0x100000000ull + a.chunksPerRow - 1) / a.chunksPerRow);
+    a.cyLo = uint32_t(cy[0]) | (uint32_t(cy[1]) << 8);
+    a.cyHi = a.cyLo << 16;
+    a.cx0 = cx[0];
+    a.cx1 = cx[1];
+    const long long items = (long long)a.chunksPerRow * DH;
+    dim3 grid((unsigned)((items + 255) / 256), (unsigned)nFrames);
+    resizeArea2Kernel<<<grid, 256, 0, stream>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
 }
 
 int halfSourceRowsMax()

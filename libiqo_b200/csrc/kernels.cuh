@@ -107,6 +107,12 @@ int packedPadNP(int np);  // smallest instantiated pair-word count >= np, 0 if n
 PackedGeom choosePackedGeom(const int32_t *firstXClamped, int N, int S, int D, int npt, int ntMax);
 cudaError_t launchPacked(const PackedArgs &a, cudaStream_t stream);
 
+// Area 2:1 x 2:1 streaming kernel (two-tap single-phase tables, coefficients < 256 vertically).
+// Needs 16-byte aligned source rows and an even-width multiple of 16 source; at most 65535 frames.
+cudaError_t launchArea2(const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch, long long srcFrameStride,
+                        long long dstFrameStride, int DW, int DH, int nFrames, const int32_t cy[2], const int32_t cx[2],
+                        cudaStream_t stream);
+
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D);
 cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_t stream);
 cudaError_t initKernels();  // sets function attributes once per device

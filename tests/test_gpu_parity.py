@@ -372,3 +372,18 @@ def test_plan_cache_and_workspace_pool():
         dst[:] = 0
         r.resize(192, src, 96, dst)
     assert np.array_equal(dst, want)
+
+
+@pytest.mark.parametrize("case", [(3840, 2160, 0, "area2"), (96, 54, 0, "area2"), (208, 50, 0, "area2"),
+                                  (100, 54, 0, "packed")])   # width not a multiple of 16: general kernel
+def test_area_2to1_streaming_kernel(case):
+    sw, sh, spad, kname = case
+    src = lcg_image(sh, sw + spad, seed=31)
+    rc, want = oracle_resize(AREA, src, sw // 2, sh // 2, sw=sw)
+    got, kernel = gpu_resize(AREA, src, sw // 2, sh // 2, sw=sw)
+    assert kernel == kname
+    assert np.array_equal(got, want)
+    for v in (0, 255):
+        flat = np.full((sh, sw), v, np.uint8)
+        got, _ = gpu_resize(AREA, flat, sw // 2, sh // 2)
+        assert (got == v).all()

@@ -344,6 +344,28 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
             return IQO_CUDA_OK;
         }
     }
+    // Linear 2x / 3x up-sampling on X: streaming kernel
+    {
+        const AxisPlan &X = r->plan.x, &Y = r->plan.y;
+        const int K = (X.S > 0 && X.D % X.S == 0) ? int(X.D / X.S) : 0;
+        if (r->path == IQO_CUDA_PATH_AUTO && r->plan.kind == kLinear && whole && (K == 2 || K == 3) && X.S % 4 == 0 &&
+            !Y.identity && Y.N == 2 && Y.D <= 65535 && ((uintptr_t)src % 4) == 0 && srcSt % 4 == 0 && srcFrameStride % 4 == 0 &&
+            ((uintptr_t)dst % 4) == 0 && dstSt % 4 == 0 && dstFrameStride % 4 == 0) {
+            uint32_t cw[3] = {0, 0, 0};
+            for (int t = 0; t < K; ++t) {
+                const uint32_t c0 = uint32_t(X.coef[size_t(t) * 2]), c1 = uint32_t(X.coef[size_t(t) * 2 + 1]);
+                cw[t] = (c0 & 0xff) | ((c1 & 0xff) << 8) | ((c0 >> 8) << 16) | ((c1 >> 8) << 24);
+            }
+            r->lastKernel = (K == 2) ? "linear_up2" : "linear_up3";
+            for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
+                const int nf = int(std::min<size_t>(65535, nFrames - f0));
+                CUDA_TRY(launchLinearUp(K, src + f0 * srcFrameStride, dst + f0 * dstFrameStride, (long long)srcSt, (long long)dstSt,
+                                        (long long)srcFrameStride, (long long)dstFrameStride, int(X.S), int(Y.S), int(X.D), int(Y.D),
+                                        nf, sp.ty.first, sp.ty.row, sp.ty.coef, cw, stream));
+            }
+            return IQO_CUDA_OK;
+        }
+    }
     if (r->path == IQO_CUDA_PATH_AUTO && sp.packed.eligible && ((uintptr_t)src % 4) == 0 && srcSt % 4 == 0 &&
         srcFrameStride % 4 == 0 && dstRows <= size_t(65535) * sp.pgeom.tileH) {
         PackedArgs q;

@@ -869,6 +869,96 @@ __global__ void __launch_bounds__(256) resizeArea2Kernel(const __grid_constant__
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Linear up-sampling by an integer factor K (2 or 3) on the X axis (BASELINE config 2b is 3x),
+// any Linear ratio on Y.  Pure streaming, no shared memory.
+// A thread owns one destination row and one aligned source word (4 columns) = 4K destination
+// pixels.  Destination pixel d = 4K j + i blends the source columns 4j + g(i), 4j + g(i) + 1 with
+// g(i) = floor((2i + 1 - K) / 2K) in [-1, 3] and the weights of phase i mod K -- a static pattern,
+// so the five possible column pairs are built once:
+//   vertical    pair word (col a, col a+1) as two 16-bit lanes = lanes(row f) * q0 + lanes(row f+1) * q1
+//               (two IMAD per pair; <= 255 * 256 per lane, no carry)      [resizeYmain / resizeYborder]
+//   horizontal  dp2a(pair, low byte plane) then dp2a(pair, high byte plane) from (acc >> 8),
+//               >> 15, saturating pack                                      [resizeXmain]
+// The first and the last pixel of a row replicate the edge column (resizeXborder,
+// src/IQOLinearResizerImpl_Generic.cpp:355-366).
+// ---------------------------------------------------------------------------------------
+struct LinearUpArgs {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long srcPitch, dstPitch, srcFrameStride, dstFrameStride;
+    int SW, SH, DW, DH;
+    int wordsPerRow;           // SW / 4
+    uint32_t rcpWords;         // ceil(2^32 / wordsPerRow)
+    const int32_t *firstY, *rowY, *coefY;   // generic vertical tables (two taps per row)
+    uint32_t cwX[3];           // per phase: bytes (lo(q0), lo(q1), hi(q0), hi(q1))
+};
+
+template <int K>
+__global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constant__ LinearUpArgs a)
+{
+    // item = (destination row, source word), flattened so that rows whose word count is not a
+    // multiple of the block size do not leave threads idle
+    const uint32_t item = blockIdx.x * 256u + threadIdx.x;
+    const int y = (a.wordsPerRow == 1) ? (int)item : (int)__umulhi(item, a.rcpWords);
+    const int j = (int)item - y * a.wordsPerRow;
+    if (y >= a.DH) return;
+    const uint8_t *__restrict__ src = a.src + (long long)blockIdx.y * a.srcFrameStride;
+    uint8_t *__restrict__ out = a.dst + (long long)blockIdx.y * a.dstFrameStride + (long long)y * a.dstPitch + 4 * K * j;
+
+    // vertical taps of this destination row (uniform over the block)
+    const int fy = __ldg(a.firstY + y);
+    const int ry = __ldg(a.rowY + y);
+    const uint32_t q0 = (uint32_t)__ldg(a.coefY + 2 * ry), q1 = (uint32_t)__ldg(a.coefY + 2 * ry + 1);
+    const int r0 = min(max(fy, 0), a.SH - 1), r1 = min(max(fy + 1, 0), a.SH - 1);
+    const uint32_t *row0 = reinterpret_cast<const uint32_t *>(src + (long long)r0 * a.srcPitch);
+    const uint32_t *row1 = reinterpret_cast<const uint32_t *>(src + (long long)r1 * a.srcPitch);
+    const int jm = max(j - 1, 0), jp = min(j + 1, a.wordsPerRow - 1);
+    const uint32_t am = __ldg(row0 + jm), a0 = __ldg(row0 + j), ap = __ldg(row0 + jp);
+    const uint32_t bm = __ldg(row1 + jm), b0 = __ldg(row1 + j), bp = __ldg(row1 + jp);
+
+    // pair words (col 4j-1+n, col 4j+n) for n = 0..4 as two 16-bit lanes, vertically blended
+    const uint32_t ua = __funnelshift_r(am, a0, 24), ub = __funnelshift_r(bm, b0, 24);  // columns 4j-1 .. 4j+2
+    const uint32_t va = __funnelshift_r(a0, ap, 24), vb = __funnelshift_r(b0, bp, 24);  // columns 4j+3 .. 4j+6
+    uint32_t P[5];
+    P[0] = prmt(ua, 0u, 0x4140) * q0 + prmt(ub, 0u, 0x4140) * q1;
+    P[1] = prmt(a0, 0u, 0x4140) * q0 + prmt(b0, 0u, 0x4140) * q1;
+    P[2] = prmt(a0, 0u, 0x4241) * q0 + prmt(b0, 0u, 0x4241) * q1;
+    P[3] = prmt(a0, 0u, 0x4342) * q0 + prmt(b0, 0u, 0x4342) * q1;
+    P[4] = prmt(va, 0u, 0x4140) * q0 + prmt(vb, 0u, 0x4140) * q1;
+
+    uint32_t packed[K];
+#pragma unroll
+    for (int quad = 0; quad < K; ++quad) {
+        int v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int i = 4 * quad + e;
+            // g(i) + 1 = floor((2 i + 1 + K) / (2 K))
+            const int n = (2 * i + 1 + K) / (2 * K);
+            const uint32_t cw = a.cwX[i % K];
+            int acc = 1 << 22;
+            acc = dp2a_lo_uu(P[n], cw, acc);
+            acc >>= 8;
+            acc = dp2a_hi_uu(P[n], cw, acc);
+            v[e] = acc >> 15;
+        }
+        packed[quad] = packSatU8(v[1], v[0], packSatU8(v[3], v[2], 0u));
+    }
+    // replicated edge columns
+    if (j == 0) {
+        const int v = (int)((P[1] & 0xffffu) + 128u) >> 8;
+        packed[0] = (packed[0] & 0xffffff00u) | (uint32_t)min(v, 255);
+    }
+    if (j == a.wordsPerRow - 1) {
+        const int v = (int)((P[4] & 0xffffu) + 128u) >> 8;  // low lane of the last pair = column S-1
+        packed[K - 1] = (packed[K - 1] & 0x00ffffffu) | ((uint32_t)min(v, 255) << 24);
+    }
+#pragma unroll
+    for (int quad = 0; quad < K; ++quad) *reinterpret_cast<uint32_t *>(out + 4 * quad) = packed[quad];
+}
+
 }  // namespace
 
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D)
@@ -1026,6 +1116,41 @@ cudaError_t launchArea2(const uint8_t *src, uint8_t *dst, long long srcPitch, lo
     const long long items = (long long)a.chunksPerRow * DH;
     dim3 grid((unsigned)((items + 255) / 256), (unsigned)nFrames);
     resizeArea2Kernel<<<grid, 256, 0, stream>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launchLinearUp(int K, const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch,
+                           long long srcFrameStride, long long dstFrameStride, int SW, int SH, int DW, int DH, int nFrames,
+                           const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const uint32_t cwX[3],
+                           cudaStream_t stream)
+{
+    LinearUpArgs a;
+    a.src = src;
+    a.dst = dst;
+    a.srcPitch = srcPitch;
+    a.dstPitch = dstPitch;
+    a.srcFrameStride = srcFrameStride;
+    a.dstFrameStride = dstFrameStride;
+    a.SW = SW;
+    a.SH = SH;
+    a.DW = DW;
+    a.DH = DH;
+    a.wordsPerRow = SW / 4;
+    a.firstY = firstY;
+    a.rowY = rowY;
+    a.coefY = coefY;
+    for (int i = 0; i < 3; ++i) a.cwX[i] = cwX[i];
+    a.rcpWords = (uint32_t)((0x100000000ull + a.wordsPerRow - 1) / a.wordsPerRow);
+    const long long items = (long long)a.wordsPerRow * DH;
+    if (items >= (1ll << 31)) return cudaErrorInvalidConfiguration;
+    dim3 grid((unsigned)((items + 255) / 256), nFrames);
+    if (K == 2)
+        resizeLinearUpKernel<2><<<grid, 256, 0, stream>>>(a);
+    else if (K == 3)
+        resizeLinearUpKernel<3><<<grid, 256, 0, stream>>>(a);
+    else
+        return cudaErrorInvalidValue;
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }

@@ -113,6 +113,13 @@ cudaError_t launchArea2(const uint8_t *src, uint8_t *dst, long long srcPitch, lo
                         long long dstFrameStride, int DW, int DH, int nFrames, const int32_t cy[2], const int32_t cx[2],
                         cudaStream_t stream);
 
+// Linear up-sampling by K = 2 or 3 on X (any Linear ratio on Y): streaming kernel.  Needs SW % 4 == 0 and
+// 4-byte aligned source / destination rows; DH <= 65535, nFrames <= 65535.
+cudaError_t launchLinearUp(int K, const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch,
+                           long long srcFrameStride, long long dstFrameStride, int SW, int SH, int DW, int DH, int nFrames,
+                           const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const uint32_t cwX[3],
+                           cudaStream_t stream);
+
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D);
 cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_t stream);
 cudaError_t initKernels();  // sets function attributes once per device

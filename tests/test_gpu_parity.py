@@ -387,3 +387,36 @@ def test_area_2to1_streaming_kernel(case):
         flat = np.full((sh, sw), v, np.uint8)
         got, _ = gpu_resize(AREA, flat, sw // 2, sh // 2)
         assert (got == v).all()
+
+
+@pytest.mark.parametrize("kind,deg,sw,sh,dw,dh", [(LANCZOS, 1, 32, 16, 16, 8), (AREA, 0, 32, 16, 16, 8),
+                                                  (LINEAR, 0, 8, 4, 16, 8), (LANCZOS, 2, 24, 12, 16, 8)])
+def test_more_than_65535_frames_in_one_call(kind, deg, sw, sh, dw, dh):
+    """gridDim.z is limited to 65535: the batch entry point must chunk transparently."""
+    torch = pytest.importorskip("torch")
+    n = 70000
+    gen = torch.Generator(device="cuda")
+    gen.manual_seed(7)
+    dsrc = torch.randint(0, 256, (n, sh, sw), dtype=torch.uint8, device="cuda", generator=gen)
+    ddst = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
+    with iqo.make_resizer(kind, deg, sw, sh, dw, dh) as r:
+        r.resize_batch(n, sw, sw * sh, dsrc, dw, dw * dh, ddst, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+    for f in (0, 1, 65534, 65535, 65536, n - 1):
+        rc, want = oracle_resize(kind, dsrc[f].cpu().numpy(), dw, dh, deg)
+        assert rc == 0 and np.array_equal(ddst[f].cpu().numpy(), want), f
+
+
+@pytest.mark.parametrize("case", [(1280, 720, 3840, 2160, "linear_up3"), (64, 36, 192, 108, "linear_up3"),
+                                  (64, 36, 128, 72, "linear_up2"), (64, 36, 128, 100, "linear_up2"),
+                                  (64, 36, 192, 36, "packed"),      # Y pass-through: general kernel
+                                  (68, 10, 204, 23, "linear_up3"), (4, 4, 12, 12, "linear_up3"), (8, 3, 16, 7, "linear_up2")])
+def test_linear_integer_upsampling_kernel(case):
+    sw, sh, dw, dh, kname = case
+    for seed, fill in ((41, None), (0, 255), (0, 0)):
+        src = lcg_image(sh, sw, seed=seed) if fill is None else np.full((sh, sw), fill, np.uint8)
+        rc, want = oracle_resize(LINEAR, src, dw, dh)
+        got, kernel = gpu_resize(LINEAR, src, dw, dh)
+        assert kernel == kname
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, (len(bad), bad[:6].tolist())

@@ -164,7 +164,8 @@ IQO_CUDA_API int iqo_cuda_plan_query(int kind, unsigned degree,
                                      int32_t *coefs, size_t coefCap,
                                      int32_t *first, int32_t *row, size_t indexCap);
 /* Host-only: which kernel IQO_CUDA_PATH_AUTO selects for this shape when the buffers are
- * suitably aligned ("half_sym", "half", "packed", "generic"), and why the more specialised
+ * suitably aligned ("half_small", "half_sym", "half", "area2", "linear_up2", "linear_up3", "packed",
+ * "generic"), and why the more specialised
  * kernels are not eligible.  Both strings are copied NUL-terminated into the caller's buffers. */
 IQO_CUDA_API int iqo_cuda_plan_kernel(int kind, unsigned degree,
                                       size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale,

@@ -98,6 +98,7 @@ size_t alignUp(size_t v, size_t a)
 struct SharedPlan {
     Plan plan;
     HalfPlan half;
+    SmallPlan small;
     PackedPlan packed;
     GenericGeom geom;
     PackedGeom pgeom;
@@ -108,8 +109,10 @@ struct SharedPlan {
     // packed kernel tables
     int32_t *pFirstY, *pNtapY, *pCoefOffY, *pRecX;
     uint32_t *pMagicY, *pCwX;
+    int32_t *sRowsY;      // small-kernel path
+    uint32_t *sMagicY;
     SharedPlan()
-        : device(0), dBorderY(0), dMagicY(0), dBorderX(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0)
+        : device(0), dBorderY(0), dMagicY(0), dBorderX(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), sRowsY(0), sMagicY(0)
     {
     }
     ~SharedPlan();
@@ -193,6 +196,8 @@ SharedPlan::~SharedPlan()
     cudaFree(pNtapY);
     cudaFree(pCoefOffY);
     cudaFree(pRecX);
+    cudaFree(sRowsY);
+    cudaFree(sMagicY);
     cudaFree(pMagicY);
     cudaFree(pCwX);
     cudaGetLastError();
@@ -255,6 +260,44 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
     a.lanczos = r->plan.kind == kLanczos;
     a.workSigned = r->plan.workSigned;
     const bool whole = dstRow0 == 0 && dstRows == size_t(r->plan.y.D) && srcRow0 == 0;
+    // 2:1 Lanczos with at most four non-zero taps per axis (YUV420 chroma planes): streaming kernel
+    if (r->path == IQO_CUDA_PATH_AUTO && r->sp->small.eligible && whole && ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 &&
+        srcFrameStride % 16 == 0 && ((uintptr_t)dst % 8) == 0 && dstSt % 8 == 0 && dstFrameStride % 8 == 0) {
+        const SmallPlan &sm = r->sp->small;
+        SmallArgs q;
+        q.srcPitch = (long long)srcSt;
+        q.dstPitch = (long long)dstSt;
+        q.srcFrameStride = (long long)srcFrameStride;
+        q.dstFrameStride = (long long)dstFrameStride;
+        q.SW = int(r->plan.x.S);
+        q.SH = int(r->plan.y.S);
+        q.DW = int(r->plan.x.D);
+        q.DH = int(r->plan.y.D);
+        q.TY = sm.TY;
+        q.cy0 = sm.cy0;
+        q.NW = sm.NW;
+        q.wbase = sm.wbase;
+        memcpy(q.cY, sm.cY, sizeof q.cY);
+        memcpy(q.cwX, sm.cwX, sizeof q.cwX);
+        q.accInit = sm.accInit;
+        q.workBias = sm.workBias;
+        q.mbX = int(r->plan.x.mainBegin);
+        q.meX = int(r->plan.x.mainEnd);
+        q.mbY = int(r->plan.y.mainBegin);
+        q.meY = int(r->plan.y.mainEnd);
+        q.rowsY = r->sp->sRowsY;
+        q.magicY = r->sp->sMagicY;
+        q.gx = a.x;
+        q.gy = a.y;
+        r->lastKernel = "half_small";
+        for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
+            q.nFrames = int(std::min<size_t>(65535, nFrames - f0));
+            q.src = src + f0 * srcFrameStride;
+            q.dst = dst + f0 * dstFrameStride;
+            CUDA_TRY(launchSmall(q, stream));
+        }
+        return IQO_CUDA_OK;
+    }
     if (r->path == IQO_CUDA_PATH_AUTO && r->half.eligible && whole &&
         ((uintptr_t)src % 4) == 0 && srcSt % 4 == 0 && srcFrameStride % 4 == 0) {
         const HalfPlan &hp = r->half;
@@ -514,6 +557,11 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
         }
     }
     sp->geom = chooseGenericGeom(sp->plan.x.first.data(), sp->plan.x.N, int(sp->plan.x.S), int(sp->plan.x.D));
+    buildSmallPlan(sp->plan, sp->small);
+    if (sp->small.eligible && (!uploadVec(sp->sRowsY, sp->small.rowsY) || !uploadVec(sp->sMagicY, sp->small.magicY))) {
+        cudaGetLastError();
+        sp->small.eligible = false;
+    }
     buildPackedPlan(sp->plan, sp->packed, packedPadNP(sp->plan.x.N / 2 + 1));
     if (sp->packed.eligible) {
         const PackedPlan &q = sp->packed;
@@ -795,8 +843,14 @@ int iqo_cuda_plan_kernel(int kind, unsigned degree, size_t srcW, size_t srcH, si
     buildHalfPlan(p, h);
     PackedPlan q;
     buildPackedPlan(p, q, packedPadNP(p.x.N / 2 + 1));
+    SmallPlan sm;
+    buildSmallPlan(p, sm);
+    const bool area2 = p.kind == kArea && p.x.rD == 1 && p.x.rS == 2 && p.y.rD == 1 && p.y.rS == 2 && p.x.N == 2 && p.y.N == 2 && p.x.S % 16 == 0;
+    const long long kx = (p.x.D % p.x.S == 0) ? p.x.D / p.x.S : 0;
+    const bool linup = p.kind == kLinear && (kx == 2 || kx == 3) && p.x.S % 4 == 0 && !p.y.identity;
     if (kernel && kernelCap)
-        snprintf(kernel, kernelCap, "%s", h.eligible ? (h.symmetric ? "half_sym" : "half") : q.eligible ? "packed" : "generic");
+        snprintf(kernel, kernelCap, "%s", sm.eligible ? "half_small" : h.eligible ? (h.symmetric ? "half_sym" : "half") : area2 ? "area2"
+                                          : linup ? (kx == 2 ? "linear_up2" : "linear_up3") : q.eligible ? "packed" : "generic");
     if (why && whyCap) snprintf(why, whyCap, "%s%s%s", h.why.c_str(), q.eligible ? "" : "; packed: ", q.eligible ? "" : q.why.c_str());
     return IQO_CUDA_OK;
 }

@@ -959,6 +959,181 @@ __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constan
     for (int quad = 0; quad < K; ++quad) *reinterpret_cast<uint32_t *>(out + 4 * quad) = packed[quad];
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Streaming 2:1 x 2:1 Lanczos for kernels with at most four non-zero taps per axis (the pxScale=2
+// chroma planes of YUV420 4K->1080p, Lanczos1).  No shared memory: a thread owns 8 adjacent
+// destination pixels (16 source columns + one word either side) for 6 consecutive destination
+// rows.  Source rows are read once, top to bottom (LDG.128 + 2 LDG.32), spread into 16-bit lane
+// pairs (PRMT) and accumulated straight into the destination rows they belong to: one IMAD per
+// lane pair and tap (packed-lane trick of resizePackedKernel; bias keeps lanes in [0, 65535]).
+// A finished row goes through the dp2a byte-plane horizontal pass and leaves as one 8-byte store.
+// Everything is unrolled, so rows in flight live in registers.  Border rows use masked
+// coefficients + the multiply-high division; border columns are recomputed afterwards from the
+// generic tables, one pixel per thread.
+// ---------------------------------------------------------------------------------------
+constexpr int kSmallRows = 6;
+
+// one destination pixel exactly as the reference computes it (any kind of row / column)
+__device__ __noinline__ uint8_t genericPixel(const AxisDev &gx, const AxisDev &gy, const uint8_t *src, long long pitch, int y, int d,
+                                             int shift, bool lanczos)
+{
+    const int fx = __ldg(gx.first + d), rx = __ldg(gx.row + d);
+    const int fy = __ldg(gy.first + y), ry = __ldg(gy.row + y);
+    const int denoY = __ldg(gy.deno + ry);
+    int nume = 0;
+    for (int i = 0; i < gx.N; ++i) {
+        const int cx = __ldg(gx.coef + rx * gx.N + i);
+        if (cx == 0) continue;
+        const int col = min(max(fx + i, 0), gx.S - 1);
+        int acc = 0;
+        for (int t = 0; t < gy.N; ++t) {
+            const int row = min(max(fy + t, 0), gy.S - 1);
+            acc += __ldg(gy.coef + ry * gy.N + t) * (int)__ldg(src + (long long)row * pitch + col);
+        }
+        if (denoY != 0) acc = ((int)(short)acc * 64) / denoY;
+        nume += cx * (int)(short)acc;
+    }
+    return finishPixel(nume, lanczos ? __ldg(gx.deno + rx) : 0, shift);
+}
+
+template <int TY, int NW, int WB, bool EDGE>
+__device__ __forceinline__ void smallRows(const SmallArgs &a, const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, int c, int y0)
+{
+    constexpr int R = kSmallRows;
+    constexpr int NS = 2 * R + TY - 2;  // source rows consumed
+    const int B = a.workBias;
+    const uint32_t biased = (uint32_t)B | ((uint32_t)B << 16);
+    int coef[R][TY];
+    int deno[R];
+    uint32_t magic[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        deno[j] = 0;
+        magic[j] = 0;
+#pragma unroll
+        for (int t = 0; t < TY; ++t) coef[j][t] = a.cY[t];
+        if (EDGE) {
+            const int y = y0 + j;
+            if (y < a.DH && (y < a.mbY || y >= a.meY)) {
+                const int row = __ldg(a.gy.row + y);
+                deno[j] = __ldg(a.gy.deno + row);
+                magic[j] = __ldg(a.magicY + row);
+#pragma unroll
+                for (int t = 0; t < TY; ++t) coef[j][t] = __ldg(a.rowsY + row * 4 + t);
+            }
+        }
+    }
+    uint32_t acc[R][10];
+#pragma unroll
+    for (int j = 0; j < R; ++j)
+#pragma unroll
+        for (int m = 0; m < 10; ++m) acc[j][m] = (EDGE && deno[j]) ? 0u : biased;
+
+    const uint8_t *base = src + 16 * c;
+    const int prevOff = (c > 0) ? -4 : 0, nextOff = (16 * c + 16 < a.SW) ? 16 : 12;  // clamped: edge values meet zero weights
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        int row = 2 * y0 + a.cy0 + s;
+        if (EDGE) row = min(max(row, 0), a.SH - 1);
+        const uint8_t *rp = base + (long long)row * a.srcPitch;
+        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(rp));
+        const uint32_t wp = __ldg(reinterpret_cast<const uint32_t *>(rp + prevOff));
+        const uint32_t wn = __ldg(reinterpret_cast<const uint32_t *>(rp + nextOff));
+        uint32_t L[10];
+        L[0] = prmt(wp, 0u, 0x4342);
+        L[1] = prmt(w.x, 0u, 0x4140);
+        L[2] = prmt(w.x, 0u, 0x4342);
+        L[3] = prmt(w.y, 0u, 0x4140);
+        L[4] = prmt(w.y, 0u, 0x4342);
+        L[5] = prmt(w.z, 0u, 0x4140);
+        L[6] = prmt(w.z, 0u, 0x4342);
+        L[7] = prmt(w.w, 0u, 0x4140);
+        L[8] = prmt(w.w, 0u, 0x4342);
+        L[9] = prmt(wn, 0u, 0x4140);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int t = s - 2 * j;
+            if (t >= 0 && t < TY) {
+                const uint32_t cf = (uint32_t)coef[j][t];
+#pragma unroll
+                for (int m = 1 + WB; m <= 8 + WB + NW - 1; ++m) acc[j][m] += L[m] * cf;
+            }
+        }
+        // the destination row whose last tap this was is complete
+        if (s >= TY - 1 && ((s - (TY - 1)) & 1) == 0) {
+            const int j = (s - (TY - 1)) >> 1;
+            const int y = y0 + j;
+            if (j < R && y < a.DH) {
+                if (EDGE && deno[j]) {
+#pragma unroll
+                    for (int m = 1 + WB; m <= 8 + WB + NW - 1; ++m) {
+                        const uint32_t lo = acc[j][m] & 0xffffu;
+                        const uint32_t hi = (acc[j][m] >> 16) + ((lo & 0x8000u) ? 1u : 0u);
+                        uint32_t out = 0;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int n = (int)(short)(h ? hi : lo) * 64;
+                            const uint32_t mag = (uint32_t)abs(n);
+                            const int qv = magic[j] ? (int)__umulhi(mag, magic[j]) : (int)mag;
+                            const int wv = (int)(short)(n < 0 ? -qv : qv) + B;
+                            out |= ((uint32_t)wv & 0xffffu) << (16 * h);
+                        }
+                        acc[j][m] = out;
+                    }
+                }
+                int v[8];
+#pragma unroll
+                for (int p = 0; p < 8; ++p) {
+                    int x = a.accInit;
+#pragma unroll
+                    for (int q = 0; q < NW; ++q) x = dp2a_lo_uu(acc[j][1 + p + WB + q], a.cwX[q], x);
+                    x >>= 8;
+#pragma unroll
+                    for (int q = 0; q < NW; ++q) x = dp2a_hi_us(acc[j][1 + p + WB + q], a.cwX[q], x);
+                    v[p] = x >> 12;
+                }
+                uint2 o;
+                o.x = packSatU8(v[1], v[0], packSatU8(v[3], v[2], 0u));
+                o.y = packSatU8(v[5], v[4], packSatU8(v[7], v[6], 0u));
+                *reinterpret_cast<uint2 *>(dst + (long long)y * a.dstPitch + 8 * c) = o;
+            }
+        }
+    }
+}
+
+template <int TY, int NW, int WB>
+__global__ void __launch_bounds__(128) resizeHalfSmallKernel(const __grid_constant__ SmallArgs a)
+{
+    const int c = blockIdx.x * 128 + threadIdx.x;  // 8-pixel chunk of the row
+    const int y0 = blockIdx.y * kSmallRows;
+    const uint8_t *__restrict__ src = a.src + (long long)blockIdx.z * a.srcFrameStride;
+    uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
+    const int chunks = a.DW >> 3;
+    if (c < chunks) {
+        const int lastSrcRow = 2 * y0 + a.cy0 + 2 * kSmallRows + TY - 3;
+        const bool edge = (2 * y0 + a.cy0 < 0) || (lastSrcRow >= a.SH) || (y0 < a.mbY) || (y0 + kSmallRows > a.meY);
+        if (edge)
+            smallRows<TY, NW, WB, true>(a, src, dst, c, y0);
+        else
+            smallRows<TY, NW, WB, false>(a, src, dst, c, y0);
+    }
+    // border columns of this block's pixel range
+    const int px0 = blockIdx.x * 128 * 8, px1 = min(px0 + 128 * 8, a.DW);
+    const int l0 = px0, l1 = min(px1, a.mbX);                 // left border columns [l0, l1)
+    const int r0 = max(px0, max(a.meX, a.mbX)), r1 = px1;     // right border columns [r0, r1)
+    const int nl = max(l1 - l0, 0), nr = max(r1 - r0, 0);
+    if (nl + nr > 0) {
+        __syncthreads();  // the streamed stores of these pixels come first
+        const int rows = min(kSmallRows, a.DH - y0);
+        for (int item = threadIdx.x; item < rows * (nl + nr); item += blockDim.x) {
+            const int r = item / (nl + nr), k = item - r * (nl + nr);
+            const int d = (k < nl) ? l0 + k : r0 + (k - nl);
+            dst[(long long)(y0 + r) * a.dstPitch + d] = genericPixel(a.gx, a.gy, src, a.srcPitch, y0 + r, d, 20, true);
+        }
+    }
+}
+
 }  // namespace
 
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D)
@@ -1153,6 +1328,27 @@ cudaError_t launchLinearUp(int K, const uint8_t *src, uint8_t *dst, long long sr
         return cudaErrorInvalidValue;
     g_launches.fetch_add(1);
     return cudaGetLastError();
+}
+
+cudaError_t launchSmall(const SmallArgs &a, cudaStream_t stream)
+{
+    const int chunks = a.DW / 8;
+    dim3 grid((chunks + 127) / 128, (a.DH + kSmallRows - 1) / kSmallRows, a.nFrames);
+    if (grid.y > 65535) return cudaErrorInvalidConfiguration;
+    g_launches.fetch_add(1);
+#define IQO_SMALL_CASE(T, N, W)                                      \
+    if (a.TY == T && a.NW == N && a.wbase == W) {                    \
+        resizeHalfSmallKernel<T, N, W><<<grid, 128, 0, stream>>>(a); \
+        return cudaGetLastError();                                   \
+    }
+#define IQO_SMALL_TY(T) IQO_SMALL_CASE(T, 1, 0) IQO_SMALL_CASE(T, 2, 0) IQO_SMALL_CASE(T, 2, -1) IQO_SMALL_CASE(T, 3, -1)
+    IQO_SMALL_TY(1)
+    IQO_SMALL_TY(2)
+    IQO_SMALL_TY(3)
+    IQO_SMALL_TY(4)
+#undef IQO_SMALL_TY
+#undef IQO_SMALL_CASE
+    return cudaErrorInvalidValue;
 }
 
 int halfSourceRowsMax()

@@ -120,6 +120,24 @@ cudaError_t launchLinearUp(int K, const uint8_t *src, uint8_t *dst, long long sr
                            const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const uint32_t cwX[3],
                            cudaStream_t stream);
 
+// Arguments of the streaming 2:1 small-kernel path (plan.hpp SmallPlan).
+struct SmallArgs {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long srcPitch, dstPitch, srcFrameStride, dstFrameStride;
+    int SW, SH, DW, DH;
+    int nFrames;
+    int TY, cy0, NW, wbase;
+    int32_t cY[4];
+    uint32_t cwX[3];
+    int accInit, workBias;
+    int mbX, meX, mbY, meY;
+    const int32_t *rowsY;      // [numRowsY][4]
+    const uint32_t *magicY;    // [numRowsY]
+    AxisDev gx, gy;            // generic tables: border pixels are recomputed from them
+};
+cudaError_t launchSmall(const SmallArgs &a, cudaStream_t stream);
+
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D);
 cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_t stream);
 cudaError_t initKernels();  // sets function attributes once per device

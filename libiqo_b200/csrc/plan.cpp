@@ -616,3 +616,76 @@ void buildPackedPlan(const Plan &p, PackedPlan &q, int padNP)
 }
 
 }  // namespace iqo_b200
+
+// ---------------------------------------------------------------------------------------------
+// Plan of the streaming small-kernel 2:1 path
+// ---------------------------------------------------------------------------------------------
+namespace iqo_b200 {
+
+void buildSmallPlan(const Plan &p, SmallPlan &s)
+{
+    s.eligible = false;
+    s.why.clear();
+    const AxisPlan &X = p.x, &Y = p.y;
+    if (p.kind != kLanczos) { s.why = "not Lanczos"; return; }
+    if (X.rD != 1 || X.rS != 2 || Y.rD != 1 || Y.rS != 2) { s.why = "not 2:1 on both axes"; return; }
+    if (X.S % 16 != 0) { s.why = "source width not a multiple of 16"; return; }
+    // trimmed main-phase taps
+    int ly = 0, ty = Y.N;
+    while (ly < Y.N - 1 && Y.coef[ly] == 0) ++ly;
+    while (ty > ly + 1 && Y.coef[ty - 1] == 0) --ty;
+    int lx = 0, tx = X.N;
+    while (lx < X.N - 1 && X.coef[lx] == 0) ++lx;
+    while (tx > lx + 1 && X.coef[tx - 1] == 0) --tx;
+    s.TY = ty - ly;
+    s.cy0 = 1 - Y.N / 2 + ly;
+    s.TX = tx - lx;
+    s.cx0 = 1 - X.N / 2 + lx;
+    if (s.TY > 4 || s.TX > 4) { s.why = "more than four non-zero taps"; return; }
+    if (s.cx0 < -2 || s.cx0 + s.TX - 1 > 3) { s.why = "horizontal window outside the thread's column range"; return; }
+    for (int t = 0; t < 4; ++t) s.cY[t] = (t < s.TY) ? Y.coef[ly + t] : 0;
+    // every coefficient row at the main tap positions; a border row must not need other positions
+    s.rowsY.assign(size_t(Y.numRows) * 4, 0);
+    s.magicY.assign(size_t(Y.numRows), 0);
+    long long wmin = 0, wmax = 0;
+    for (int r = 0; r < Y.numRows; ++r) {
+        long long pos = 0, neg = 0;
+        for (int i = 0; i < Y.N; ++i) {
+            const int c = Y.coef[size_t(r) * Y.N + i];
+            if (c != 0 && (i < ly || i >= ty)) { s.why = "border row uses a tap outside the trimmed window"; return; }
+            (c > 0 ? pos : neg) += c;
+        }
+        for (int t = 0; t < s.TY; ++t) s.rowsY[size_t(r) * 4 + t] = Y.coef[size_t(r) * Y.N + ly + t];
+        long long lo = 255 * neg, hi = 255 * pos;
+        if (lo < -32768 || hi > 32767) { s.why = "vertical sum may wrap int16"; return; }
+        const int den = Y.deno[size_t(r)];
+        if (den != 0) {
+            if (den < 0 || den > 255) { s.why = "border denominator out of range"; return; }
+            lo = lo * 64 / den - 1;
+            hi = hi * 64 / den + 1;
+            if (den > 1) s.magicY[size_t(r)] = uint32_t((1ull << 32) / uint64_t(den) + 1);
+        }
+        wmin = std::min(wmin, lo);
+        wmax = std::max(wmax, hi);
+    }
+    s.workBias = int(-wmin);
+    if (wmax + s.workBias > 65535) { s.why = "intermediate range wider than a 16-bit lane"; return; }
+    for (int64_t d = 0; d < X.D; ++d)
+        if (X.deno[size_t(X.row[d])] < 0) { s.why = "negative border denominator"; return; }
+    // horizontal pair words: column 2d + cx0 + i sits in half (par + i) & 1 of word d + wbase + ((par + i) >> 1)
+    const int par = s.cx0 & 1;
+    s.wbase = floorDivI(s.cx0, 2);
+    s.NW = (par + s.TX + 1) / 2;
+    long long sum = 0;
+    for (int i = 0; i < X.N; ++i) sum += X.coef[i];
+    for (int w = 0; w < 3; ++w) {
+        const int ia = 2 * w - par, ib = 2 * w + 1 - par;
+        const int ca = (ia >= 0 && ia < s.TX) ? X.coef[lx + ia] : 0;
+        const int cb = (ib >= 0 && ib < s.TX) ? X.coef[lx + ib] : 0;
+        s.cwX[w] = (w < s.NW) ? pairWord(ca, cb) : 0u;
+    }
+    s.accInit = int((1ll << (p.shift - 1)) - (long long)s.workBias * sum);
+    s.eligible = true;
+}
+
+}  // namespace iqo_b200

@@ -127,3 +127,25 @@ struct PackedPlan {
 void buildPackedPlan(const Plan &plan, PackedPlan &q, int padNP);
 
 }  // namespace iqo_b200
+
+namespace iqo_b200 {
+
+// 2:1 x 2:1 single-phase Lanczos whose kernel has at most four non-zero taps per axis (the
+// pxScale=2 chroma planes of YUV420, Lanczos1): streamed without shared memory
+// (kernels.cu: resizeHalfSmallKernel).
+struct SmallPlan {
+    bool eligible;
+    std::string why;
+    int TY, cy0;                 // destination row y reads source rows 2y + cy0 .. 2y + cy0 + TY - 1
+    int32_t cY[4];
+    std::vector<int32_t> rowsY;  // [numRowsY][4]: every coefficient row at those tap positions (border rows masked)
+    std::vector<uint32_t> magicY;
+    int TX, cx0;                 // destination column d reads source columns 2d + cx0 .. 2d + cx0 + TX - 1
+    int NW, wbase;               // ... = pair words d + wbase .. d + wbase + NW - 1
+    uint32_t cwX[3];             // bytes lo_a, lo_b, hi_a, hi_b per pair word
+    int accInit, workBias;
+};
+
+void buildSmallPlan(const Plan &plan, SmallPlan &s);
+
+}  // namespace iqo_b200

@@ -210,11 +210,13 @@ HALF_CASES = [
     # (degree, pxScale, srcW, srcH, srcPad, dstPad, expected kernel)
     (3, 1, 1920, 1080, 0, 0, "half_sym"),     # cfg4
     (2, 1, 3840, 2160, 0, 0, "half_sym"),     # cfg3 luma
-    (2, 2, 1920, 1080, 0, 0, "half"),         # cfg3 chroma (asymmetric 4-tap table)
+    (2, 2, 1920, 1080, 0, 0, "half_small"),   # cfg3 chroma (asymmetric 4-tap table): streaming kernel
+    (4, 2, 480, 272, 0, 0, "half"),           # asymmetric 8-tap table: tiled kernel, general pair words
+    (2, 2, 488, 250, 4, 0, "half"),           # width not a multiple of 16: the streaming kernel declines
     (3, 1, 480, 272, 0, 0, "half_sym"),       # several tiles, last tile row partial
     (3, 1, 488, 250, 4, 0, "half_sym"),       # width not a multiple of the tile, odd dstH, padded src
     (2, 1, 264, 100, 8, 3, "half_sym"),       # unaligned dst stride -> byte stores
-    (1, 1, 256, 64, 0, 0, "half_sym"),
+    (1, 1, 256, 64, 0, 0, "half_small"),
     (3, 2, 960, 540, 0, 0, "generic"),        # negative border denominator: specialised kernel declines
     (2, 1, 64, 32, 0, 0, "half_sym"),         # image smaller than a tile
     (3, 1, 28, 26, 0, 0, "half_sym"),
@@ -231,7 +233,7 @@ def test_half_kernel(case, path):
     assert rc == 0
     got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad, path=path)
     # host images are staged on the device with a 16-byte aligned pitch, so AUTO feeds the tile by TMA
-    assert kernel == (kname + "_tma" if path == iqo.PATH_AUTO and kname != "generic" else kname)
+    assert kernel == (kname + "_tma" if path == iqo.PATH_AUTO and kname in ("half", "half_sym") else kname)
     assert iqo.plan_kernel(LANCZOS, deg, sw, sh, dw, dh, px)[0] == kname
     bad = np.argwhere(got != want)
     assert bad.size == 0, (len(bad), bad[:8].tolist())
@@ -252,6 +254,15 @@ def test_half_kernel_extreme_values():
             got, kernel = gpu_resize(LANCZOS, src, sw // 2, sh // 2, deg, px)
             assert kernel.startswith("half")
             assert np.array_equal(got, want), (name, deg, px)
+    # the tiled kernel on the same small-tap shapes (the streaming kernel needs 16-column multiples)
+    sw = 488
+    yy, xx = np.mgrid[0:sh, 0:sw]
+    for src in (np.full((sh, sw), 255, np.uint8), (((yy + xx) & 1) * 255).astype(np.uint8)):
+        for deg, px in ((2, 2), (1, 1)):
+            rc, want = oracle_resize(LANCZOS, src, sw // 2, sh // 2, deg, px)
+            got, kernel = gpu_resize(LANCZOS, src, sw // 2, sh // 2, deg, px)
+            assert kernel.startswith("half") and kernel != "half_small"
+            assert np.array_equal(got, want), (deg, px)
 
 
 def test_half_kernel_device_pitches():

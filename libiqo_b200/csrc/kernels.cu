@@ -1032,14 +1032,25 @@ __device__ __forceinline__ void smallRows(const SmallArgs &a, const uint8_t *__r
 
     const uint8_t *base = src + 16 * c;
     const int prevOff = (c > 0) ? -4 : 0, nextOff = (16 * c + 16 < a.SW) ? 16 : 12;  // clamped: edge values meet zero weights
-#pragma unroll
-    for (int s = 0; s < NS; ++s) {
+    // source rows are fetched two rows ahead of their use (the loop is fully unrolled, so the
+    // three buffers are plain registers): global-load latency overlaps the arithmetic
+    auto fetch = [&](int s, uint4 &w, uint32_t &wp, uint32_t &wn) {
         int row = 2 * y0 + a.cy0 + s;
         if (EDGE) row = min(max(row, 0), a.SH - 1);
         const uint8_t *rp = base + (long long)row * a.srcPitch;
-        const uint4 w = __ldg(reinterpret_cast<const uint4 *>(rp));
-        const uint32_t wp = __ldg(reinterpret_cast<const uint32_t *>(rp + prevOff));
-        const uint32_t wn = __ldg(reinterpret_cast<const uint32_t *>(rp + nextOff));
+        w = __ldg(reinterpret_cast<const uint4 *>(rp));
+        wp = __ldg(reinterpret_cast<const uint32_t *>(rp + prevOff));
+        wn = __ldg(reinterpret_cast<const uint32_t *>(rp + nextOff));
+    };
+    uint4 bw[3];
+    uint32_t bp[3], bn[3];
+    fetch(0, bw[0], bp[0], bn[0]);
+    if (NS > 1) fetch(1, bw[1], bp[1], bn[1]);
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+        if (s + 2 < NS) fetch(s + 2, bw[(s + 2) % 3], bp[(s + 2) % 3], bn[(s + 2) % 3]);
+        const uint4 w = bw[s % 3];
+        const uint32_t wp = bp[s % 3], wn = bn[s % 3];
         uint32_t L[10];
         L[0] = prmt(wp, 0u, 0x4342);
         L[1] = prmt(w.x, 0u, 0x4140);

@@ -57,9 +57,11 @@ enum {
 enum {
     IQO_CUDA_PATH_AUTO = 0,    /* fastest eligible kernel                                          */
     IQO_CUDA_PATH_GENERIC = 1, /* the general tile kernel (any stride, ratio, kind)                */
-    IQO_CUDA_PATH_NO_TMA = 2   /* like AUTO, but specialised kernels read the source with plain
-                                  global loads instead of TMA (what AUTO itself does when the
-                                  source pitch or base is not 16-byte aligned)                     */
+    IQO_CUDA_PATH_NO_TMA = 2,  /* like NO_STREAM, but the tiled 2:1 Lanczos kernel reads the source
+                                  with plain global loads instead of TMA (what AUTO itself does
+                                  when the source pitch or base is not 8/16-byte aligned)          */
+    IQO_CUDA_PATH_NO_STREAM = 3 /* like AUTO, but 2:1 Lanczos uses the tiled (TMA) kernel instead of
+                                  the warp-streaming one                                           */
 };
 
 /* Replaces: I{Lanczos,Area,Linear}ResizerImpl::init (reference src/IQOLanczosResizerImpl.hpp:17-22,

@@ -104,15 +104,15 @@ struct SharedPlan {
     PackedGeom pgeom;
     int device;
     AxisTables tx, ty;
-    uint32_t *dBorderY, *dMagicY;
-    int32_t *dBorderX;
+    uint32_t *dBorderY, *dMagicY, *dSBorderY;
+    int32_t *dBorderX, *dBorderXo;
     // packed kernel tables
     int32_t *pFirstY, *pNtapY, *pCoefOffY, *pRecX;
     uint32_t *pMagicY, *pCwX;
     int32_t *sRowsY;      // small-kernel path
     uint32_t *sMagicY;
     SharedPlan()
-        : device(0), dBorderY(0), dMagicY(0), dBorderX(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), sRowsY(0), sMagicY(0)
+        : device(0), dBorderY(0), dMagicY(0), dSBorderY(0), dBorderX(0), dBorderXo(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), sRowsY(0), sMagicY(0)
     {
     }
     ~SharedPlan();
@@ -145,7 +145,7 @@ struct iqo_cuda_resizer {
     cudaStream_t *stream;
     uint8_t **dSrc, **dDst;
     int device;
-    bool useTma;
+    bool useTma, useStream;
     int path;
     const char *lastKernel;
     size_t srcPitch, dstPitch;  // device pitches of the staging frames
@@ -154,7 +154,7 @@ struct iqo_cuda_resizer {
     iqo_cuda_resizer(const std::shared_ptr<SharedPlan> &s, Workspace *w)
         : sp(s), ws(w), plan(s->plan), half(s->half), tx(s->tx), ty(s->ty), geom(s->geom), dBorderY(s->dBorderY),
           dMagicY(s->dMagicY), dBorderX(s->dBorderX), stream(w->stream), dSrc(w->dSrc), dDst(w->dDst), device(s->device),
-          useTma(true), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
+          useTma(true), useStream(true), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
     {
     }
 };
@@ -192,6 +192,8 @@ SharedPlan::~SharedPlan()
     cudaFree(dBorderY);
     cudaFree(dMagicY);
     cudaFree(dBorderX);
+    cudaFree(dSBorderY);
+    cudaFree(dBorderXo);
     cudaFree(pFirstY);
     cudaFree(pNtapY);
     cudaFree(pCoefOffY);
@@ -341,9 +343,48 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         h.borderX = r->dBorderX;
         h.NX = r->plan.x.N;
         h.zero = 0;
+        h.bandPairs = 0;
+        h.delta = 0;
+        h.zmask = 0;
+        h.NXH = 0;
+        h.skipHi0 = 0;
+        memset(h.cwXo, 0, sizeof h.cwXo);
         const int boxRows = 4 * (h.tileRows / 2 + hp.NG - 1);
         const bool tmaOk = r->useTma && encodeTiled() != 0 && boxRows <= halfSourceRowsMax() &&
                            ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 && (nFrames == 1 || srcFrameStride % 16 == 0);
+        // streaming variant (a warp per column strip and row band): 8-byte aligned source rows
+        const bool streamOk = r->useStream && hp.sEligible && h.SW % 8 == 0 && ((uintptr_t)src % 8) == 0 && srcSt % 8 == 0 &&
+                              srcFrameStride % 8 == 0;
+        if (streamOk) {
+            // bands: enough warps to fill the device several times over, but long enough that the
+            // ring refill and the re-read halo rows of a band stay small
+            const long long strips = (h.DW + 119) / 120, pairs = (h.DH + 1) / 2;
+            int bandPairs = 96;
+            if (const char *e = getenv("IQO_CUDA_STREAM_BAND_PAIRS")) bandPairs = std::max(1, atoi(e));
+            const long long wantWarps = 6ll * 148 * 20;
+            while (bandPairs > 24 && strips * ((pairs + bandPairs - 1) / bandPairs) * (long long)nFrames < wantWarps) bandPairs /= 2;
+            const long long bands = (pairs + bandPairs - 1) / bandPairs;
+            h.bandPairs = int((pairs + bands - 1) / bands);
+            h.tileShift = 0;
+            h.qmin = hp.sQmin;
+            h.NG = hp.sNG;
+            memcpy(h.cwY, hp.sCwY, sizeof h.cwY);
+            h.borderY = r->sp->dSBorderY;
+            h.borderX = r->sp->dBorderXo;
+            h.delta = hp.sDelta;
+            h.zmask = hp.sZ;
+            h.NXH = hp.NXH;
+            h.skipHi0 = hp.skipHi0;
+            memcpy(h.cwXo, hp.cwXo, sizeof h.cwXo);
+            r->lastKernel = hp.symmetric ? "half_sym_stream" : "half_stream";
+            for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
+                h.src = src + f0 * srcFrameStride;
+                h.dst = dst + f0 * dstFrameStride;
+                h.nFrames = int(std::min<size_t>(65535, nFrames - f0));
+                CUDA_TRY(launchHalfStream(h, stream));
+            }
+            return IQO_CUDA_OK;
+        }
         for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
             const size_t nf = std::min<size_t>(65535, nFrames - f0);
             h.src = src + f0 * srcFrameStride;
@@ -554,6 +595,11 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
             cudaMemcpy(sp->dBorderX, hp.borderX.data(), hp.borderX.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
             cudaGetLastError();
             sp->half.eligible = false;
+        }
+        if (sp->half.eligible && sp->half.sEligible &&
+            (!halfStreamHasKernel(hp.sNG, hp.NXH) || !uploadVec(sp->dSBorderY, hp.sBorderY) || !uploadVec(sp->dBorderXo, hp.borderXo))) {
+            cudaGetLastError();
+            sp->half.sEligible = false;
         }
     }
     sp->geom = chooseGenericGeom(sp->plan.x.first.data(), sp->plan.x.N, int(sp->plan.x.S), int(sp->plan.x.D));
@@ -786,8 +832,9 @@ int iqo_cuda_sync(iqo_cuda_resizer *r)
 
 int iqo_cuda_set_path(iqo_cuda_resizer *r, int path)
 {
-    if (!r || path < 0 || path > IQO_CUDA_PATH_NO_TMA) return fail(IQO_CUDA_E_ARG, "bad path");
+    if (!r || path < 0 || path > IQO_CUDA_PATH_NO_STREAM) return fail(IQO_CUDA_E_ARG, "bad path");
     r->useTma = (path != IQO_CUDA_PATH_NO_TMA);
+    r->useStream = (path == IQO_CUDA_PATH_AUTO);
     r->path = (path == IQO_CUDA_PATH_GENERIC) ? IQO_CUDA_PATH_GENERIC : IQO_CUDA_PATH_AUTO;
     return IQO_CUDA_OK;
 }

@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <type_traits>
 
 namespace iqo_b200 {
 
@@ -386,11 +387,11 @@ __device__ __forceinline__ void halfVertical(const HalfArgs &a, const uint8_t *_
 // table entry of column c0.
 template <int NWX>
 __device__ __noinline__ void halfBorderColumns(const HalfArgs &a, const uint32_t *W, uint8_t *dstTile, const int32_t *bx,
-                                               int tx0, int c0, int c1, int th)
+                                               int tx0, int c0, int c1, int th, int tid, int nthr)
 {
     constexpr int kBase = 4 - (NWX - 1) / 2;
     const int nb = c1 - c0;
-    for (int item = threadIdx.x; item < nb * th; item += blockDim.x) {
+    for (int item = tid; item < nb * th; item += nthr) {
         const int r = item / nb;
         const int j = item - r * nb;
         const int d = c0 + j;
@@ -414,104 +415,113 @@ __device__ __noinline__ void halfStoreBytes(uint8_t *out, uint2 o, int lo, int h
     for (int p = lo; p < hi; ++p) out[p] = (uint8_t)(((p < 4 ? o.x : o.y) >> (8 * (p & 3))) & 0xffu);
 }
 
+// Horizontal pass of eight adjacent destination pixels from the 16 pair words n[] that start at
+// the group's first 16-byte chunk; returns the eight saturated bytes.
+template <int NWX, bool SYM, bool ENDHI>
+__device__ __forceinline__ uint2 halfGroupPixels(const HalfArgs &a, const uint32_t (&n)[16])
+{
+    constexpr int kBase = 4 - (NWX - 1) / 2;  // pair word of tap pair 0 for pixel 0 (wa + 4)
+    int v[8];
+    if (SYM) {
+        constexpr int m = NWX / 2;
+        // swapped halves of the words that serve as mirror partners
+        uint32_t sw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sw[i] = (i >= kBase + m + 1 && i <= kBase + NWX - 2 + 7) ? prmt(n[i], n[i], 0x1032) : 0u;
+        // mirrored pairs are added as packed u16 halves (no carry can cross: every
+        // half-sum fits 16 bits).  The third addend is a kernel argument that is always
+        // 0: a three-input add can only be an IADD3, which keeps these adds off the
+        // multiplier pipe that the dp2a/dp4a instructions saturate.
+        uint32_t sum[8][m > 1 ? m - 1 : 1];
+#pragma unroll
+        for (int j = 1; j < m; ++j)
+#pragma unroll
+            for (int p = 0; p < 8; ++p) sum[p][j - 1] = n[kBase + p + j] + sw[kBase + p + NWX - 1 - j] + a.zero;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            const uint32_t ctr = n[kBase + p + m];
+            const uint32_t ends = prmt(n[kBase + p], n[kBase + p + NWX - 1], 0x3254);
+            // low byte plane first; the high plane continues from (low >> 8):
+            // floor((lo + 256 hi) / 2^20) == floor((floor(lo / 256) + hi) / 2^12)
+            int acc = a.accInit;
+#pragma unroll
+            for (int j = 1; j < m; ++j) acc = dp2a_lo_uu(sum[p][j - 1], a.cwXs[j - 1], acc);
+            acc = dp2a_lo_uu(ctr, a.cwXs[m - 1], acc);
+            acc = dp2a_lo_uu(ends, a.cwXs[m], acc);
+            acc >>= 8;
+#pragma unroll
+            for (int j = 1; j < m; ++j) acc = dp2a_hi_us(sum[p][j - 1], a.cwXs[j - 1], acc);
+            acc = dp2a_hi_us(ctr, a.cwXs[m - 1], acc);
+            if (ENDHI) acc = dp2a_hi_us(ends, a.cwXs[m], acc);  // skipped when both end taps fit the low byte plane
+            v[p] = acc >> 12;
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            int acc = a.accInit;
+#pragma unroll
+            for (int j = 0; j < NWX; ++j) acc = dp2a_lo_uu(n[kBase + p + j], a.cwX[j], acc);
+            acc >>= 8;
+#pragma unroll
+            for (int j = 0; j < NWX; ++j) acc = dp2a_hi_us(n[kBase + p + j], a.cwX[j], acc);
+            v[p] = acc >> 12;
+        }
+    }
+    uint2 o;
+    o.x = packSatU8(v[1], v[0], packSatU8(v[3], v[2], 0u));
+    o.y = packSatU8(v[5], v[4], packSatU8(v[7], v[6], 0u));
+    return o;
+}
+
+// Group l of a W row `wr` (tiled variants: swizzled chunks), first pixel d0.
+template <int NWX, bool SYM, bool ENDHI>
+__device__ __forceinline__ void halfGroup(const HalfArgs &a, const uint32_t *wr, uint8_t *__restrict__ out, int d0, int l)
+{
+    int pc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) pc[j] = swzWord(4 * (2 * l + j));
+    // 8-byte store when the pixel group is 8-aligned, two 4-byte stores when the tile grid is
+    // shifted by 4 (TMA variant), bytes for partial groups or unaligned destinations
+    const bool vecStore = a.dstVec && d0 >= 0 && (d0 + 8 <= a.DW);
+    const bool vec8 = (d0 & 7) == 0;
+    // a group cut in half by the image edge (shifted grid): one aligned 4-byte store
+    const bool halfLo = a.dstVec && !vecStore && d0 >= 0 && d0 + 4 == a.DW;
+    const bool halfHi = a.dstVec && !vecStore && d0 == -4 && a.DW >= 4;
+    uint32_t n[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint4 q = *reinterpret_cast<const uint4 *>(wr + pc[j]);
+        n[4 * j] = q.x;
+        n[4 * j + 1] = q.y;
+        n[4 * j + 2] = q.z;
+        n[4 * j + 3] = q.w;
+    }
+    const uint2 o = halfGroupPixels<NWX, SYM, ENDHI>(a, n);
+    if (vecStore) {
+        if (vec8) {
+            *reinterpret_cast<uint2 *>(out) = o;
+        } else {
+            *reinterpret_cast<uint32_t *>(out) = o.x;
+            *reinterpret_cast<uint32_t *>(out + 4) = o.y;
+        }
+    } else if (halfLo || halfHi) {
+        if (halfLo) *reinterpret_cast<uint32_t *>(out) = o.x;
+        if (halfHi) *reinterpret_cast<uint32_t *>(out + 4) = o.y;
+    } else {
+        halfStoreBytes(out, o, max(0, -d0), min(8, a.DW - d0));
+    }
+}
+
 // Horizontal pass of a tile + border columns.  The caller has synchronised after the vertical pass.
 template <int NWX, bool SYM, bool ENDHI>
 __device__ __forceinline__ void halfHorizontal(const HalfArgs &a, const uint32_t *W, uint8_t *__restrict__ dst,
                                                int xs0, int tx0, int ty0, int th)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    constexpr int kBase = 4 - (NWX - 1) / 2;  // pair word of tap pair 0 for pixel 0 (wa + 4)
     const int txEnd = min(tx0 + kHalfTileW, a.DW);
     const int groups = (txEnd - tx0 + 7) >> 3;  // 8-pixel groups holding at least one pixel of the image
 
-    // eight adjacent destination pixels (group l) of local row r
-    auto doGroup = [&](const uint32_t *wr, uint8_t *out, int l) {
-        const int d0 = tx0 + 8 * l;
-        int pc[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) pc[j] = swzWord(4 * (2 * l + j));
-        // 8-byte store when the pixel group is 8-aligned, two 4-byte stores when the tile grid is
-        // shifted by 4 (TMA variant), bytes for partial groups or unaligned destinations
-        const bool vecStore = a.dstVec && d0 >= 0 && (d0 + 8 <= a.DW);
-        const bool vec8 = (d0 & 7) == 0;
-        // a group cut in half by the image edge (shifted grid): one aligned 4-byte store
-        const bool halfLo = a.dstVec && !vecStore && d0 >= 0 && d0 + 4 == a.DW;
-        const bool halfHi = a.dstVec && !vecStore && d0 == -4 && a.DW >= 4;
-        {
-        uint32_t n[16];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const uint4 q = *reinterpret_cast<const uint4 *>(wr + pc[j]);
-            n[4 * j] = q.x;
-            n[4 * j + 1] = q.y;
-            n[4 * j + 2] = q.z;
-            n[4 * j + 3] = q.w;
-        }
-        int v[8];
-        if (SYM) {
-            constexpr int m = NWX / 2;
-            // swapped halves of the words that serve as mirror partners
-            uint32_t sw[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) sw[i] = (i >= kBase + m + 1 && i <= kBase + NWX - 2 + 7) ? prmt(n[i], n[i], 0x1032) : 0u;
-            // mirrored pairs are added as packed u16 halves (no carry can cross: every
-            // half-sum fits 16 bits).  The third addend is a kernel argument that is always
-            // 0: a three-input add can only be an IADD3, which keeps these adds off the
-            // multiplier pipe that the dp2a/dp4a instructions saturate.
-            uint32_t sum[8][m > 1 ? m - 1 : 1];
-#pragma unroll
-            for (int j = 1; j < m; ++j)
-#pragma unroll
-                for (int p = 0; p < 8; ++p) sum[p][j - 1] = n[kBase + p + j] + sw[kBase + p + NWX - 1 - j] + a.zero;
-#pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                const uint32_t ctr = n[kBase + p + m];
-                const uint32_t ends = prmt(n[kBase + p], n[kBase + p + NWX - 1], 0x3254);
-                // low byte plane first; the high plane continues from (low >> 8):
-                // floor((lo + 256 hi) / 2^20) == floor((floor(lo / 256) + hi) / 2^12)
-                int acc = a.accInit;
-#pragma unroll
-                for (int j = 1; j < m; ++j) acc = dp2a_lo_uu(sum[p][j - 1], a.cwXs[j - 1], acc);
-                acc = dp2a_lo_uu(ctr, a.cwXs[m - 1], acc);
-                acc = dp2a_lo_uu(ends, a.cwXs[m], acc);
-                acc >>= 8;
-#pragma unroll
-                for (int j = 1; j < m; ++j) acc = dp2a_hi_us(sum[p][j - 1], a.cwXs[j - 1], acc);
-                acc = dp2a_hi_us(ctr, a.cwXs[m - 1], acc);
-                if (ENDHI) acc = dp2a_hi_us(ends, a.cwXs[m], acc);  // skipped when both end taps fit the low byte plane
-                v[p] = acc >> 12;
-            }
-        } else {
-#pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                int acc = a.accInit;
-#pragma unroll
-                for (int j = 0; j < NWX; ++j) acc = dp2a_lo_uu(n[kBase + p + j], a.cwX[j], acc);
-                acc >>= 8;
-#pragma unroll
-                for (int j = 0; j < NWX; ++j) acc = dp2a_hi_us(n[kBase + p + j], a.cwX[j], acc);
-                v[p] = acc >> 12;
-            }
-        }
-        uint2 o;
-        o.x = packSatU8(v[1], v[0], packSatU8(v[3], v[2], 0u));
-        o.y = packSatU8(v[5], v[4], packSatU8(v[7], v[6], 0u));
-        if (vecStore) {
-            if (vec8) {
-                *reinterpret_cast<uint2 *>(out) = o;
-            } else {
-                *reinterpret_cast<uint32_t *>(out) = o.x;
-                *reinterpret_cast<uint32_t *>(out + 4) = o.y;
-            }
-        } else if (halfLo || halfHi) {
-            if (halfLo) *reinterpret_cast<uint32_t *>(out) = o.x;
-            if (halfHi) *reinterpret_cast<uint32_t *>(out + 4) = o.y;
-        } else {
-            halfStoreBytes(out, o, max(0, -d0), min(8, a.DW - d0));
-        }
-
-        }
-    };
+    auto doGroup = [&](const uint32_t *wr, uint8_t *out, int l) { halfGroup<NWX, SYM, ENDHI>(a, wr, out, tx0 + 8 * l, l); };
 
     if (groups == 15) {
         // full tile: a half-warp per row (15 of 16 lanes busy), two rows per warp and iteration
@@ -538,10 +548,12 @@ __device__ __forceinline__ void halfHorizontal(const HalfArgs &a, const uint32_t
     if (left || right) {
         __syncthreads();  // the main stores of these pixels come first (block-scope ordering)
         uint8_t *dstTile = dst + (long long)ty0 * a.dstPitch + tx0;
-        if (left) halfBorderColumns<NWX>(a, W, dstTile, a.borderX + 9 * max(tx0, 0), tx0, max(tx0, 0), min(a.mbX, txEnd), th);
+        if (left)
+            halfBorderColumns<NWX>(a, W, dstTile, a.borderX + 9 * max(tx0, 0), tx0, max(tx0, 0), min(a.mbX, txEnd), th, threadIdx.x,
+                                   blockDim.x);
         if (right) {
             const int c0 = max(a.meX, max(tx0, a.mbX));
-            halfBorderColumns<NWX>(a, W, dstTile, a.borderX + 9 * (a.mbX + c0 - a.meX), tx0, c0, txEnd, th);
+            halfBorderColumns<NWX>(a, W, dstTile, a.borderX + 9 * (a.mbX + c0 - a.meX), tx0, c0, txEnd, th, threadIdx.x, blockDim.x);
         }
     }
 }
@@ -652,6 +664,386 @@ cudaError_t launchHalfT(const HalfArgs &a, const CUtensorMap *tmap, int boxRows,
     } else {
         resizeHalfKernel<NG, NWX, SYM, ENDHI><<<grid, threads, 0, stream>>>(a);
     }
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+// Horizontal pass of eight adjacent destination pixels for the streaming variant: the pair words
+// hold columns (2m-1, 2m), so pixel p reads exactly the NXH words n[kBo + p .. kBo + p + NXH - 1]
+// and a symmetric table folds them into NXH / 2 pre-added words.
+template <int NXH, bool SYM, bool SKIP0>
+__device__ __forceinline__ uint2 halfGroupPixelsOdd(const HalfArgs &a, const uint32_t (&n)[16])
+{
+    constexpr int kBo = 5 - NXH / 2;
+    int v[8];
+    if (SYM) {
+        constexpr int m = NXH / 2;
+        uint32_t sw[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) sw[i] = (i >= kBo + m && i <= kBo + NXH - 1 + 7) ? prmt(n[i], n[i], 0x1032) : 0u;
+        uint32_t sum[8][m];
+#pragma unroll
+        for (int j = 0; j < m; ++j)
+#pragma unroll
+            for (int p = 0; p < 8; ++p) sum[p][j] = n[kBo + p + j] + sw[kBo + p + NXH - 1 - j] + a.zero;  // see halfGroupPixels
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            int acc = a.accInit;
+#pragma unroll
+            for (int j = 0; j < m; ++j) acc = dp2a_lo_uu(sum[p][j], a.cwXo[j], acc);
+            acc >>= 8;
+#pragma unroll
+            for (int j = 0; j < m; ++j)
+                if (!(SKIP0 && j == 0)) acc = dp2a_hi_us(sum[p][j], a.cwXo[j], acc);
+            v[p] = acc >> 12;
+        }
+    } else {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            int acc = a.accInit;
+#pragma unroll
+            for (int j = 0; j < NXH; ++j) acc = dp2a_lo_uu(n[kBo + p + j], a.cwXo[j], acc);
+            acc >>= 8;
+#pragma unroll
+            for (int j = 0; j < NXH; ++j) acc = dp2a_hi_us(n[kBo + p + j], a.cwXo[j], acc);
+            v[p] = acc >> 12;
+        }
+    }
+    uint2 o;
+    o.x = packSatU8(v[1], v[0], packSatU8(v[3], v[2], 0u));
+    o.y = packSatU8(v[5], v[4], packSatU8(v[7], v[6], 0u));
+    return o;
+}
+
+// ---- variant 3: warp-autonomous streaming ----
+// A warp owns one 120-pixel column strip of one frame and walks down a band of destination row
+// pairs on its own: no CTA-wide barrier, no per-tile prologue, and the register ring of
+// transposed source groups lives for the whole band instead of being refilled per tile.
+//   source      a lane owns 8 adjacent source columns.  Its 8 bytes of each source row travel
+//               global -> shared with cp.async into a private FIFO (kStreamRing groups of four
+//               rows deep), so the loads of the next three row pairs are always in flight and
+//               cost no registers; nobody else reads a lane's FIFO, so no barrier is needed.
+//   vertical    2 x (4x4 byte transposes) per group, 8 x NG dp4a per destination row, one
+//               16-byte store per row into the warp's private double-buffered W rows;
+//   horizontal  after one __syncwarp: lane = (row of the pair, 8-pixel group), 30 of 32 lanes
+//               busy, same pre-added dp2a planes as the tiled variants (halfGroup).
+//   borders     border rows: masked coefficient words + truncating division, in the turns that
+//               touch them.  Border columns: the few W words they need are parked in a side
+//               buffer and recomputed for 32 rows at a time by the whole warp.
+// Needs 8-byte aligned source rows and a source width that is a multiple of 8.
+template <bool B>
+struct BoolTag {
+    static constexpr bool value = B;
+};
+
+#ifndef IQO_STREAM_MINB
+#define IQO_STREAM_MINB 4
+#endif
+constexpr int kStreamRing = 4;        // source row groups in flight per lane (power of two)
+constexpr int kStreamSideRows = 32;   // destination rows parked before the border columns are flushed
+constexpr int kStreamSideWords = 32;  // per parked row: W chunks 0..3 (left) and rc0..rc0+3 (right)
+
+// Border columns [c0, c1) of `nrows` parked rows; `wordOff` maps (column + pair word) to a side word.
+template <int NXH>
+__device__ __noinline__ void streamBorderColumns(const HalfArgs &a, const uint32_t *side, uint8_t *dstRow0, const int32_t *bx,
+                                                 int wordOff, int c0, int c1, int nrows, int lane)
+{
+    const int nb = c1 - c0;
+    for (int item = lane; item < nb * nrows; item += 32) {
+        const int r = item / nb;
+        const int j = item - r * nb;
+        const int d = c0 + j;
+        const uint32_t *wr = side + r * kStreamSideWords + d + wordOff;
+        const int32_t *e = bx + j * 8;
+        int lo = __ldg(e + 7), hi = 0;
+#pragma unroll
+        for (int i = 0; i < NXH; ++i) {
+            const uint32_t word = wr[i];
+            const uint32_t cw = (uint32_t)__ldg(e + i);
+            lo = dp2a_lo_uu(word, cw, lo);
+            hi = dp2a_hi_us(word, cw, hi);
+        }
+        const int v = (int)(short)((lo + (hi << 8)) / __ldg(e + 6));
+        dstRow0[(long long)r * a.dstPitch + d] = (uint8_t)min(max(v, 0), 255);
+    }
+}
+
+// shared-memory accesses by 32-bit shared address (keeps the address arithmetic to one add per step)
+template <int OFF>
+__device__ __forceinline__ uint4 ldsV4(uint32_t addr)
+{
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+%5];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+
+template <int OFF>
+__device__ __forceinline__ uint2 ldsV2(uint32_t addr)
+{
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+
+template <int OFF>
+__device__ __forceinline__ void stsV4(uint32_t addr, uint4 v)
+{
+    asm volatile("st.shared.v4.u32 [%0+%1], {%2, %3, %4, %5};" ::"r"(addr), "n"(OFF), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+constexpr int kStreamRowBytes = 4 * kHalfRowWords + 16;  // W row stride: the 16-byte skew keeps the two rows of a pair on different banks
+constexpr int kStreamWBytes = 4 * kStreamRowBytes;       // per warp: 2 buffers x 2 rows
+
+template <int NG, int NXH, bool SYM, bool SKIP0, int Z>
+__global__ void __launch_bounds__(128, IQO_STREAM_MINB) resizeHalfStreamKernel(const __grid_constant__ HalfArgs a)
+{
+    __shared__ __align__(16) uint8_t Wsh[4 * kStreamWBytes];                           // [warp][buffer][row][528 bytes]
+    __shared__ __align__(16) uint2 ringSh[4 * kStreamRing * 4 * 32];                   // [warp][slot][row][lane]
+    __shared__ __align__(16) uint32_t sideSh[4 * kStreamSideRows * kStreamSideWords];  // [warp][row][32 words]
+    constexpr int kBase = 5 - NXH / 2;  // pair word of taps 0, 1 of pixel 0
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tx0 = (blockIdx.x * 4 + warp) * kHalfTileW;
+    if (tx0 >= a.DW) return;
+    const int pairs = (a.DH + 1) >> 1;
+    const int k0 = blockIdx.y * a.bandPairs;
+    const int k1 = min(k0 + a.bandPairs, pairs);
+    if (k0 >= k1) return;
+    const uint8_t *__restrict__ src = a.src + (long long)blockIdx.z * a.srcFrameStride;
+    uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
+    const int xs0 = 2 * tx0 - 8;  // first source column of lane 0 (multiple of 8); W element i is column xs0 + i - 1
+    const int txEnd = min(tx0 + kHalfTileW, a.DW);
+    uint32_t *side = sideSh + warp * (kStreamSideRows * kStreamSideWords);
+
+    // vertical role: columns outside the image only ever meet zero coefficients (read column 0)
+    const int col = xs0 + 8 * lane;
+    const uint8_t *base = src + ((col >= 0 && col < a.SW) ? col : 0);
+    const long long pitch = a.srcPitch;
+    const int SHm1 = a.SH - 1;
+    const int B = a.workBias;
+    const uint32_t wBase = smemAddr(Wsh + warp * kStreamWBytes);
+    uint32_t wst = wBase + 16 * lane;  // this lane's chunk of row 0 of the buffer being written
+    const uint32_t ringAddr = smemAddr(ringSh + (warp * kStreamRing * 4) * 32 + lane);
+    constexpr uint32_t kSlotBytes = 4 * 32 * 8, kRingMask = kStreamRing * kSlotBytes - 1;
+    // horizontal role: within every group of eight lanes four read row 0 and four row 1, so that
+    // the 16-byte loads of a quarter warp fall on eight different bank groups
+    const int hrow = (lane >> 2) & 1, hl = (lane & 3) | ((lane >> 3) << 2);
+    const int d0 = tx0 + 8 * hl;
+    // 0: nothing to store, 1: one 8-byte store, 2: one 4-byte store (group cut by the image edge), 3: bytes
+    int hmode = 0;
+    if (hl < 15 && d0 < txEnd) hmode = !a.dstVec ? 3 : d0 + 8 <= a.DW ? 1 : d0 + 4 == a.DW ? 2 : 3;
+    uint32_t wld = wBase + hrow * kStreamRowBytes + 32 * hl;
+    uint8_t *outp = dst + (long long)(2 * k0 + hrow) * a.dstPitch + d0;
+    const long long ostep = 2 * a.dstPitch;
+    // border columns: the lanes whose W chunks they read park them in the side buffer
+    const bool left = tx0 < a.mbX, right = txEnd > a.meX;
+    const int rcol0 = max(a.meX, max(tx0, a.mbX));    // first right border column of this strip
+    const int rc0 = (rcol0 - tx0 + kBase) >> 2;       // first W chunk the right border columns read
+    const bool parkL = left && lane < 4, parkR = right && (unsigned)(lane - rc0) < 4u;
+    const bool edgeStrip = left || right;
+    uint32_t sideAddr = smemAddr(side);
+    const uint32_t sideL = 16 * lane, sideR = 64 + 16 * (lane - rc0);
+    int sideRows = 0;
+
+    // steps [kIntB, kIntE) touch no border row and request only source rows inside the image
+    const int gAhead = a.qmin + NG + kStreamRing - 2;  // step k requests group k + gAhead
+    const int kIntB = max((a.mbY + 1) >> 1, -gAhead);
+    const int kIntE = min(a.meY >> 1, ((a.SH - a.delta) >> 2) - gAhead);
+
+    int g = k0 + a.qmin;  // next source group to request
+    const uint8_t *gp = base + (long long)(4 * g + a.delta) * pitch;
+    uint32_t wr = 0, rd = 0;
+    auto issue = [&](auto edgeTag) {  // request the four rows of group g, advance to the next group
+        const uint32_t sa = ringAddr + wr;
+        if (decltype(edgeTag)::value) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int row = min(max(4 * g + a.delta + j, 0), SHm1);
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 256 * j), "l"(base + (long long)row * pitch) : "memory");
+            }
+        } else {
+            const uint8_t *p1 = gp + pitch;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gp) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0+256], [%1], 8;" ::"r"(sa), "l"(p1) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0+512], [%1], 8;" ::"r"(sa), "l"(gp + 2 * pitch) : "memory");
+            asm volatile("cp.async.ca.shared.global [%0+768], [%1], 8;" ::"r"(sa), "l"(p1 + 2 * pitch) : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        wr = (wr + kSlotBytes) & kRingMask;
+        gp += 4 * pitch;
+        ++g;
+    };
+    // oldest requested group -> transposed columns: .x/.y/.z/.w = four vertical bytes of column 0..3 (A) and 4..7 (B)
+    auto consume = [&](uint4 &ca, uint4 &cb) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kStreamRing - 1) : "memory");
+        const uint32_t ra = ringAddr + rd;
+        const uint2 r0 = ldsV2<0>(ra), r1 = ldsV2<256>(ra), r2 = ldsV2<512>(ra), r3 = ldsV2<768>(ra);
+        rd = (rd + kSlotBytes) & kRingMask;
+        const uint32_t t0 = prmt(r0.x, r1.x, 0x5140), t1 = prmt(r0.x, r1.x, 0x7362);
+        const uint32_t t2 = prmt(r2.x, r3.x, 0x5140), t3 = prmt(r2.x, r3.x, 0x7362);
+        ca.x = prmt(t0, t2, 0x5410);
+        ca.y = prmt(t0, t2, 0x7632);
+        ca.z = prmt(t1, t3, 0x5410);
+        ca.w = prmt(t1, t3, 0x7632);
+        const uint32_t u0 = prmt(r0.y, r1.y, 0x5140), u1 = prmt(r0.y, r1.y, 0x7362);
+        const uint32_t u2 = prmt(r2.y, r3.y, 0x5140), u3 = prmt(r2.y, r3.y, 0x7362);
+        cb.x = prmt(u0, u2, 0x5410);
+        cb.y = prmt(u0, u2, 0x7632);
+        cb.z = prmt(u1, u3, 0x5410);
+        cb.w = prmt(u1, u3, 0x7632);
+    };
+    // The request of group n + kStreamRing - 1 goes out before group n is read: it lands in the
+    // slot read one step earlier.
+    uint4 winA[NG], winB[NG];
+#pragma unroll
+    for (int j = 0; j < kStreamRing - 1; ++j) issue(BoolTag<true>());
+#pragma unroll
+    for (int j = 0; j < NG - 1; ++j) {
+        issue(BoolTag<true>());
+        consume(winA[j], winB[j]);
+    }
+
+    // border columns of the parked rows (they end with row pair k)
+    auto flush = [&](const int k) {
+        __syncwarp();
+        const int y0 = 2 * k + 2 - sideRows;
+        const int nrows = min(sideRows, a.DH - y0);
+        uint8_t *drow = dst + (long long)y0 * a.dstPitch;
+        if (left) streamBorderColumns<NXH>(a, side, drow, a.borderX + 8 * tx0, kBase - tx0, tx0, min(a.mbX, txEnd), nrows, lane);
+        if (right)
+            streamBorderColumns<NXH>(a, side, drow, a.borderX + 8 * (a.mbX + rcol0 - a.meX), kBase - tx0 - 4 * rc0 + 16, rcol0, txEnd,
+                                     nrows, lane);
+        __syncwarp();
+        sideRows = 0;
+        sideAddr = smemAddr(side);
+    };
+
+    // vertical pass of destination row pair k; `s` (compile-time) is the position of the register ring
+    auto vertical = [&](auto edgeTag, auto ringPos, const int k) {
+        constexpr bool EDGE = decltype(edgeTag)::value;
+        constexpr int s = decltype(ringPos)::value;
+        issue(edgeTag);  // runs kStreamRing - 1 groups ahead (overshoots the band end, clamped to the image)
+        consume(winA[(s + NG - 1) % NG], winB[(s + NG - 1) % NG]);
+#pragma unroll
+        for (int par = 0; par < 2; ++par) {
+            uint32_t c0 = a.cwY[par][0], c1 = NG > 1 ? a.cwY[par][1] : 0u, c2 = NG > 2 ? a.cwY[par][2] : 0u;
+            int deno = 0;
+            uint32_t magic = 0;
+            if (EDGE) {
+                const int y = 2 * k + par;
+                if (y < a.DH && (y < a.mbY || y >= a.meY)) {
+                    const int row = __ldg(a.rowY + y);
+                    deno = __ldg(a.denoY + row);
+                    magic = __ldg(a.magicY + row);
+                    c0 = __ldg(a.borderY + row * 3);
+                    c1 = __ldg(a.borderY + row * 3 + 1);
+                    c2 = __ldg(a.borderY + row * 3 + 2);
+                }
+            }
+            const int init = (EDGE && deno) ? 0 : B;
+            int v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = init;
+#pragma unroll
+            for (int t = 0; t < NG; ++t) {
+                if (!EDGE && ((Z >> (par * 3 + t)) & 1)) continue;  // zero word of the main phase
+                const uint4 qa = winA[(s + t) % NG], qb = winB[(s + t) % NG];
+                const uint32_t c = t == 0 ? c0 : t == 1 ? c1 : c2;
+                v[0] = dp4a_us(qa.x, c, v[0]);
+                v[1] = dp4a_us(qa.y, c, v[1]);
+                v[2] = dp4a_us(qa.z, c, v[2]);
+                v[3] = dp4a_us(qa.w, c, v[3]);
+                v[4] = dp4a_us(qb.x, c, v[4]);
+                v[5] = dp4a_us(qb.y, c, v[5]);
+                v[6] = dp4a_us(qb.z, c, v[6]);
+                v[7] = dp4a_us(qb.w, c, v[7]);
+            }
+            if (EDGE && deno) {
+                // resizeYborder: see halfVerticalStrip
+                auto bdiv = [&](int x) -> int {
+                    const int n = (int)(short)x * 64;
+                    const uint32_t m = (uint32_t)abs(n);
+                    const int q = magic ? (int)__umulhi(m, magic) : (int)m;
+                    return (int)(short)(n < 0 ? -q : q) + B;
+                };
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = bdiv(v[i]);
+            }
+            // pair words (column 2m-1, column 2m): the lane's last column travels to its right neighbour
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, (uint32_t)v[7], 1);
+            uint4 o;
+            o.x = prmt(prev, (uint32_t)v[0], 0x5410);
+            o.y = prmt((uint32_t)v[1], (uint32_t)v[2], 0x5410);
+            o.z = prmt((uint32_t)v[3], (uint32_t)v[4], 0x5410);
+            o.w = prmt((uint32_t)v[5], (uint32_t)v[6], 0x5410);
+            if (par == 0) {
+                stsV4<0>(wst, o);
+                if (parkL) stsV4<0>(sideAddr + sideL, o);
+                if (parkR) stsV4<0>(sideAddr + sideR, o);
+            } else {
+                stsV4<kStreamRowBytes>(wst, o);
+                if (parkL) stsV4<4 * kStreamSideWords>(sideAddr + sideL, o);
+                if (parkR) stsV4<4 * kStreamSideWords>(sideAddr + sideR, o);
+            }
+        }
+    };
+
+    int s = 0;
+    int wflip = 2 * kStreamRowBytes;
+    for (int k = k0; k < k1; ++k) {
+        if (k >= kIntB && k < kIntE) {
+            if (NG == 1 || s == 0)
+                vertical(BoolTag<false>(), std::integral_constant<int, 0>(), k);
+            else if (NG == 2 || s == 1)
+                vertical(BoolTag<false>(), std::integral_constant<int, 1 % NG>(), k);
+            else
+                vertical(BoolTag<false>(), std::integral_constant<int, 2 % NG>(), k);
+        } else {
+            if (NG == 1 || s == 0)
+                vertical(BoolTag<true>(), std::integral_constant<int, 0>(), k);
+            else if (NG == 2 || s == 1)
+                vertical(BoolTag<true>(), std::integral_constant<int, 1 % NG>(), k);
+            else
+                vertical(BoolTag<true>(), std::integral_constant<int, 2 % NG>(), k);
+        }
+        s = (s + 1 == NG) ? 0 : s + 1;
+        __syncwarp();
+        // horizontal pass of the pair: lane = (row, 8-pixel group)
+        if (hmode != 0 && 2 * k + hrow < a.DH) {
+            uint32_t n[16];
+            const uint4 q0 = ldsV4<0>(wld), q1 = ldsV4<16>(wld), q2 = ldsV4<32>(wld), q3 = ldsV4<48>(wld);
+            n[0] = q0.x, n[1] = q0.y, n[2] = q0.z, n[3] = q0.w;
+            n[4] = q1.x, n[5] = q1.y, n[6] = q1.z, n[7] = q1.w;
+            n[8] = q2.x, n[9] = q2.y, n[10] = q2.z, n[11] = q2.w;
+            n[12] = q3.x, n[13] = q3.y, n[14] = q3.z, n[15] = q3.w;
+            const uint2 o = halfGroupPixelsOdd<NXH, SYM, SKIP0>(a, n);
+            if (hmode == 1)
+                *reinterpret_cast<uint2 *>(outp) = o;
+            else if (hmode == 2)
+                *reinterpret_cast<uint32_t *>(outp) = o.x;
+            else
+                halfStoreBytes(outp, o, 0, min(8, a.DW - d0));
+        }
+        outp += ostep;
+        wst += wflip;  // the other W buffer
+        wld += wflip;
+        wflip = -wflip;
+        if (edgeStrip) {
+            sideRows += 2;
+            sideAddr += 2 * 4 * kStreamSideWords;
+            if (sideRows == kStreamSideRows) flush(k);
+        }
+    }
+    if (sideRows) flush(k1 - 1);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+template <int NG, int NXH, bool SYM, bool SKIP0, int Z>
+cudaError_t launchHalfStreamT(const HalfArgs &a, cudaStream_t stream)
+{
+    const int strips = (a.DW + kHalfTileW - 1) / kHalfTileW;
+    const int pairs = (a.DH + 1) / 2;
+    dim3 grid((strips + 3) / 4, (pairs + a.bandPairs - 1) / a.bandPairs, a.nFrames);
+    resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z><<<grid, 128, 0, stream>>>(a);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -1215,6 +1607,31 @@ cudaError_t launchHalf(const HalfArgs &a, const CUtensorMap *tmap, int boxRows, 
     IQO_HALF_CASE(1, 5)
     IQO_HALF_CASE(1, 7)
 #undef IQO_HALF_CASE
+    return cudaErrorInvalidValue;
+}
+
+bool halfStreamHasKernel(int NG, int NXH)
+{
+    return (NG == 2 || NG == 3) && (NXH == 2 || NXH == 4 || NXH == 6);
+}
+
+cudaError_t launchHalfStream(const HalfArgs &a, cudaStream_t stream)
+{
+#define IQO_STREAM_CASE(G, NH, ZM)                                                              \
+    if (a.NG == G && a.NXH == NH && a.zmask == ZM)                                              \
+        return !a.symmetric ? launchHalfStreamT<G, NH, false, false, ZM>(a, stream)             \
+               : a.skipHi0  ? launchHalfStreamT<G, NH, true, true, ZM>(a, stream)               \
+                            : launchHalfStreamT<G, NH, true, false, ZM>(a, stream);
+    IQO_STREAM_CASE(3, 6, 0)
+    IQO_STREAM_CASE(3, 4, 0)
+    IQO_STREAM_CASE(3, 2, 0)
+    IQO_STREAM_CASE(3, 6, 4)
+    IQO_STREAM_CASE(3, 4, 4)
+    IQO_STREAM_CASE(3, 2, 4)
+    IQO_STREAM_CASE(2, 6, 0)
+    IQO_STREAM_CASE(2, 4, 0)
+    IQO_STREAM_CASE(2, 2, 0)
+#undef IQO_STREAM_CASE
     return cudaErrorInvalidValue;
 }
 

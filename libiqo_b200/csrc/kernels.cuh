@@ -50,6 +50,12 @@ struct HalfArgs {
     int tileRows;             // destination rows per tile (even, <= 64)
     int tileShift;            // tiles start at 120*i - tileShift destination columns (0, or 4 for TMA)
     int dstVec;               // destination rows may be written with 8-byte stores
+    // streaming variant (plan.hpp HalfPlan, s* fields): qmin / NG / cwY / borderY / borderX hold its tables
+    int bandPairs;            // destination row pairs per warp
+    int delta;                // source-row groups start at rows 4g + delta
+    int zmask;                // zero main-phase coefficient words the kernel skips
+    int NXH, skipHi0;
+    uint32_t cwXo[6];
     // vertical
     int qmin, NG;
     uint32_t cwY[2][3];
@@ -75,6 +81,10 @@ struct HalfArgs {
 // over the source frames with box 256 x boxRows x 1 (at most 65535 frames per launch either way).
 cudaError_t launchHalf(const HalfArgs &a, const CUtensorMap *tmap, int boxRows, cudaStream_t stream);
 int halfSourceRowsMax();
+// Streaming variant: a warp per (120-pixel column strip, band of a.bandPairs row pairs, frame).
+// Needs 8-byte aligned source rows and SW % 8 == 0; at most 65535 frames and bands per launch.
+cudaError_t launchHalfStream(const HalfArgs &a, cudaStream_t stream);
+bool halfStreamHasKernel(int NG, int NXH);
 
 // Arguments of the general packed kernel (see plan.hpp PackedPlan).
 struct PackedArgs {

@@ -2,6 +2,8 @@
 // rounding steps below decide the integer coefficients bit-for-bit.
 #include "plan.hpp"
 
+#include <string.h>
+
 #include <math.h>
 #include <stdio.h>
 
@@ -374,6 +376,7 @@ uint32_t pairWord(int cLowHalf, int cHighHalf)
 void buildHalfPlan(const Plan &p, HalfPlan &h)
 {
     h.eligible = false;
+    h.sEligible = false;
     h.why.clear();
     const AxisPlan &X = p.x, &Y = p.y;
     if (p.kind != kLanczos) { h.why = "not Lanczos"; return; }
@@ -487,6 +490,79 @@ void buildHalfPlan(const Plan &p, HalfPlan &h)
         h.borderX.push_back(int32_t((1ll << (p.shift - 1)) - (long long)h.workBias * sum));
     }
     h.eligible = true;
+
+    // ---- streaming variant ----
+    h.sEligible = false;
+    {
+        // group offset: fewest non-zero main-phase words among the patterns the kernel is built for
+        // (no zero word, or only the last word of parity 0 zero)
+        int best = 1 << 30;
+        for (int delta = 0; delta < 4; ++delta) {
+            int lo = 1 << 30, hi = -(1 << 30);
+            for (int par = 0; par < 2; ++par) {
+                lo = std::min(lo, floorDivI(2 * par + cy0 - delta, 4));
+                hi = std::max(hi, floorDivI(2 * par + cy0 + NYt - 1 - delta, 4));
+            }
+            const int ng = hi - lo + 1;
+            if (ng < 2 || ng > 3) continue;  // group counts the streaming kernel is built for
+            uint32_t w[2][3] = {{0, 0, 0}, {0, 0, 0}};
+            for (int par = 0; par < 2; ++par)
+                for (int i = 0; i < NY; ++i) {
+                    const int c = cy[i];
+                    if (c == 0) continue;
+                    const int pos = 2 * par + (1 - NY / 2 + i) - delta - 4 * lo;
+                    w[par][pos >> 2] |= (uint32_t(c) & 0xffu) << (8 * (pos & 3));
+                }
+            int z = 0, words = 0;
+            for (int par = 0; par < 2; ++par)
+                for (int g = 0; g < ng; ++g) {
+                    if (w[par][g] == 0) z |= 1 << (par * 3 + g);
+                    else ++words;
+                }
+            if (!(z == 0 || (z == 4 && ng == 3))) {  // pattern without a kernel: compute the zero words too
+                z = 0;
+                words = 2 * ng;
+            }
+            if (words < best) {
+                best = words;
+                h.sDelta = delta;
+                h.sQmin = lo;
+                h.sNG = ng;
+                h.sZ = z;
+                memcpy(h.sCwY, w, sizeof w);
+            }
+        }
+        if (best < (1 << 30) && h.sNG >= 2) {
+            h.sBorderY.assign(size_t(Y.numRows) * 3, 0);
+            bool ok = true;
+            for (int r = 1; r < Y.numRows && ok; ++r) {
+                if (rowOwner[size_t(r)] < 0) continue;
+                const int par = rowOwner[size_t(r)] & 1;
+                for (int i = 0; i < NY; ++i) {
+                    const int c = Y.coef[size_t(r) * NY + i];
+                    if (c == 0) continue;
+                    const int pos = 2 * par + (1 - NY / 2 + i) - h.sDelta - 4 * h.sQmin;
+                    if (pos < 0 || pos >= 4 * h.sNG) { ok = false; break; }
+                    h.sBorderY[size_t(r) * 3 + size_t(pos >> 2)] |= (uint32_t(c) & 0xffu) << (8 * (pos & 3));
+                }
+            }
+            h.NXH = NX / 2;
+            for (int i = 0; i < 6; ++i) h.cwXo[i] = 0;
+            for (int i = 0; i < h.NXH; ++i) h.cwXo[i] = pairWord(cx[2 * i], cx[2 * i + 1]);
+            h.skipHi0 = h.symmetric && (h.cwXo[0] >> 16) == 0;
+            h.borderXo.clear();
+            for (int64_t d = 0; d < X.D; ++d) {
+                if (d >= X.mainBegin && d < X.mainEnd) continue;
+                const int32_t *c = &X.coef[size_t(X.row[d]) * NX];
+                long long sum = 0;
+                for (int i = 0; i < 6; ++i) h.borderXo.push_back(i < h.NXH ? int32_t(pairWord(c[2 * i], c[2 * i + 1])) : 0);
+                for (int i = 0; i < NX; ++i) sum += c[i];
+                h.borderXo.push_back(int32_t(X.deno[size_t(X.row[d])] * 64));
+                h.borderXo.push_back(int32_t((1ll << (p.shift - 1)) - (long long)h.workBias * sum));
+            }
+            h.sEligible = ok && X.D >= 32;  // narrower images: left and right border columns would share W chunks
+        }
+    }
 }
 
 }  // namespace iqo_b200

@@ -94,6 +94,21 @@ struct HalfPlan {
     // border columns in order (left ones, then right ones), 9 words each:
     // [0..6] pair words of the masked taps (general form), [7] denominator * 64, [8] accumulator init
     std::vector<int32_t> borderX;
+
+    // ---- streaming variant (kernels.cu: resizeHalfStreamKernel) ----
+    // vertical: the 4-row groups start at source rows 4g + sDelta; the offset is chosen so that as
+    // few coefficient words as possible are non-zero (Lanczos2: 5 instead of 6)
+    bool sEligible;
+    int sDelta, sQmin, sNG;
+    uint32_t sCwY[2][3];
+    int sZ;                   // bit (parity * 3 + group): that main-phase word is zero and skipped by the kernel
+    std::vector<uint32_t> sBorderY;  // [numRowsY][3]
+    // horizontal: 16-bit pairs (columns 2m-1, 2m), so that the NX taps of a pixel fill exactly NX/2
+    // pair words: word i holds taps 2i (low half) and 2i+1 (high half)
+    int NXH;                  // NX / 2 (2, 4 or 6)
+    uint32_t cwXo[6];         // bytes (lo(c_2i), lo(c_2i+1), hi(c_2i), hi(c_2i+1)); symmetric tables use the first NXH/2
+    bool skipHi0;             // symmetric form: both taps of word 0 fit the low byte plane
+    std::vector<int32_t> borderXo;   // [border columns][8]: 6 pair words, denominator * 64, accumulator init
 };
 
 void buildHalfPlan(const Plan &plan, HalfPlan &h);

@@ -220,10 +220,24 @@ HALF_CASES = [
     (3, 2, 960, 540, 0, 0, "generic"),        # negative border denominator: specialised kernel declines
     (2, 1, 64, 32, 0, 0, "half_sym"),         # image smaller than a tile
     (3, 1, 28, 26, 0, 0, "half_sym"),
+    (3, 1, 1208, 98, 0, 0, "half_sym"),       # eleven strips (three CTAs, the last one partly empty), odd dstH
+    (2, 1, 248, 1000, 8, 4, "half_sym"),      # tall: several row bands per strip
+    (4, 2, 968, 520, 0, 0, "half"),
 ]
 
 
-@pytest.mark.parametrize("path", [iqo.PATH_AUTO, iqo.PATH_NO_TMA])
+def half_variant(kname, path, sw):
+    """Name of the 2:1 Lanczos kernel a host image (staged with a 16-byte aligned pitch) runs on."""
+    if kname not in ("half", "half_sym"):
+        return kname
+    if path == iqo.PATH_AUTO and sw % 8 == 0:
+        return kname + "_stream"     # a warp per column strip: needs whole 8-column words
+    if path in (iqo.PATH_AUTO, iqo.PATH_NO_STREAM):
+        return kname + "_tma"        # tiled kernel, source window staged by TMA
+    return kname                     # tiled kernel, plain global loads
+
+
+@pytest.mark.parametrize("path", [iqo.PATH_AUTO, iqo.PATH_NO_STREAM, iqo.PATH_NO_TMA])
 @pytest.mark.parametrize("case", HALF_CASES)
 def test_half_kernel(case, path):
     deg, px, sw, sh, spad, dpad, kname = case
@@ -232,8 +246,7 @@ def test_half_kernel(case, path):
     rc, want = oracle_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
     assert rc == 0
     got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad, path=path)
-    # host images are staged on the device with a 16-byte aligned pitch, so AUTO feeds the tile by TMA
-    assert kernel == (kname + "_tma" if path == iqo.PATH_AUTO and kname in ("half", "half_sym") else kname)
+    assert kernel == half_variant(kname, path, sw)
     assert iqo.plan_kernel(LANCZOS, deg, sw, sh, dw, dh, px)[0] == kname
     bad = np.argwhere(got != want)
     assert bad.size == 0, (len(bad), bad[:8].tolist())
@@ -266,20 +279,24 @@ def test_half_kernel_extreme_values():
 
 
 def test_half_kernel_device_pitches():
-    """Device-resident frames: a 16-byte aligned pitch takes the TMA variant, a pitch that is only
-    4-byte aligned takes the global-load variant, an odd pitch falls back to the generic kernel."""
+    """Device-resident frames: an 8-byte aligned pitch takes the streaming variant, one that is only
+    4-byte aligned the tiled global-load variant, an odd pitch falls back to the generic kernel;
+    without the streaming variant a 16-byte aligned pitch takes the TMA variant."""
     torch = pytest.importorskip("torch")
     sw, sh, dw, dh, n = 488, 250, 244, 125, 3
-    for pitch, expect in ((496, "half_sym_tma"), (492, "half_sym"), (489, "generic")):
+    for pitch, path, expect in ((496, iqo.PATH_AUTO, "half_sym_stream"), (496, iqo.PATH_NO_STREAM, "half_sym_tma"),
+                                (504, iqo.PATH_NO_STREAM, "half_sym"), (492, iqo.PATH_AUTO, "half_sym"),
+                                (489, iqo.PATH_AUTO, "generic")):
         host = np.stack([lcg_image(sh, pitch, seed=40 + f) for f in range(n)])
         want = np.stack([oracle_resize(LANCZOS, host[f], dw, dh, 3, sw=sw)[1] for f in range(n)])
         dsrc = torch.from_numpy(host).cuda()
         ddst = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
         with iqo.LanczosResizer(3, sw, sh, dw, dh) as r:
+            r.set_path(path)
             r.resize_batch(n, pitch, pitch * sh, dsrc, dw, dw * dh, ddst, torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
-            assert r.last_kernel() == expect
-        assert np.array_equal(ddst.cpu().numpy(), want), pitch
+            assert r.last_kernel() == expect, (pitch, path)
+        assert np.array_equal(ddst.cpu().numpy(), want), (pitch, path)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -1046,6 +1046,10 @@ struct iqo_cuda_yuv420 {
     size_t srcSizeY, srcSizeU, srcSize, dstSizeY, dstSizeU, dstSize;
     uint8_t *dIn[2], *dOut[2];
     size_t slotFrames;
+    // the chroma planes run on side streams forked from / joined to the caller's stream, so that
+    // their CTAs fill the SMs the tail of the luma kernel leaves idle
+    cudaStream_t side[2];
+    cudaEvent_t fork, join[2];
 };
 
 namespace {
@@ -1053,10 +1057,16 @@ namespace {
 int yuvLaunch(iqo_cuda_yuv420 *h, size_t n, const uint8_t *src, uint8_t *dst, cudaStream_t s)
 {
     iqo_cuda_resizer *y = h->luma, *c = h->chroma;
+    CUDA_TRY(cudaEventRecord(h->fork, s));
     int rc = launch(y, n, 0, size_t(y->plan.y.D), 0, size_t(y->plan.y.S), h->srcStX, h->srcSize, src, h->dstStX, h->dstSize, dst, s);
-    for (int p = 0; p < 2 && rc == IQO_CUDA_OK; ++p)
+    for (int p = 0; p < 2 && rc == IQO_CUDA_OK; ++p) {
+        CUDA_TRY(cudaStreamWaitEvent(h->side[p], h->fork, 0));
         rc = launch(c, n, 0, size_t(c->plan.y.D), 0, size_t(c->plan.y.S), h->srcStX / 2, h->srcSize,
-                    src + h->srcSizeY + p * h->srcSizeU, h->dstStX / 2, h->dstSize, dst + h->dstSizeY + p * h->dstSizeU, s);
+                    src + h->srcSizeY + p * h->srcSizeU, h->dstStX / 2, h->dstSize, dst + h->dstSizeY + p * h->dstSizeU, h->side[p]);
+        // join even after a failed launch: the caller's stream must not run ahead of the side stream
+        CUDA_TRY(cudaEventRecord(h->join[p], h->side[p]));
+        CUDA_TRY(cudaStreamWaitEvent(s, h->join[p], 0));
+    }
     return rc;
 }
 
@@ -1084,6 +1094,15 @@ int iqo_cuda_yuv420_create(iqo_cuda_yuv420 **out, int kind, unsigned degree, siz
     int rc = iqo_cuda_create(&h->luma, kind, degree, srcW, srcH, dstW, dstH, 1);
     if (rc == IQO_CUDA_OK)
         rc = iqo_cuda_create(&h->chroma, kind, degree, h->srcStX / 2, h->srcStY / 2, h->dstStX / 2, h->dstStY / 2, 2);
+    if (rc == IQO_CUDA_OK) {
+        DeviceGuard guard(h->luma->device);
+        cudaError_t e = cudaEventCreateWithFlags(&h->fork, cudaEventDisableTiming);
+        for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+            e = cudaStreamCreateWithFlags(&h->side[i], cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->join[i], cudaEventDisableTiming);
+        }
+        if (e != cudaSuccess) rc = fail(IQO_CUDA_E_CUDA, "cannot create the chroma streams: %s", cudaGetErrorString(e));
+    }
     if (rc != IQO_CUDA_OK) {
         std::string keep = t_lastError;
         iqo_cuda_yuv420_destroy(h);
@@ -1102,9 +1121,15 @@ void iqo_cuda_yuv420_destroy(iqo_cuda_yuv420 *h)
         cudaStreamSynchronize(h->luma->stream[0]);
         cudaStreamSynchronize(h->luma->stream[1]);
         for (int i = 0; i < 2; ++i) {
+            if (h->side[i]) {
+                cudaStreamSynchronize(h->side[i]);
+                cudaStreamDestroy(h->side[i]);
+            }
+            if (h->join[i]) cudaEventDestroy(h->join[i]);
             cudaFree(h->dIn[i]);
             cudaFree(h->dOut[i]);
         }
+        if (h->fork) cudaEventDestroy(h->fork);
         cudaGetLastError();
     }
     iqo_cuda_destroy(h->luma);

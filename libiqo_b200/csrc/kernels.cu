@@ -739,6 +739,13 @@ struct BoolTag {
 #ifndef IQO_STREAM_MINB
 #define IQO_STREAM_MINB 4
 #endif
+#ifndef IQO_STREAM_MAXREG
+#define IQO_STREAM_MAXREG 112
+#endif
+#ifndef IQO_STREAM_WARPS
+#define IQO_STREAM_WARPS 4
+#endif
+constexpr int kStreamWarps = IQO_STREAM_WARPS;  // strips (warps) per CTA
 constexpr int kStreamRing = 4;        // source row groups in flight per lane (power of two)
 constexpr int kStreamSideRows = 32;   // destination rows parked before the border columns are flushed
 constexpr int kStreamSideWords = 32;  // per parked row: W chunks 0..3 (left) and rc0..rc0+3 (right)
@@ -795,14 +802,14 @@ constexpr int kStreamRowBytes = 4 * kHalfRowWords + 16;  // W row stride: the 16
 constexpr int kStreamWBytes = 4 * kStreamRowBytes;       // per warp: 2 buffers x 2 rows
 
 template <int NG, int NXH, bool SYM, bool SKIP0, int Z>
-__global__ void __launch_bounds__(128, IQO_STREAM_MINB) resizeHalfStreamKernel(const __grid_constant__ HalfArgs a)
+__global__ void __launch_bounds__(32 * kStreamWarps, IQO_STREAM_MINB) resizeHalfStreamKernel(const __grid_constant__ HalfArgs a)
 {
-    __shared__ __align__(16) uint8_t Wsh[4 * kStreamWBytes];                           // [warp][buffer][row][528 bytes]
-    __shared__ __align__(16) uint2 ringSh[4 * kStreamRing * 4 * 32];                   // [warp][slot][row][lane]
-    __shared__ __align__(16) uint32_t sideSh[4 * kStreamSideRows * kStreamSideWords];  // [warp][row][32 words]
+    __shared__ __align__(16) uint8_t Wsh[kStreamWarps * kStreamWBytes];                           // [warp][buffer][row][528 bytes]
+    __shared__ __align__(16) uint2 ringSh[kStreamWarps * kStreamRing * 4 * 32];                   // [warp][slot][row][lane]
+    __shared__ __align__(16) uint32_t sideSh[kStreamWarps * kStreamSideRows * kStreamSideWords];  // [warp][row][32 words]
     constexpr int kBase = 5 - NXH / 2;  // pair word of taps 0, 1 of pixel 0
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tx0 = (blockIdx.x * 4 + warp) * kHalfTileW;
+    const int tx0 = (blockIdx.x * kStreamWarps + warp) * kHalfTileW;
     if (tx0 >= a.DW) return;
     const int pairs = (a.DH + 1) >> 1;
     const int k0 = blockIdx.y * a.bandPairs;
@@ -838,10 +845,12 @@ __global__ void __launch_bounds__(128, IQO_STREAM_MINB) resizeHalfStreamKernel(c
     const bool left = tx0 < a.mbX, right = txEnd > a.meX;
     const int rcol0 = max(a.meX, max(tx0, a.mbX));    // first right border column of this strip
     const int rc0 = (rcol0 - tx0 + kBase) >> 2;       // first W chunk the right border columns read
+    // (destination rows are at least 32 pixels wide here, so no lane serves both sides)
     const bool parkL = left && lane < 4, parkR = right && (unsigned)(lane - rc0) < 4u;
+    const bool park = parkL || parkR;
     const bool edgeStrip = left || right;
-    uint32_t sideAddr = smemAddr(side);
-    const uint32_t sideL = 16 * lane, sideR = 64 + 16 * (lane - rc0);
+    const uint32_t sideLane = smemAddr(side) + (parkL ? 16 * lane : 64 + 16 * (lane - rc0));
+    uint32_t sideAddr = sideLane;
     int sideRows = 0;
 
     // steps [kIntB, kIntE) touch no border row and request only source rows inside the image
@@ -851,7 +860,7 @@ __global__ void __launch_bounds__(128, IQO_STREAM_MINB) resizeHalfStreamKernel(c
 
     int g = k0 + a.qmin;  // next source group to request
     const uint8_t *gp = base + (long long)(4 * g + a.delta) * pitch;
-    uint32_t wr = 0, rd = 0;
+    uint32_t wr = 0, rd = 0;  // byte offsets of the FIFO slot to fill / to read
     auto issue = [&](auto edgeTag) {  // request the four rows of group g, advance to the next group
         const uint32_t sa = ringAddr + wr;
         if (decltype(edgeTag)::value) {
@@ -868,7 +877,6 @@ __global__ void __launch_bounds__(128, IQO_STREAM_MINB) resizeHalfStreamKernel(c
             asm volatile("cp.async.ca.shared.global [%0+768], [%1], 8;" ::"r"(sa), "l"(p1 + 2 * pitch) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        wr = (wr + kSlotBytes) & kRingMask;
         gp += 4 * pitch;
         ++g;
     };
@@ -877,6 +885,7 @@ __global__ void __launch_bounds__(128, IQO_STREAM_MINB) resizeHalfStreamKernel(c
         asm volatile("cp.async.wait_group %0;" ::"n"(kStreamRing - 1) : "memory");
         const uint32_t ra = ringAddr + rd;
         const uint2 r0 = ldsV2<0>(ra), r1 = ldsV2<256>(ra), r2 = ldsV2<512>(ra), r3 = ldsV2<768>(ra);
+        wr = rd;  // the next request refills the slot just read
         rd = (rd + kSlotBytes) & kRingMask;
         const uint32_t t0 = prmt(r0.x, r1.x, 0x5140), t1 = prmt(r0.x, r1.x, 0x7362);
         const uint32_t t2 = prmt(r2.x, r3.x, 0x5140), t3 = prmt(r2.x, r3.x, 0x7362);
@@ -895,7 +904,10 @@ __global__ void __launch_bounds__(128, IQO_STREAM_MINB) resizeHalfStreamKernel(c
     // slot read one step earlier.
     uint4 winA[NG], winB[NG];
 #pragma unroll
-    for (int j = 0; j < kStreamRing - 1; ++j) issue(BoolTag<true>());
+    for (int j = 0; j < kStreamRing - 1; ++j) {
+        issue(BoolTag<true>());
+        wr += kSlotBytes;
+    }
 #pragma unroll
     for (int j = 0; j < NG - 1; ++j) {
         issue(BoolTag<true>());
@@ -914,7 +926,7 @@ __global__ void __launch_bounds__(128, IQO_STREAM_MINB) resizeHalfStreamKernel(c
                                      nrows, lane);
         __syncwarp();
         sideRows = 0;
-        sideAddr = smemAddr(side);
+        sideAddr = sideLane;
     };
 
     // vertical pass of destination row pair k; `s` (compile-time) is the position of the register ring
@@ -977,12 +989,10 @@ __global__ void __launch_bounds__(128, IQO_STREAM_MINB) resizeHalfStreamKernel(c
             o.w = prmt((uint32_t)v[5], (uint32_t)v[6], 0x5410);
             if (par == 0) {
                 stsV4<0>(wst, o);
-                if (parkL) stsV4<0>(sideAddr + sideL, o);
-                if (parkR) stsV4<0>(sideAddr + sideR, o);
+                if (park) stsV4<0>(sideAddr, o);
             } else {
                 stsV4<kStreamRowBytes>(wst, o);
-                if (parkL) stsV4<4 * kStreamSideWords>(sideAddr + sideL, o);
-                if (parkR) stsV4<4 * kStreamSideWords>(sideAddr + sideR, o);
+                if (park) stsV4<4 * kStreamSideWords>(sideAddr, o);
             }
         }
     };
@@ -1042,8 +1052,8 @@ cudaError_t launchHalfStreamT(const HalfArgs &a, cudaStream_t stream)
 {
     const int strips = (a.DW + kHalfTileW - 1) / kHalfTileW;
     const int pairs = (a.DH + 1) / 2;
-    dim3 grid((strips + 3) / 4, (pairs + a.bandPairs - 1) / a.bandPairs, a.nFrames);
-    resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z><<<grid, 128, 0, stream>>>(a);
+    dim3 grid((strips + kStreamWarps - 1) / kStreamWarps, (pairs + a.bandPairs - 1) / a.bandPairs, a.nFrames);
+    resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z><<<grid, 32 * kStreamWarps, 0, stream>>>(a);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }

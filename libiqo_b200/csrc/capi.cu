@@ -359,7 +359,7 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
             // bands: enough warps to fill the device several times over, but long enough that the
             // ring refill and the re-read halo rows of a band stay small
             const long long strips = (h.DW + 119) / 120, pairs = (h.DH + 1) / 2;
-            int bandPairs = 96;
+            int bandPairs = 144;
             if (const char *e = getenv("IQO_CUDA_STREAM_BAND_PAIRS")) bandPairs = std::max(1, atoi(e));
             const long long wantWarps = 6ll * 148 * 20;
             while (bandPairs > 24 && strips * ((pairs + bandPairs - 1) / bandPairs) * (long long)nFrames < wantWarps) bandPairs /= 2;

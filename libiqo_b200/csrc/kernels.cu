@@ -720,7 +720,7 @@ __device__ __forceinline__ uint2 halfGroupPixelsOdd(const HalfArgs &a, const uin
 // pairs on its own: no CTA-wide barrier, no per-tile prologue, and the register ring of
 // transposed source groups lives for the whole band instead of being refilled per tile.
 //   source      a lane owns 8 adjacent source columns.  Its 8 bytes of each source row travel
-//               global -> shared with cp.async into a private FIFO (kStreamRing groups of four
+//               global -> shared with cp.async into a private FIFO (one turn = NG groups of four
 //               rows deep), so the loads of the next three row pairs are always in flight and
 //               cost no registers; nobody else reads a lane's FIFO, so no barrier is needed.
 //   vertical    2 x (4x4 byte transposes) per group, 8 x NG dp4a per destination row, one
@@ -746,8 +746,7 @@ struct BoolTag {
 #define IQO_STREAM_WARPS 4
 #endif
 constexpr int kStreamWarps = IQO_STREAM_WARPS;  // strips (warps) per CTA
-constexpr int kStreamRing = 4;        // source row groups in flight per lane (power of two)
-constexpr int kStreamSideRows = 32;   // destination rows parked before the border columns are flushed
+constexpr int kStreamSideRows = 16;   // destination rows parked before the border columns are flushed
 constexpr int kStreamSideWords = 32;  // per parked row: W chunks 0..3 (left) and rc0..rc0+3 (right)
 
 // Border columns [c0, c1) of `nrows` parked rows; `wordOff` maps (column + pair word) to a side word.
@@ -799,15 +798,26 @@ __device__ __forceinline__ void stsV4(uint32_t addr, uint4 v)
 }
 
 constexpr int kStreamRowBytes = 4 * kHalfRowWords + 16;  // W row stride: the 16-byte skew keeps the two rows of a pair on different banks
-constexpr int kStreamWBytes = 4 * kStreamRowBytes;       // per warp: 2 buffers x 2 rows
+constexpr int kStreamSlotBytes = 4 * 32 * 8;             // one source group of a warp: 4 rows x 256 bytes
+#ifndef IQO_STREAM_FIFO_TURNS
+#define IQO_STREAM_FIFO_TURNS 2
+#endif
+// shared bytes of one warp: W rows of one turn, the source FIFO, the parked border chunks
+__host__ __device__ constexpr int streamWarpBytes(int NG)
+{
+    return 2 * NG * kStreamRowBytes + IQO_STREAM_FIFO_TURNS * NG * kStreamSlotBytes + kStreamSideRows * kStreamSideWords * 4;
+}
 
+// The loop runs in *turns* of NG row pairs (one revolution of the register ring), so that ring
+// positions, FIFO slots and W rows are compile-time constants and the per-pair bookkeeping is
+// paid once per turn: NG vertical passes, one __syncwarp, then the horizontal pass of the 2 NG rows.
 template <int NG, int NXH, bool SYM, bool SKIP0, int Z>
 __global__ void __launch_bounds__(32 * kStreamWarps, IQO_STREAM_MINB) resizeHalfStreamKernel(const __grid_constant__ HalfArgs a)
 {
-    __shared__ __align__(16) uint8_t Wsh[kStreamWarps * kStreamWBytes];                           // [warp][buffer][row][528 bytes]
-    __shared__ __align__(16) uint2 ringSh[kStreamWarps * kStreamRing * 4 * 32];                   // [warp][slot][row][lane]
-    __shared__ __align__(16) uint32_t sideSh[kStreamWarps * kStreamSideRows * kStreamSideWords];  // [warp][row][32 words]
+    extern __shared__ __align__(16) uint8_t streamSmem[];
     constexpr int kBase = 5 - NXH / 2;  // pair word of taps 0, 1 of pixel 0
+    constexpr int kFifo = IQO_STREAM_FIFO_TURNS * NG;      // groups in a lane's FIFO
+    constexpr int kWBuf = 2 * NG * kStreamRowBytes;        // W rows of one turn
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx0 = (blockIdx.x * kStreamWarps + warp) * kHalfTileW;
     if (tx0 >= a.DW) return;
@@ -819,7 +829,10 @@ __global__ void __launch_bounds__(32 * kStreamWarps, IQO_STREAM_MINB) resizeHalf
     uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
     const int xs0 = 2 * tx0 - 8;  // first source column of lane 0 (multiple of 8); W element i is column xs0 + i - 1
     const int txEnd = min(tx0 + kHalfTileW, a.DW);
-    uint32_t *side = sideSh + warp * (kStreamSideRows * kStreamSideWords);
+    uint8_t *warpSmem = streamSmem + warp * streamWarpBytes(NG);
+    const uint32_t wBase = smemAddr(warpSmem);
+    const uint32_t fifoBase = wBase + kWBuf + 8 * lane;
+    uint32_t *side = reinterpret_cast<uint32_t *>(warpSmem + kWBuf + kFifo * kStreamSlotBytes);
 
     // vertical role: columns outside the image only ever meet zero coefficients (read column 0)
     const int col = xs0 + 8 * lane;
@@ -827,10 +840,7 @@ __global__ void __launch_bounds__(32 * kStreamWarps, IQO_STREAM_MINB) resizeHalf
     const long long pitch = a.srcPitch;
     const int SHm1 = a.SH - 1;
     const int B = a.workBias;
-    const uint32_t wBase = smemAddr(Wsh + warp * kStreamWBytes);
-    uint32_t wst = wBase + 16 * lane;  // this lane's chunk of row 0 of the buffer being written
-    const uint32_t ringAddr = smemAddr(ringSh + (warp * kStreamRing * 4) * 32 + lane);
-    constexpr uint32_t kSlotBytes = 4 * 32 * 8, kRingMask = kStreamRing * kSlotBytes - 1;
+    const uint32_t wst = wBase + 16 * lane;  // this lane's chunk of W row 0
     // horizontal role: within every group of eight lanes four read row 0 and four row 1, so that
     // the 16-byte loads of a quarter warp fall on eight different bank groups
     const int hrow = (lane >> 2) & 1, hl = (lane & 3) | ((lane >> 3) << 2);
@@ -838,14 +848,14 @@ __global__ void __launch_bounds__(32 * kStreamWarps, IQO_STREAM_MINB) resizeHalf
     // 0: nothing to store, 1: one 8-byte store, 2: one 4-byte store (group cut by the image edge), 3: bytes
     int hmode = 0;
     if (hl < 15 && d0 < txEnd) hmode = !a.dstVec ? 3 : d0 + 8 <= a.DW ? 1 : d0 + 4 == a.DW ? 2 : 3;
-    uint32_t wld = wBase + hrow * kStreamRowBytes + 32 * hl;
+    const uint32_t wld = wBase + hrow * kStreamRowBytes + 32 * hl;
     uint8_t *outp = dst + (long long)(2 * k0 + hrow) * a.dstPitch + d0;
     const long long ostep = 2 * a.dstPitch;
     // border columns: the lanes whose W chunks they read park them in the side buffer
+    // (destination rows are at least 32 pixels wide here, so no lane serves both sides)
     const bool left = tx0 < a.mbX, right = txEnd > a.meX;
     const int rcol0 = max(a.meX, max(tx0, a.mbX));    // first right border column of this strip
     const int rc0 = (rcol0 - tx0 + kBase) >> 2;       // first W chunk the right border columns read
-    // (destination rows are at least 32 pixels wide here, so no lane serves both sides)
     const bool parkL = left && lane < 4, parkR = right && (unsigned)(lane - rc0) < 4u;
     const bool park = parkL || parkR;
     const bool edgeStrip = left || right;
@@ -853,16 +863,17 @@ __global__ void __launch_bounds__(32 * kStreamWarps, IQO_STREAM_MINB) resizeHalf
     uint32_t sideAddr = sideLane;
     int sideRows = 0;
 
-    // steps [kIntB, kIntE) touch no border row and request only source rows inside the image
-    const int gAhead = a.qmin + NG + kStreamRing - 2;  // step k requests group k + gAhead
+    // turns starting at pairs [kIntB, kIntE] (whole turn inside) touch no border row and request only rows inside the image
+    const int gAhead = a.qmin + NG - 1 + kFifo - 1;  // the step of pair k requests group k + gAhead
     const int kIntB = max((a.mbY + 1) >> 1, -gAhead);
-    const int kIntE = min(a.meY >> 1, ((a.SH - a.delta) >> 2) - gAhead);
+    const int kIntE = min(min(a.meY >> 1, ((a.SH - a.delta) >> 2) - gAhead), k1);
 
     int g = k0 + a.qmin;  // next source group to request
     const uint8_t *gp = base + (long long)(4 * g + a.delta) * pitch;
-    uint32_t wr = 0, rd = 0;  // byte offsets of the FIFO slot to fill / to read
-    auto issue = [&](auto edgeTag) {  // request the four rows of group g, advance to the next group
-        const uint32_t sa = ringAddr + wr;
+    // FIFO slot of the n-th group of the band is n mod kFifo.  With a FIFO two turns deep the slots
+    // of a turn alternate between the halves fifoCur / fifoOth.
+    uint32_t fifoCur = fifoBase, fifoOth = fifoBase + (IQO_STREAM_FIFO_TURNS > 1 ? NG * kStreamSlotBytes : 0);
+    auto issue = [&](auto edgeTag, const uint32_t sa) {  // request the four rows of group g into slot `sa`
         if (decltype(edgeTag)::value) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -880,13 +891,10 @@ __global__ void __launch_bounds__(32 * kStreamWarps, IQO_STREAM_MINB) resizeHalf
         gp += 4 * pitch;
         ++g;
     };
-    // oldest requested group -> transposed columns: .x/.y/.z/.w = four vertical bytes of column 0..3 (A) and 4..7 (B)
-    auto consume = [&](uint4 &ca, uint4 &cb) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(kStreamRing - 1) : "memory");
-        const uint32_t ra = ringAddr + rd;
+    // oldest requested group (slot `ra`) -> transposed columns: .x/.y/.z/.w = four vertical bytes of column 0..3 (A) and 4..7 (B)
+    auto consume = [&](const uint32_t ra, uint4 &ca, uint4 &cb) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kFifo - 1) : "memory");
         const uint2 r0 = ldsV2<0>(ra), r1 = ldsV2<256>(ra), r2 = ldsV2<512>(ra), r3 = ldsV2<768>(ra);
-        wr = rd;  // the next request refills the slot just read
-        rd = (rd + kSlotBytes) & kRingMask;
         const uint32_t t0 = prmt(r0.x, r1.x, 0x5140), t1 = prmt(r0.x, r1.x, 0x7362);
         const uint32_t t2 = prmt(r2.x, r3.x, 0x5140), t3 = prmt(r2.x, r3.x, 0x7362);
         ca.x = prmt(t0, t2, 0x5410);
@@ -900,41 +908,46 @@ __global__ void __launch_bounds__(32 * kStreamWarps, IQO_STREAM_MINB) resizeHalf
         cb.z = prmt(u1, u3, 0x5410);
         cb.w = prmt(u1, u3, 0x7632);
     };
-    // The request of group n + kStreamRing - 1 goes out before group n is read: it lands in the
-    // slot read one step earlier.
+    // Group n of the band (n = 0 is group k0 + qmin) lives in slot n mod kFifo; the request of group
+    // n + kFifo - 1 goes out right before group n is read and lands in the slot read one step earlier.
+    // Before the first turn: groups 0 .. NG-2 are in the register ring, groups up to NG + kFifo - 3 requested.
     uint4 winA[NG], winB[NG];
 #pragma unroll
-    for (int j = 0; j < kStreamRing - 1; ++j) {
-        issue(BoolTag<true>());
-        wr += kSlotBytes;
-    }
+    for (int j = 0; j < kFifo - 1; ++j) issue(BoolTag<true>(), fifoBase + j * kStreamSlotBytes);
 #pragma unroll
     for (int j = 0; j < NG - 1; ++j) {
-        issue(BoolTag<true>());
-        consume(winA[j], winB[j]);
+        issue(BoolTag<true>(), fifoBase + ((j + kFifo - 1) % kFifo) * kStreamSlotBytes);
+        consume(fifoBase + j * kStreamSlotBytes, winA[j], winB[j]);
     }
 
-    // border columns of the parked rows (they end with row pair k)
-    auto flush = [&](const int k) {
+    // border columns of the parked rows; `yEnd` is the row after the last parked one
+    auto flush = [&](const int yEnd) {
         __syncwarp();
-        const int y0 = 2 * k + 2 - sideRows;
+        const int y0 = yEnd - sideRows;
         const int nrows = min(sideRows, a.DH - y0);
         uint8_t *drow = dst + (long long)y0 * a.dstPitch;
-        if (left) streamBorderColumns<NXH>(a, side, drow, a.borderX + 8 * tx0, kBase - tx0, tx0, min(a.mbX, txEnd), nrows, lane);
-        if (right)
-            streamBorderColumns<NXH>(a, side, drow, a.borderX + 8 * (a.mbX + rcol0 - a.meX), kBase - tx0 - 4 * rc0 + 16, rcol0, txEnd,
-                                     nrows, lane);
+        if (nrows > 0) {
+            if (left) streamBorderColumns<NXH>(a, side, drow, a.borderX + 8 * tx0, kBase - tx0, tx0, min(a.mbX, txEnd), nrows, lane);
+            if (right)
+                streamBorderColumns<NXH>(a, side, drow, a.borderX + 8 * (a.mbX + rcol0 - a.meX), kBase - tx0 - 4 * rc0 + 16, rcol0,
+                                         txEnd, nrows, lane);
+        }
         __syncwarp();
         sideRows = 0;
         sideAddr = sideLane;
     };
 
-    // vertical pass of destination row pair k; `s` (compile-time) is the position of the register ring
-    auto vertical = [&](auto edgeTag, auto ringPos, const int k) {
+    // vertical pass of the s-th row pair (k) of a turn; s is also the position of the register ring
+    auto vertical = [&](auto edgeTag, auto stepTag, const int k) {
         constexpr bool EDGE = decltype(edgeTag)::value;
-        constexpr int s = decltype(ringPos)::value;
-        issue(edgeTag);  // runs kStreamRing - 1 groups ahead (overshoots the band end, clamped to the image)
-        consume(winA[(s + NG - 1) % NG], winB[(s + NG - 1) % NG]);
+        constexpr int s = decltype(stepTag)::value;
+        // step s of a turn reads group n = NG t + s + NG - 1: slot NG-1 of the current half for s == 0, else slot s-1 of
+        // the other half; the request goes into the slot read one step earlier
+        const uint32_t ra = s == 0 ? fifoCur + (NG - 1) * kStreamSlotBytes : fifoOth + (s - 1) * kStreamSlotBytes;
+        const uint32_t sa = s == 0 ? fifoCur + (NG - 2) * kStreamSlotBytes
+                          : s == 1 ? fifoCur + (NG - 1) * kStreamSlotBytes : fifoOth + (s - 2) * kStreamSlotBytes;
+        issue(edgeTag, sa);
+        consume(ra, winA[(s + NG - 1) % NG], winB[(s + NG - 1) % NG]);
 #pragma unroll
         for (int par = 0; par < 2; ++par) {
             uint32_t c0 = a.cwY[par][0], c1 = NG > 1 ? a.cwY[par][1] : 0u, c2 = NG > 2 ? a.cwY[par][2] : 0u;
@@ -988,62 +1001,63 @@ __global__ void __launch_bounds__(32 * kStreamWarps, IQO_STREAM_MINB) resizeHalf
             o.z = prmt((uint32_t)v[3], (uint32_t)v[4], 0x5410);
             o.w = prmt((uint32_t)v[5], (uint32_t)v[6], 0x5410);
             if (par == 0) {
-                stsV4<0>(wst, o);
-                if (park) stsV4<0>(sideAddr, o);
+                stsV4<2 * s * kStreamRowBytes>(wst, o);
+                if (park) stsV4<2 * s * 4 * kStreamSideWords>(sideAddr, o);
             } else {
-                stsV4<kStreamRowBytes>(wst, o);
-                if (park) stsV4<4 * kStreamSideWords>(sideAddr, o);
+                stsV4<(2 * s + 1) * kStreamRowBytes>(wst, o);
+                if (park) stsV4<(2 * s + 1) * 4 * kStreamSideWords>(sideAddr, o);
             }
         }
     };
 
-    int s = 0;
-    int wflip = 2 * kStreamRowBytes;
-    for (int k = k0; k < k1; ++k) {
-        if (k >= kIntB && k < kIntE) {
-            if (NG == 1 || s == 0)
-                vertical(BoolTag<false>(), std::integral_constant<int, 0>(), k);
-            else if (NG == 2 || s == 1)
-                vertical(BoolTag<false>(), std::integral_constant<int, 1 % NG>(), k);
-            else
-                vertical(BoolTag<false>(), std::integral_constant<int, 2 % NG>(), k);
+    for (int k = k0; k < k1; k += NG) {
+        if (k >= kIntB && k + NG <= kIntE) {
+            vertical(BoolTag<false>(), std::integral_constant<int, 0>(), k);
+            if (NG > 1) vertical(BoolTag<false>(), std::integral_constant<int, 1 % NG>(), k + 1);
+            if (NG > 2) vertical(BoolTag<false>(), std::integral_constant<int, 2 % NG>(), k + 2);
         } else {
-            if (NG == 1 || s == 0)
-                vertical(BoolTag<true>(), std::integral_constant<int, 0>(), k);
-            else if (NG == 2 || s == 1)
-                vertical(BoolTag<true>(), std::integral_constant<int, 1 % NG>(), k);
-            else
-                vertical(BoolTag<true>(), std::integral_constant<int, 2 % NG>(), k);
+            vertical(BoolTag<true>(), std::integral_constant<int, 0>(), k);
+            if (NG > 1) vertical(BoolTag<true>(), std::integral_constant<int, 1 % NG>(), k + 1);
+            if (NG > 2) vertical(BoolTag<true>(), std::integral_constant<int, 2 % NG>(), k + 2);
         }
-        s = (s + 1 == NG) ? 0 : s + 1;
         __syncwarp();
-        // horizontal pass of the pair: lane = (row, 8-pixel group)
-        if (hmode != 0 && 2 * k + hrow < a.DH) {
-            uint32_t n[16];
-            const uint4 q0 = ldsV4<0>(wld), q1 = ldsV4<16>(wld), q2 = ldsV4<32>(wld), q3 = ldsV4<48>(wld);
-            n[0] = q0.x, n[1] = q0.y, n[2] = q0.z, n[3] = q0.w;
-            n[4] = q1.x, n[5] = q1.y, n[6] = q1.z, n[7] = q1.w;
-            n[8] = q2.x, n[9] = q2.y, n[10] = q2.z, n[11] = q2.w;
-            n[12] = q3.x, n[13] = q3.y, n[14] = q3.z, n[15] = q3.w;
-            const uint2 o = halfGroupPixelsOdd<NXH, SYM, SKIP0>(a, n);
-            if (hmode == 1)
-                *reinterpret_cast<uint2 *>(outp) = o;
-            else if (hmode == 2)
-                *reinterpret_cast<uint32_t *>(outp) = o.x;
-            else
-                halfStoreBytes(outp, o, 0, min(8, a.DW - d0));
+        // horizontal pass of the turn's row pairs that belong to the band: lane = (row of the pair, 8-pixel group)
+        const int np = min(NG, k1 - k);
+        if (hmode != 0) {
+            uint32_t wl = wld;
+            uint8_t *op = outp;
+#pragma unroll
+            for (int i = 0; i < NG; ++i, wl += 2 * kStreamRowBytes, op += ostep) {
+                if (i >= np) break;
+                if (2 * (k + i) + hrow >= a.DH) break;
+                uint32_t n[16];
+                const uint4 q0 = ldsV4<0>(wl), q1 = ldsV4<16>(wl), q2 = ldsV4<32>(wl), q3 = ldsV4<48>(wl);
+                n[0] = q0.x, n[1] = q0.y, n[2] = q0.z, n[3] = q0.w;
+                n[4] = q1.x, n[5] = q1.y, n[6] = q1.z, n[7] = q1.w;
+                n[8] = q2.x, n[9] = q2.y, n[10] = q2.z, n[11] = q2.w;
+                n[12] = q3.x, n[13] = q3.y, n[14] = q3.z, n[15] = q3.w;
+                const uint2 o = halfGroupPixelsOdd<NXH, SYM, SKIP0>(a, n);
+                if (hmode == 1)
+                    *reinterpret_cast<uint2 *>(op) = o;
+                else if (hmode == 2)
+                    *reinterpret_cast<uint32_t *>(op) = o.x;
+                else
+                    halfStoreBytes(op, o, 0, min(8, a.DW - d0));
+            }
         }
-        outp += ostep;
-        wst += wflip;  // the other W buffer
-        wld += wflip;
-        wflip = -wflip;
+        outp += NG * ostep;
+        __syncwarp();  // the W rows are free again
+        if (IQO_STREAM_FIFO_TURNS > 1) {
+            const uint32_t t = fifoCur;
+            fifoCur = fifoOth;
+            fifoOth = t;
+        }
         if (edgeStrip) {
-            sideRows += 2;
-            sideAddr += 2 * 4 * kStreamSideWords;
-            if (sideRows == kStreamSideRows) flush(k);
+            sideRows += 2 * np;
+            sideAddr += 2 * NG * 4 * kStreamSideWords;
+            if (sideRows + 2 * NG > kStreamSideRows || k + NG >= k1) flush(2 * (k + np));
         }
     }
-    if (sideRows) flush(k1 - 1);
     asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
@@ -1053,7 +1067,15 @@ cudaError_t launchHalfStreamT(const HalfArgs &a, cudaStream_t stream)
     const int strips = (a.DW + kHalfTileW - 1) / kHalfTileW;
     const int pairs = (a.DH + 1) / 2;
     dim3 grid((strips + kStreamWarps - 1) / kStreamWarps, (pairs + a.bandPairs - 1) / a.bandPairs, a.nFrames);
-    resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z><<<grid, 32 * kStreamWarps, 0, stream>>>(a);
+    constexpr int smem = kStreamWarps * streamWarpBytes(NG);
+    static PerDeviceOnce attrSet;  // per instantiation; a benign race sets it twice at worst
+    const int dev = currentDevice();
+    if (!attrSet.done(dev)) {
+        cudaError_t e = cudaFuncSetAttribute(resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        attrSet.set(dev);
+    }
+    resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z><<<grid, 32 * kStreamWarps, smem, stream>>>(a);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }

@@ -736,14 +736,19 @@ struct BoolTag {
     static constexpr bool value = B;
 };
 
+#ifndef IQO_STREAM_WARPS
+#define IQO_STREAM_WARPS 1
+#endif
 #ifndef IQO_STREAM_MINB
-#define IQO_STREAM_MINB 4
+#define IQO_STREAM_MINB 16
 #endif
 #ifndef IQO_STREAM_MAXREG
-#define IQO_STREAM_MAXREG 112
+#define IQO_STREAM_MAXREG 0
 #endif
-#ifndef IQO_STREAM_WARPS
-#define IQO_STREAM_WARPS 4
+#if IQO_STREAM_MAXREG
+#define IQO_STREAM_BOUNDS __maxnreg__(IQO_STREAM_MAXREG)
+#else
+#define IQO_STREAM_BOUNDS __launch_bounds__(32 * IQO_STREAM_WARPS, IQO_STREAM_MINB)
 #endif
 constexpr int kStreamWarps = IQO_STREAM_WARPS;  // strips (warps) per CTA
 constexpr int kStreamSideRows = 16;   // destination rows parked before the border columns are flushed
@@ -812,7 +817,7 @@ __host__ __device__ constexpr int streamWarpBytes(int NG)
 // positions, FIFO slots and W rows are compile-time constants and the per-pair bookkeeping is
 // paid once per turn: NG vertical passes, one __syncwarp, then the horizontal pass of the 2 NG rows.
 template <int NG, int NXH, bool SYM, bool SKIP0, int Z>
-__global__ void __launch_bounds__(32 * kStreamWarps, IQO_STREAM_MINB) resizeHalfStreamKernel(const __grid_constant__ HalfArgs a)
+__global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__ HalfArgs a)
 {
     extern __shared__ __align__(16) uint8_t streamSmem[];
     constexpr int kBase = 5 - NXH / 2;  // pair word of taps 0, 1 of pixel 0

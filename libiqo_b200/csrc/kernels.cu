@@ -7,6 +7,8 @@
 // is exact.
 #include "kernels.cuh"
 
+#include <stdlib.h>
+
 #include <algorithm>
 #include <atomic>
 #include <type_traits>
@@ -751,31 +753,32 @@ struct BoolTag {
 #define IQO_STREAM_BOUNDS __launch_bounds__(32 * IQO_STREAM_WARPS, IQO_STREAM_MINB)
 #endif
 constexpr int kStreamWarps = IQO_STREAM_WARPS;  // strips (warps) per CTA
-constexpr int kStreamSideRows = 16;   // destination rows parked before the border columns are flushed
+#ifndef IQO_STREAM_SIDE_ROWS
+#define IQO_STREAM_SIDE_ROWS 16
+#endif
+constexpr int kStreamSideRows = IQO_STREAM_SIDE_ROWS;   // destination rows parked before the border columns are flushed
 constexpr int kStreamSideWords = 32;  // per parked row: W chunks 0..3 (left) and rc0..rc0+3 (right)
 
-// Border columns [c0, c1) of `nrows` parked rows; `wordOff` maps (column + pair word) to a side word.
+// Border columns [c0, c1) of `nrows` (<= 32) parked rows: a lane per row, the columns in a loop so
+// that their coefficient words are uniform loads; `wordOff` maps (column + pair word) to a side word.
 template <int NXH>
 __device__ __noinline__ void streamBorderColumns(const HalfArgs &a, const uint32_t *side, uint8_t *dstRow0, const int32_t *bx,
                                                  int wordOff, int c0, int c1, int nrows, int lane)
 {
-    const int nb = c1 - c0;
-    for (int item = lane; item < nb * nrows; item += 32) {
-        const int r = item / nb;
-        const int j = item - r * nb;
-        const int d = c0 + j;
-        const uint32_t *wr = side + r * kStreamSideWords + d + wordOff;
-        const int32_t *e = bx + j * 8;
-        int lo = __ldg(e + 7), hi = 0;
+    if (lane >= nrows) return;
+    const uint32_t *wr = side + lane * kStreamSideWords + wordOff;
+    uint8_t *out = dstRow0 + (long long)lane * a.dstPitch;
+    for (int d = c0; d < c1; ++d, bx += 8) {
+        int lo = __ldg(bx + 7), hi = 0;
 #pragma unroll
         for (int i = 0; i < NXH; ++i) {
-            const uint32_t word = wr[i];
-            const uint32_t cw = (uint32_t)__ldg(e + i);
+            const uint32_t word = wr[d + i];
+            const uint32_t cw = (uint32_t)__ldg(bx + i);
             lo = dp2a_lo_uu(word, cw, lo);
             hi = dp2a_hi_us(word, cw, hi);
         }
-        const int v = (int)(short)((lo + (hi << 8)) / __ldg(e + 6));
-        dstRow0[(long long)r * a.dstPitch + d] = (uint8_t)min(max(v, 0), 255);
+        const int v = (int)(short)((lo + (hi << 8)) / __ldg(bx + 6));
+        out[d] = (uint8_t)min(max(v, 0), 255);
     }
 }
 
@@ -803,7 +806,8 @@ __device__ __forceinline__ void stsV4(uint32_t addr, uint4 v)
 }
 
 constexpr int kStreamRowBytes = 4 * kHalfRowWords + 16;  // W row stride: the 16-byte skew keeps the two rows of a pair on different banks
-constexpr int kStreamSlotBytes = 4 * 32 * 8;             // one source group of a warp: 4 rows x 256 bytes
+constexpr int kStreamSrcRowBytes = 272;                  // staged bytes of a source row: 17 aligned 16-byte chunks
+constexpr int kStreamSlotBytes = 4 * kStreamSrcRowBytes; // one source group of a warp: 4 rows
 #ifndef IQO_STREAM_FIFO_TURNS
 #define IQO_STREAM_FIFO_TURNS 2
 #endif
@@ -836,12 +840,15 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
     const int txEnd = min(tx0 + kHalfTileW, a.DW);
     uint8_t *warpSmem = streamSmem + warp * streamWarpBytes(NG);
     const uint32_t wBase = smemAddr(warpSmem);
-    const uint32_t fifoBase = wBase + kWBuf + 8 * lane;
+    const uint32_t fifoBase = wBase + kWBuf;
     uint32_t *side = reinterpret_cast<uint32_t *>(warpSmem + kWBuf + kFifo * kStreamSlotBytes);
 
-    // vertical role: columns outside the image only ever meet zero coefficients (read column 0)
-    const int col = xs0 + 8 * lane;
-    const uint8_t *base = src + ((col >= 0 && col < a.SW) ? col : 0);
+    // source role: lanes 0..16 copy the 16-byte aligned chunks [xs0 - 8 + 16 lane, +16) of a source row (L1 bypassed);
+    // chunks outside the image are zero-filled without a read, one that straddles the right edge reads 8 bytes
+    const int ccol = xs0 - 8 + 16 * lane;
+    const bool copyLane = lane < 17;
+    const int csize = (ccol < 0 || ccol >= a.SW) ? 0 : min(16, a.SW - ccol);
+    const uint8_t *base = src + (csize ? ccol : 0);
     const long long pitch = a.srcPitch;
     const int SHm1 = a.SH - 1;
     const int B = a.workBias;
@@ -878,28 +885,36 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
     // FIFO slot of the n-th group of the band is n mod kFifo.  With a FIFO two turns deep the slots
     // of a turn alternate between the halves fifoCur / fifoOth.
     uint32_t fifoCur = fifoBase, fifoOth = fifoBase + (IQO_STREAM_FIFO_TURNS > 1 ? NG * kStreamSlotBytes : 0);
-    auto issue = [&](auto edgeTag, const uint32_t sa) {  // request the four rows of group g into slot `sa`
-        if (decltype(edgeTag)::value) {
+    auto issue = [&](auto edgeTag, const uint32_t slot) {  // request the four rows of group g into `slot`
+        const uint32_t sa = slot + 16 * lane;
+        if (copyLane) {
+            if (decltype(edgeTag)::value) {
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int row = min(max(4 * g + a.delta + j, 0), SHm1);
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa + 256 * j), "l"(base + (long long)row * pitch) : "memory");
+                for (int j = 0; j < 4; ++j) {
+                    const int row = min(max(4 * g + a.delta + j, 0), SHm1);
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa + kStreamSrcRowBytes * j),
+                                 "l"(base + (long long)row * pitch), "r"(csize)
+                                 : "memory");
+                }
+            } else {
+                const uint8_t *p1 = gp + pitch;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gp), "r"(csize) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0+272], [%1], 16, %2;" ::"r"(sa), "l"(p1), "r"(csize) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0+544], [%1], 16, %2;" ::"r"(sa), "l"(gp + 2 * pitch), "r"(csize) : "memory");
+                asm volatile("cp.async.cg.shared.global [%0+816], [%1], 16, %2;" ::"r"(sa), "l"(p1 + 2 * pitch), "r"(csize) : "memory");
             }
-        } else {
-            const uint8_t *p1 = gp + pitch;
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(sa), "l"(gp) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0+256], [%1], 8;" ::"r"(sa), "l"(p1) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0+512], [%1], 8;" ::"r"(sa), "l"(gp + 2 * pitch) : "memory");
-            asm volatile("cp.async.ca.shared.global [%0+768], [%1], 8;" ::"r"(sa), "l"(p1 + 2 * pitch) : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
         gp += 4 * pitch;
         ++g;
     };
     // oldest requested group (slot `ra`) -> transposed columns: .x/.y/.z/.w = four vertical bytes of column 0..3 (A) and 4..7 (B)
-    auto consume = [&](const uint32_t ra, uint4 &ca, uint4 &cb) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(kFifo - 1) : "memory");
-        const uint2 r0 = ldsV2<0>(ra), r1 = ldsV2<256>(ra), r2 = ldsV2<512>(ra), r3 = ldsV2<768>(ra);
+    auto consume = [&](const uint32_t slot, uint4 &ca, uint4 &cb) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(kFifo - 2) : "memory");
+        __syncwarp();  // the chunks were copied by other lanes; everybody has also read the slot refilled next
+        const uint32_t ra = slot + 8 + 8 * lane;
+        const uint2 r0 = ldsV2<0>(ra), r1 = ldsV2<kStreamSrcRowBytes>(ra), r2 = ldsV2<2 * kStreamSrcRowBytes>(ra),
+                    r3 = ldsV2<3 * kStreamSrcRowBytes>(ra);
         const uint32_t t0 = prmt(r0.x, r1.x, 0x5140), t1 = prmt(r0.x, r1.x, 0x7362);
         const uint32_t t2 = prmt(r2.x, r3.x, 0x5140), t3 = prmt(r2.x, r3.x, 0x7362);
         ca.x = prmt(t0, t2, 0x5410);
@@ -914,15 +929,15 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
         cb.w = prmt(u1, u3, 0x7632);
     };
     // Group n of the band (n = 0 is group k0 + qmin) lives in slot n mod kFifo; the request of group
-    // n + kFifo - 1 goes out right before group n is read and lands in the slot read one step earlier.
+    // n + kFifo - 1 goes out right after group n is read and lands in the slot read one step earlier.
     // Before the first turn: groups 0 .. NG-2 are in the register ring, groups up to NG + kFifo - 3 requested.
     uint4 winA[NG], winB[NG];
 #pragma unroll
     for (int j = 0; j < kFifo - 1; ++j) issue(BoolTag<true>(), fifoBase + j * kStreamSlotBytes);
 #pragma unroll
     for (int j = 0; j < NG - 1; ++j) {
-        issue(BoolTag<true>(), fifoBase + ((j + kFifo - 1) % kFifo) * kStreamSlotBytes);
         consume(fifoBase + j * kStreamSlotBytes, winA[j], winB[j]);
+        issue(BoolTag<true>(), fifoBase + ((j + kFifo - 1) % kFifo) * kStreamSlotBytes);
     }
 
     // border columns of the parked rows; `yEnd` is the row after the last parked one
@@ -951,8 +966,8 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
         const uint32_t ra = s == 0 ? fifoCur + (NG - 1) * kStreamSlotBytes : fifoOth + (s - 1) * kStreamSlotBytes;
         const uint32_t sa = s == 0 ? fifoCur + (NG - 2) * kStreamSlotBytes
                           : s == 1 ? fifoCur + (NG - 1) * kStreamSlotBytes : fifoOth + (s - 2) * kStreamSlotBytes;
-        issue(edgeTag, sa);
         consume(ra, winA[(s + NG - 1) % NG], winB[(s + NG - 1) % NG]);
+        issue(edgeTag, sa);
 #pragma unroll
         for (int par = 0; par < 2; ++par) {
             uint32_t c0 = a.cwY[par][0], c1 = NG > 1 ? a.cwY[par][1] : 0u, c2 = NG > 2 ? a.cwY[par][2] : 0u;
@@ -1078,6 +1093,10 @@ cudaError_t launchHalfStreamT(const HalfArgs &a, cudaStream_t stream)
     if (!attrSet.done(dev)) {
         cudaError_t e = cudaFuncSetAttribute(resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
+        if (const char *c = getenv("IQO_CUDA_STREAM_CARVEOUT")) {  // experiment: percent of the L1/shared array used as shared memory
+            e = cudaFuncSetAttribute(resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
+            if (e != cudaSuccess) return e;
+        }
         attrSet.set(dev);
     }
     resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z><<<grid, 32 * kStreamWarps, smem, stream>>>(a);

@@ -738,20 +738,14 @@ struct BoolTag {
     static constexpr bool value = B;
 };
 
+// Launch shape of the streaming kernel: one warp per CTA, 16 CTAs per SM.
 #ifndef IQO_STREAM_WARPS
 #define IQO_STREAM_WARPS 1
 #endif
 #ifndef IQO_STREAM_MINB
 #define IQO_STREAM_MINB 16
 #endif
-#ifndef IQO_STREAM_MAXREG
-#define IQO_STREAM_MAXREG 0
-#endif
-#if IQO_STREAM_MAXREG
-#define IQO_STREAM_BOUNDS __maxnreg__(IQO_STREAM_MAXREG)
-#else
 #define IQO_STREAM_BOUNDS __launch_bounds__(32 * IQO_STREAM_WARPS, IQO_STREAM_MINB)
-#endif
 constexpr int kStreamWarps = IQO_STREAM_WARPS;  // strips (warps) per CTA
 #ifndef IQO_STREAM_SIDE_ROWS
 #define IQO_STREAM_SIDE_ROWS 16
@@ -1093,10 +1087,6 @@ cudaError_t launchHalfStreamT(const HalfArgs &a, cudaStream_t stream)
     if (!attrSet.done(dev)) {
         cudaError_t e = cudaFuncSetAttribute(resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        if (const char *c = getenv("IQO_CUDA_STREAM_CARVEOUT")) {  // experiment: percent of the L1/shared array used as shared memory
-            e = cudaFuncSetAttribute(resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(c));
-            if (e != cudaSuccess) return e;
-        }
         attrSet.set(dev);
     }
     resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z><<<grid, 32 * kStreamWarps, smem, stream>>>(a);

@@ -363,6 +363,18 @@ def _run_cuda(args, json_fd):
                 "kernel": kernel_name, "launches_per_step": launches_per_step,
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(launch_ms, 4),
                 "macs_per_dst_px": None}
+    try:
+        # compute side: all taps counted, zeros included; the scalar-IMAD peak is the measured
+        # 64 lanes/clk/SM (profiles/r1_microbench_pipe_rates.txt) at the sampled SM clock.  dp4a/dp2a do 4/2 MACs
+        # per lane-instruction and mirrored taps are pre-added, so the achieved MAC rate may exceed that peak.
+        ny = iqo.plan_query(kind, deg, sw, sh, dw, dh, px, 1)["numCoefs"] if sh != dh else 1
+        nx = iqo.plan_query(kind, deg, sw, sh, dw, dh, px, 0)["numCoefs"] if sw != dw else 1
+        macs = (ny * sw * dh + nx * dw * dh) / float(dw * dh)
+        roofline["macs_per_dst_px"] = round(macs, 2)
+        roofline["achieved_tmac_s"] = round(value * 1e6 * macs / 1e12, 2)
+        roofline["imad_peak_tmac_s"] = round(148 * 64 * 1.965e9 / 1e12, 2)
+    except Exception:
+        pass
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

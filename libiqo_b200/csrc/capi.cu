@@ -99,6 +99,7 @@ struct SharedPlan {
     Plan plan;
     HalfPlan half;
     SmallPlan small;
+    RatioPlan ratio;
     PackedPlan packed;
     GenericGeom geom;
     PackedGeom pgeom;
@@ -109,10 +110,11 @@ struct SharedPlan {
     // packed kernel tables
     int32_t *pFirstY, *pNtapY, *pCoefOffY, *pRecX;
     uint32_t *pMagicY, *pCwX;
+    int32_t *rRowRec;     // rational-ratio streaming path
     int32_t *sRowsY;      // small-kernel path
     uint32_t *sMagicY;
     SharedPlan()
-        : device(0), dBorderY(0), dMagicY(0), dSBorderY(0), dBorderX(0), dBorderXo(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), sRowsY(0), sMagicY(0)
+        : device(0), dBorderY(0), dMagicY(0), dSBorderY(0), dBorderX(0), dBorderXo(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), rRowRec(0), sRowsY(0), sMagicY(0)
     {
     }
     ~SharedPlan();
@@ -199,6 +201,7 @@ SharedPlan::~SharedPlan()
     cudaFree(pCoefOffY);
     cudaFree(pRecX);
     cudaFree(sRowsY);
+    cudaFree(rRowRec);
     cudaFree(sMagicY);
     cudaFree(pMagicY);
     cudaFree(pCwX);
@@ -450,6 +453,51 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
             return IQO_CUDA_OK;
         }
     }
+    // Lanczos at 3:2, 1:2, 3:4 ...: rational-ratio streaming kernel
+    if (r->useStream && sp.ratio.eligible && whole && ((uintptr_t)src % 8) == 0 && srcSt % 8 == 0 && srcFrameStride % 8 == 0) {
+        const RatioPlan &rp = sp.ratio;
+        RatioArgs q;
+        q.srcPitch = (long long)srcSt;
+        q.dstPitch = (long long)dstSt;
+        q.srcFrameStride = (long long)srcFrameStride;
+        q.dstFrameStride = (long long)dstFrameStride;
+        q.SW = int(r->plan.x.S);
+        q.SH = int(r->plan.y.S);
+        q.DW = int(r->plan.x.D);
+        q.DH = int(r->plan.y.D);
+        q.RS = rp.RS;
+        q.RD = rp.RD;
+        q.NX = rp.NX;
+        q.groupsPerStrip = rp.groupsPerStrip;
+        q.c0 = rp.c0;
+        q.workBias = rp.workBias;
+        q.accInit = rp.accInit;
+        q.dstVec = ((uintptr_t)dst % 8) == 0 && dstSt % 8 == 0 && dstFrameStride % 8 == 0;
+        q.rowRec = sp.rRowRec;
+        memset(q.cwX, 0, sizeof q.cwX);
+        for (int ph = 0; ph < rp.RD && ph < 4; ++ph)
+            for (int par = 0; par < 2; ++par)
+                for (int j = 0; j < 6; ++j) q.cwX[ph][par][j] = rp.cwX[(size_t(ph) * 2 + par) * 6 + j];
+        q.mbX = int(r->plan.x.mainBegin);
+        q.meX = int(r->plan.x.mainEnd);
+        q.gx = a.x;
+        q.gy = a.y;
+        // bands of whole 8-row turns: enough warps to fill the device several times over
+        const long long strips = (q.DW + 8 * q.groupsPerStrip - 1) / (8 * q.groupsPerStrip);
+        int bandRows = 256;
+        while (bandRows > 32 && strips * ((q.DH + bandRows - 1) / bandRows) * (long long)nFrames < 6ll * 148 * 16) bandRows /= 2;
+        q.bandRows = bandRows;
+        if ((q.DH + bandRows - 1) / bandRows <= 65535) {
+            r->lastKernel = "ratio_stream";
+            for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
+                q.nFrames = int(std::min<size_t>(65535, nFrames - f0));
+                q.src = src + f0 * srcFrameStride;
+                q.dst = dst + f0 * dstFrameStride;
+                CUDA_TRY(launchRatio(q, stream));
+            }
+            return IQO_CUDA_OK;
+        }
+    }
     if (r->path == IQO_CUDA_PATH_AUTO && sp.packed.eligible && ((uintptr_t)src % 4) == 0 && srcSt % 4 == 0 &&
         srcFrameStride % 4 == 0 && dstRows <= size_t(65535) * sp.pgeom.tileH) {
         PackedArgs q;
@@ -607,6 +655,11 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
     if (sp->small.eligible && (!uploadVec(sp->sRowsY, sp->small.rowsY) || !uploadVec(sp->sMagicY, sp->small.magicY))) {
         cudaGetLastError();
         sp->small.eligible = false;
+    }
+    buildRatioPlan(sp->plan, sp->ratio);
+    if (sp->ratio.eligible && (!ratioHasKernel(sp->ratio.RS, sp->ratio.RD, sp->ratio.NX) || !uploadVec(sp->rRowRec, sp->ratio.rowRec))) {
+        cudaGetLastError();
+        sp->ratio.eligible = false;
     }
     buildPackedPlan(sp->plan, sp->packed, packedPadNP(sp->plan.x.N / 2 + 1));
     if (sp->packed.eligible) {
@@ -892,12 +945,15 @@ int iqo_cuda_plan_kernel(int kind, unsigned degree, size_t srcW, size_t srcH, si
     buildPackedPlan(p, q, packedPadNP(p.x.N / 2 + 1));
     SmallPlan sm;
     buildSmallPlan(p, sm);
+    RatioPlan rt;
+    buildRatioPlan(p, rt);
+    const bool ratio = rt.eligible && ratioHasKernel(rt.RS, rt.RD, rt.NX);
     const bool area2 = p.kind == kArea && p.x.rD == 1 && p.x.rS == 2 && p.y.rD == 1 && p.y.rS == 2 && p.x.N == 2 && p.y.N == 2 && p.x.S % 16 == 0;
     const long long kx = (p.x.D % p.x.S == 0) ? p.x.D / p.x.S : 0;
     const bool linup = p.kind == kLinear && (kx == 2 || kx == 3) && p.x.S % 4 == 0 && !p.y.identity;
     if (kernel && kernelCap)
         snprintf(kernel, kernelCap, "%s", sm.eligible ? "half_small" : h.eligible ? (h.symmetric ? "half_sym" : "half") : area2 ? "area2"
-                                          : linup ? (kx == 2 ? "linear_up2" : "linear_up3") : q.eligible ? "packed" : "generic");
+                                          : linup ? (kx == 2 ? "linear_up2" : "linear_up3") : ratio ? "ratio_stream" : q.eligible ? "packed" : "generic");
     if (why && whyCap) snprintf(why, whyCap, "%s%s%s", h.why.c_str(), q.eligible ? "" : "; packed: ", q.eligible ? "" : q.why.c_str());
     return IQO_CUDA_OK;
 }

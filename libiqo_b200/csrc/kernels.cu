@@ -1583,6 +1583,217 @@ __global__ void __launch_bounds__(128) resizeHalfSmallKernel(const __grid_consta
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Rational-ratio streaming kernel (plan.hpp RatioPlan): Lanczos at RS:RD with RD | 8 (3:2, 1:2, 3:4),
+// at most 10 horizontal taps.  Same organisation as resizeHalfStreamKernel -- one warp per CTA
+// walks down a column strip, dp4a vertical pass, dp2a horizontal pass on 8 pixels per lane --
+// but table-driven where the 2:1 kernel is hard-wired:
+//   vertical    a lane owns 8 source columns.  Every new group of four source rows is transposed
+//               once (2 x 8 PRMT) and parked in a lane-private ring of 8 groups in shared memory;
+//               a destination row reads the <= 4 groups its record names (2 LDS.128 + 8 dp4a each,
+//               coefficient words from the per-row record, so phases and border rows need no code).
+//   horizontal  every 8 destination rows: lane = (row, group of 8 pixels).  Pixel p of a group starts
+//               at W element GS q + floor(p RS / RD) (+ an even offset): word offsets and parities
+//               are compile-time, the coefficient words of (phase, parity) sit in the constant bank.
+//   borders     border rows: masked words + multiply-high division from the record; border columns
+//               are recomputed per pixel from the generic tables.
+// ---------------------------------------------------------------------------------------
+constexpr int kRatioRing = 8;                                   // transposed groups per lane
+constexpr int kRatioRingBytes = kRatioRing * 32 * 32;           // [slot][half A/B][lane][16 bytes]
+constexpr int kRatioSmem = kRatioRingBytes + 8 * kStreamRowBytes;
+
+template <int RS, int RD, int NX>
+__global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_constant__ RatioArgs a)
+{
+    extern __shared__ __align__(16) uint8_t ratioSmem[];
+    constexpr int GS = 8 * RS / RD;
+    const int lane = threadIdx.x;
+    const int tx0 = blockIdx.x * (8 * a.groupsPerStrip);
+    const int y0 = blockIdx.y * a.bandRows;
+    const int y1 = min(y0 + a.bandRows, a.DH);
+    const uint8_t *__restrict__ src = a.src + (long long)blockIdx.z * a.srcFrameStride;
+    uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
+    const int ngs = min(a.groupsPerStrip, (a.DW - tx0) >> 3);   // 8-pixel groups of this strip
+    const int first0 = GS * (tx0 >> 3) + a.c0;                  // first tap of pixel tx0
+    const int xs0 = first0 & ~7;                                 // source column of W element 0 (may be negative)
+    const int i0 = first0 - xs0;                                 // even
+    const uint32_t ringBase = smemAddr(ratioSmem) + 16 * lane;
+    const uint32_t wBase = smemAddr(ratioSmem) + kRatioRingBytes;
+    const int B = a.workBias;
+    const int SHm1 = a.SH - 1;
+    const long long pitch = a.srcPitch;
+
+    // vertical role: columns outside the image only ever meet zero coefficients (read column 0)
+    const int col = xs0 + 8 * lane;
+    const uint8_t *base = src + ((col >= 0 && col < a.SW) ? col : 0);
+    uint2 raw[4];
+    auto fetch = [&](int g) {
+        if (g >= 0 && 4 * g + 3 <= SHm1) {
+            const uint8_t *p = base + (long long)(4 * g) * pitch;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) raw[j] = __ldg(reinterpret_cast<const uint2 *>(p + j * pitch));
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int row = min(max(4 * g + j, 0), SHm1);
+                raw[j] = __ldg(reinterpret_cast<const uint2 *>(base + (long long)row * pitch));
+            }
+        }
+    };
+    auto park = [&](int g) {  // transposed group -> ring slot g mod 8
+        const uint32_t t0 = prmt(raw[0].x, raw[1].x, 0x5140), t1 = prmt(raw[0].x, raw[1].x, 0x7362);
+        const uint32_t t2 = prmt(raw[2].x, raw[3].x, 0x5140), t3 = prmt(raw[2].x, raw[3].x, 0x7362);
+        uint4 ca, cb;
+        ca.x = prmt(t0, t2, 0x5410);
+        ca.y = prmt(t0, t2, 0x7632);
+        ca.z = prmt(t1, t3, 0x5410);
+        ca.w = prmt(t1, t3, 0x7632);
+        const uint32_t u0 = prmt(raw[0].y, raw[1].y, 0x5140), u1 = prmt(raw[0].y, raw[1].y, 0x7362);
+        const uint32_t u2 = prmt(raw[2].y, raw[3].y, 0x5140), u3 = prmt(raw[2].y, raw[3].y, 0x7362);
+        cb.x = prmt(u0, u2, 0x5410);
+        cb.y = prmt(u0, u2, 0x7632);
+        cb.z = prmt(u1, u3, 0x5410);
+        cb.w = prmt(u1, u3, 0x7632);
+        const uint32_t sa = ringBase + (g & (kRatioRing - 1)) * 1024;
+        stsV4<0>(sa, ca);
+        stsV4<512>(sa, cb);
+    };
+
+    int gNext = __ldg(a.rowRec + 8 * y0);  // groups are non-decreasing in y
+    fetch(gNext);
+    const uint32_t rcp = (65536u + ngs - 1) / ngs;
+    const bool left = tx0 < a.mbX, right = tx0 + 8 * ngs > a.meX;
+
+    for (int y = y0; y < y1; ++y) {
+        const int4 r0 = __ldg(reinterpret_cast<const int4 *>(a.rowRec + 8 * y));
+        const int4 r1 = __ldg(reinterpret_cast<const int4 *>(a.rowRec + 8 * y + 4));
+        const int g0 = r0.x, ng = r0.y;
+        while (gNext < g0 + ng) {  // uniform
+            park(gNext);
+            ++gNext;
+            fetch(gNext);
+        }
+        const int deno = r1.z;
+        const uint32_t magic = (uint32_t)r1.w;
+        const int init = deno ? 0 : B;
+        int v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = init;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            if (t < ng) {
+                const uint32_t c = (uint32_t)(t == 0 ? r0.z : t == 1 ? r0.w : t == 2 ? r1.x : r1.y);
+                const uint32_t sa = ringBase + ((g0 + t) & (kRatioRing - 1)) * 1024;
+                const uint4 qa = ldsV4<0>(sa), qb = ldsV4<512>(sa);
+                v[0] = dp4a_us(qa.x, c, v[0]);
+                v[1] = dp4a_us(qa.y, c, v[1]);
+                v[2] = dp4a_us(qa.z, c, v[2]);
+                v[3] = dp4a_us(qa.w, c, v[3]);
+                v[4] = dp4a_us(qb.x, c, v[4]);
+                v[5] = dp4a_us(qb.y, c, v[5]);
+                v[6] = dp4a_us(qb.z, c, v[6]);
+                v[7] = dp4a_us(qb.w, c, v[7]);
+            }
+        }
+        if (deno) {
+            // resizeYborder: see halfVerticalStrip
+            auto bdiv = [&](int x) -> int {
+                const int n = (int)(short)x * 64;
+                const uint32_t m = (uint32_t)abs(n);
+                const int q = magic ? (int)__umulhi(m, magic) : (int)m;
+                return (int)(short)(n < 0 ? -q : q) + B;
+            };
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = bdiv(v[i]);
+        }
+        uint4 o;
+        o.x = prmt((uint32_t)v[0], (uint32_t)v[1], 0x5410);
+        o.y = prmt((uint32_t)v[2], (uint32_t)v[3], 0x5410);
+        o.z = prmt((uint32_t)v[4], (uint32_t)v[5], 0x5410);
+        o.w = prmt((uint32_t)v[6], (uint32_t)v[7], 0x5410);
+        const int slot = (y - y0) & 7;
+        stsV4<0>(wBase + slot * kStreamRowBytes + 16 * lane, o);
+        if (slot != 7 && y != y1 - 1) continue;
+
+        // ---- horizontal pass of the parked rows ----
+        __syncwarp();
+        const int nr = slot + 1, yt = y - slot;
+        for (int item = lane; item < nr * ngs; item += 32) {
+            const int r = (int)(((uint32_t)item * rcp) >> 16);
+            const int q = item - r * ngs;
+            const uint32_t wl = wBase + r * kStreamRowBytes + 2 * (i0 + GS * q);
+            constexpr int kWords = ((7 * RS / RD) >> 1) + NX / 2 + 1;  // pair words the 8 pixels span (at most)
+            uint32_t n[kWords];
+#pragma unroll
+            for (int j = 0; j < kWords; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(n[j]) : "r"(wl + 4 * j) : "memory");
+            int px[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const int off = (p * RS) / RD;
+                const int wp = off >> 1, par = off & 1, ph = p % RD;
+                const int nw = NX / 2 + par;
+                int acc = a.accInit;
+#pragma unroll
+                for (int j = 0; j < nw; ++j) acc = dp2a_lo_uu(n[wp + j], a.cwX[ph][par][j], acc);
+                acc >>= 8;
+#pragma unroll
+                for (int j = 0; j < nw; ++j) acc = dp2a_hi_us(n[wp + j], a.cwX[ph][par][j], acc);
+                px[p] = acc >> 12;
+            }
+            uint2 o2;
+            o2.x = packSatU8(px[1], px[0], packSatU8(px[3], px[2], 0u));
+            o2.y = packSatU8(px[5], px[4], packSatU8(px[7], px[6], 0u));
+            uint8_t *out = dst + (long long)(yt + r) * a.dstPitch + tx0 + 8 * q;
+            if (a.dstVec)
+                *reinterpret_cast<uint2 *>(out) = o2;
+            else
+                halfStoreBytes(out, o2, 0, 8);
+        }
+        if (left || right) {
+            __syncwarp();  // the main stores of these pixels come first
+            const int c0 = left ? tx0 : max(a.meX, tx0);
+            const int c1 = left ? min(a.mbX, tx0 + 8 * ngs) : tx0 + 8 * ngs;
+            // a strip that holds both borders (narrow images) handles the right one in a second sweep
+            for (int side = 0; side < 2; ++side) {
+                int b0 = c0, b1 = c1;
+                if (side == 1) {
+                    if (!(left && right)) break;
+                    b0 = max(a.meX, max(tx0, a.mbX));
+                    b1 = tx0 + 8 * ngs;
+                }
+                const int nb = b1 - b0;
+                for (int item = lane; item < nr * nb; item += 32) {
+                    // resizeXborder from the parked W row: masked taps, truncating division (finishPixel)
+                    const int r = item / nb, d = b0 + item - r * nb;
+                    const int fx = __ldg(a.gx.first + d), rx = __ldg(a.gx.row + d);
+                    const int32_t *cx = a.gx.coef + rx * NX;
+                    const uint32_t wr = wBase + r * kStreamRowBytes + 2 * (fx - xs0);
+                    int nume = 0;
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) {
+                        uint32_t w16;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w16) : "r"(wr + 2 * i) : "memory");
+                        nume += ((int)w16 - B) * __ldg(cx + i);
+                    }
+                    dst[(long long)(yt + r) * a.dstPitch + d] = finishPixel(nume, __ldg(a.gx.deno + rx), 20);
+                }
+            }
+        }
+        __syncwarp();  // the W rows are free again
+    }
+}
+
+template <int RS, int RD, int NX>
+cudaError_t launchRatioT(const RatioArgs &a, cudaStream_t stream)
+{
+    const int strip = 8 * a.groupsPerStrip;
+    dim3 grid((a.DW + strip - 1) / strip, (a.DH + a.bandRows - 1) / a.bandRows, a.nFrames);
+    resizeRatioStreamKernel<RS, RD, NX><<<grid, 32, kRatioSmem, stream>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D)
@@ -1678,6 +1889,20 @@ cudaError_t launchHalfStream(const HalfArgs &a, cudaStream_t stream)
     IQO_STREAM_CASE(2, 4, 0)
     IQO_STREAM_CASE(2, 2, 0)
 #undef IQO_STREAM_CASE
+    return cudaErrorInvalidValue;
+}
+
+bool ratioHasKernel(int RS, int RD, int NX)
+{
+    return (RS == 3 && RD == 2 && (NX == 10 || NX == 6)) || (RS == 1 && RD == 2 && NX == 6) || (RS == 3 && RD == 4 && NX == 6);
+}
+
+cudaError_t launchRatio(const RatioArgs &a, cudaStream_t stream)
+{
+    if (a.RS == 3 && a.RD == 2 && a.NX == 10) return launchRatioT<3, 2, 10>(a, stream);
+    if (a.RS == 3 && a.RD == 2 && a.NX == 6) return launchRatioT<3, 2, 6>(a, stream);
+    if (a.RS == 1 && a.RD == 2 && a.NX == 6) return launchRatioT<1, 2, 6>(a, stream);
+    if (a.RS == 3 && a.RD == 4 && a.NX == 6) return launchRatioT<3, 4, 6>(a, stream);
     return cudaErrorInvalidValue;
 }
 

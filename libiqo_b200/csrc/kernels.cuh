@@ -148,6 +148,26 @@ struct SmallArgs {
 };
 cudaError_t launchSmall(const SmallArgs &a, cudaStream_t stream);
 
+// Arguments of the rational-ratio streaming kernel (plan.hpp RatioPlan).
+struct RatioArgs {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long srcPitch, dstPitch, srcFrameStride, dstFrameStride;
+    int SW, SH, DW, DH;
+    int nFrames;
+    int RS, RD, NX;
+    int bandRows;              // destination rows per warp (multiple of 8)
+    int groupsPerStrip, c0;
+    int workBias, accInit;
+    int dstVec;                // destination rows may be written with 8-byte stores
+    const int32_t *rowRec;     // [DH][8]
+    uint32_t cwX[4][2][6];     // [phase][parity][pair word]
+    int mbX, meX;
+    AxisDev gx, gy;            // generic tables: border columns are recomputed from them
+};
+bool ratioHasKernel(int RS, int RD, int NX);
+cudaError_t launchRatio(const RatioArgs &a, cudaStream_t stream);
+
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D);
 cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_t stream);
 cudaError_t initKernels();  // sets function attributes once per device

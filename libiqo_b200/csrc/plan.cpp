@@ -765,3 +765,111 @@ void buildSmallPlan(const Plan &p, SmallPlan &s)
 }
 
 }  // namespace iqo_b200
+
+// ---------------------------------------------------------------------------------------------
+// Plan of the rational-ratio streaming kernel
+// ---------------------------------------------------------------------------------------------
+namespace iqo_b200 {
+
+void buildRatioPlan(const Plan &p, RatioPlan &r)
+{
+    r.eligible = false;
+    r.why.clear();
+    const AxisPlan &X = p.x, &Y = p.y;
+    if (p.kind != kLanczos) { r.why = "not Lanczos"; return; }
+    if (X.identity || Y.identity) { r.why = "pass-through axis"; return; }
+    if (X.rD > 8 || 8 % X.rD != 0) { r.why = "horizontal period does not divide 8"; return; }
+    if (X.D % 8 != 0 || X.S % 8 != 0) { r.why = "widths not multiples of 8"; return; }
+    const int NX = X.N, NY = Y.N;
+    if (NX > 10 || (NX & 1)) { r.why = "horizontal kernel longer than 10 taps"; return; }
+    if (Y.coefMin < -128 || Y.coefMax > 127) { r.why = "vertical coefficients do not fit int8"; return; }
+    r.RS = int(X.rS);
+    r.RD = int(X.rD);
+    r.NX = NX;
+    r.GS = int(8 * X.rS / X.rD);
+    if (r.GS & 1) { r.why = "odd source span per 8 pixels"; return; }
+    r.c0 = X.first[0];
+    if (r.c0 & 1) { r.why = "first tap on an odd column"; return; }
+    // the compile-time tap pattern must hold for every destination column
+    for (int64_t d = 0; d < X.D; ++d) {
+        const int64_t G = d / 8, q = d % 8;
+        if (X.first[size_t(d)] != r.GS * G + (q * X.rS) / X.rD + r.c0) { r.why = "first-tap pattern is not periodic in 8"; return; }
+        if (d >= X.mainBegin && d < X.mainEnd && X.row[size_t(d)] != d % X.rD) { r.why = "unexpected coefficient row"; return; }
+    }
+    const int i0 = ((r.c0 % 8) + 8) % 8;
+    r.groupsPerStrip = std::min(32, (256 - NX + 1 - i0) / r.GS);
+    while (r.groupsPerStrip > 1 && (r.GS * r.groupsPerStrip) % 8 != 0) --r.groupsPerStrip;  // strips start on whole 8-column words
+    if ((r.GS * r.groupsPerStrip) % 8 != 0) { r.why = "no strip width keeps the source window 8-byte aligned"; return; }
+
+    // ---- vertical records ----
+    long long wmin = 0, wmax = 0;
+    for (int rr = 0; rr < Y.numRows; ++rr) {
+        long long pos = 0, neg = 0;
+        for (int i = 0; i < NY; ++i) {
+            const int c = Y.coef[size_t(rr) * NY + i];
+            (c > 0 ? pos : neg) += c;
+        }
+        long long lo = 255 * neg, hi = 255 * pos;
+        if (lo < -32768 || hi > 32767) { r.why = "vertical sum may wrap int16"; return; }
+        const int den = Y.deno[size_t(rr)];
+        if (den != 0) {
+            if (den < 0 || den > 255) { r.why = "border denominator out of range"; return; }
+            lo = lo * 64 / den - 1;
+            hi = hi * 64 / den + 1;
+        }
+        wmin = std::min(wmin, lo);
+        wmax = std::max(wmax, hi);
+    }
+    r.workBias = int(-wmin);
+    if (wmax + r.workBias > 65535) { r.why = "intermediate range too wide"; return; }
+    r.rowRec.assign(size_t(Y.D) * 8, 0);
+    for (int64_t y = 0; y < Y.D; ++y) {
+        const int32_t *c = &Y.coef[size_t(Y.row[size_t(y)]) * NY];
+        const int f = Y.first[size_t(y)];
+        int lo = -1, hi = -1;
+        for (int i = 0; i < NY; ++i)
+            if (c[i] != 0) {
+                const int row = f + i;
+                if (row < 0 || row >= Y.S) { r.why = "vertical tap outside the image with non-zero weight"; return; }
+                if (lo < 0) lo = row;
+                hi = row;
+            }
+        int32_t *rec = &r.rowRec[size_t(y) * 8];
+        if (lo < 0) { rec[0] = 0; rec[1] = 0; continue; }  // all-zero row (cannot happen: the sum is the bias)
+        const int g0 = lo / 4, g1 = hi / 4;
+        if (g1 - g0 + 1 > 4) { r.why = "vertical kernel spans more than four 4-row groups"; return; }
+        rec[0] = g0;
+        rec[1] = g1 - g0 + 1;
+        for (int i = 0; i < NY; ++i)
+            if (c[i] != 0) {
+                const int pos = f + i - 4 * g0;
+                rec[2 + (pos >> 2)] |= int32_t((uint32_t(c[i]) & 0xffu) << (8 * (pos & 3)));
+            }
+        const int den = Y.deno[size_t(Y.row[size_t(y)])];
+        rec[6] = den;
+        rec[7] = den > 1 ? int32_t(uint32_t((1ull << 32) / uint64_t(den) + 1)) : 0;
+    }
+
+    // ---- horizontal pair words: natural pairs (2m, 2m+1); parity = first tap on an odd W element ----
+    r.cwX.assign(size_t(r.RD) * 2 * 6, 0);
+    for (int ph = 0; ph < r.RD; ++ph) {
+        const int32_t *c = &X.coef[size_t(ph) * NX];
+        for (int par = 0; par < 2; ++par)
+            for (int j = 0; j < 6; ++j) {
+                const int ta = 2 * j - par, tb = 2 * j + 1 - par;  // taps in the low / high half of word j
+                r.cwX[(size_t(ph) * 2 + par) * 6 + j] =
+                    pairWord(ta >= 0 && ta < NX ? c[ta] : 0, tb >= 0 && tb < NX ? c[tb] : 0);
+            }
+    }
+    long long sumX = 0;
+    for (int i = 0; i < NX; ++i) sumX += X.coef[i];
+    for (int ph = 1; ph < r.RD; ++ph) {
+        long long s2 = 0;
+        for (int i = 0; i < NX; ++i) s2 += X.coef[size_t(ph) * NX + i];
+        if (s2 != sumX) { r.why = "phase tables with different sums"; return; }
+    }
+    r.accInit = int((1ll << (p.shift - 1)) - (long long)r.workBias * sumX);
+    r.eligible = true;
+}
+
+}  // namespace iqo_b200

@@ -164,3 +164,28 @@ struct SmallPlan {
 void buildSmallPlan(const Plan &plan, SmallPlan &s);
 
 }  // namespace iqo_b200
+
+namespace iqo_b200 {
+
+// Lanczos at a rational ratio whose destination period divides 8 (3:2, 1:2, 3:4 ...) with a horizontal
+// kernel of at most 10 taps whose first tap sits on an even offset (kernels.cu: resizeRatioStreamKernel).
+// A warp walks down a column strip like the 2:1 streaming kernel; the vertical pass is driven by
+// one record per destination row, the horizontal pass by the compile-time tap pattern of 8 pixels.
+struct RatioPlan {
+    bool eligible;
+    std::string why;
+    int RS, RD, NX;              // gcd-reduced horizontal ratio, horizontal taps
+    int GS;                      // source columns per group of 8 destination pixels (8 RS / RD)
+    int c0;                      // first[0] on X (destination pixel 8G + p starts at GS*G + floor(p RS / RD) + c0)
+    int groupsPerStrip;          // 8-pixel groups per warp strip
+    int workBias;
+    // vertical: per destination row {first 4-row group, groups (<= 4), 4 packed s8 words, denominator, magic}
+    std::vector<int32_t> rowRec; // [DH][8]
+    // horizontal: [phase (RD)][parity (2)][6] pair words, bytes (lo_a, lo_b, hi_a, hi_b)
+    std::vector<uint32_t> cwX;
+    int accInit;
+};
+
+void buildRatioPlan(const Plan &plan, RatioPlan &r);
+
+}  // namespace iqo_b200

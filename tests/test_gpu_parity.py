@@ -252,6 +252,49 @@ def test_half_kernel(case, path):
     assert bad.size == 0, (len(bad), bad[:8].tolist())
 
 
+RATIO_CASES = [
+    # (degree, pxScale, srcW, srcH, dstW, dstH, srcPad, dstPad, expected kernel)
+    (3, 1, 1920, 1080, 1280, 720, 0, 0, "ratio_stream"),   # cfg1
+    (3, 1, 96, 60, 64, 40, 0, 0, "ratio_stream"),          # one narrow strip holding both border sides
+    (3, 1, 528, 333, 352, 222, 8, 8, "ratio_stream"),      # three strips (the last one partial), padded rows
+    (2, 1, 480, 270, 320, 180, 0, 0, "ratio_stream"),      # Lanczos2 at 3:2 (6 taps)
+    (3, 1, 320, 180, 640, 360, 0, 0, "ratio_stream"),      # Lanczos3 2x up-sampling
+    (3, 1, 384, 216, 512, 288, 0, 0, "ratio_stream"),      # Lanczos3 3:4 up-sampling
+    (3, 1, 1920, 1080, 1280, 540, 0, 0, "ratio_stream"),   # 3:2 on X, 2:1 on Y
+    (3, 1, 480, 270, 320, 180, 0, 4, "ratio_stream"),      # destination stride not a multiple of 8: byte stores
+    (3, 1, 480, 270, 320, 180, 4, 0, "ratio_stream"),      # host rows are staged with an aligned pitch
+    (3, 1, 492, 270, 328, 180, 0, 0, "packed"),            # source width not a multiple of 8
+]
+
+
+@pytest.mark.parametrize("case", RATIO_CASES)
+def test_ratio_stream_kernel(case):
+    deg, px, sw, sh, dw, dh, spad, dpad, kname = case
+    src = lcg_image(sh, sw + spad, seed=23)
+    rc, want = oracle_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+    assert rc == 0
+    got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+    assert kernel == kname
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, (len(bad), bad[:8].tolist())
+
+
+def test_ratio_stream_batch_and_extremes():
+    torch = pytest.importorskip("torch")
+    sw, sh, dw, dh, n = 960, 540, 640, 360, 5
+    host = np.stack([lcg_image(sh, sw, seed=70 + f) for f in range(n)])
+    host[3] = 255
+    host[4] = ((np.indices((sh, sw)).sum(0) & 1) * 255).astype(np.uint8)
+    want = np.stack([oracle_resize(LANCZOS, host[f], dw, dh, 3)[1] for f in range(n)])
+    dsrc = torch.from_numpy(host).cuda()
+    ddst = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
+    with iqo.LanczosResizer(3, sw, sh, dw, dh) as r:
+        r.resize_batch(n, sw, sw * sh, dsrc, dw, dw * dh, ddst, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert r.last_kernel() == "ratio_stream"
+    assert np.array_equal(ddst.cpu().numpy(), want)
+
+
 def test_half_kernel_extreme_values():
     # all-255 / all-0 / checkerboards maximise the intermediate range (bias and pair-sum headroom)
     sw, sh = 480, 272

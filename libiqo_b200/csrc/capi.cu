@@ -954,7 +954,9 @@ int iqo_cuda_plan_kernel(int kind, unsigned degree, size_t srcW, size_t srcH, si
     if (kernel && kernelCap)
         snprintf(kernel, kernelCap, "%s", sm.eligible ? "half_small" : h.eligible ? (h.symmetric ? "half_sym" : "half") : area2 ? "area2"
                                           : linup ? (kx == 2 ? "linear_up2" : "linear_up3") : ratio ? "ratio_stream" : q.eligible ? "packed" : "generic");
-    if (why && whyCap) snprintf(why, whyCap, "%s%s%s", h.why.c_str(), q.eligible ? "" : "; packed: ", q.eligible ? "" : q.why.c_str());
+    if (why && whyCap)
+        snprintf(why, whyCap, "%s%s%s%s%s", h.why.c_str(), rt.eligible ? "" : "; ratio: ", rt.eligible ? "" : rt.why.c_str(),
+                 q.eligible ? "" : "; packed: ", q.eligible ? "" : q.why.c_str());
     return IQO_CUDA_OK;
 }
 

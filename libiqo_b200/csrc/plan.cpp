@@ -822,22 +822,33 @@ void buildRatioPlan(const Plan &p, RatioPlan &r)
     }
     r.workBias = int(-wmin);
     if (wmax + r.workBias > 65535) { r.why = "intermediate range too wide"; return; }
-    r.rowRec.assign(size_t(Y.D) * 8, 0);
+    // first / last source row with a non-zero weight, per destination row
+    std::vector<int> rlo(size_t(Y.D), 0), rhi(size_t(Y.D), -1);
     for (int64_t y = 0; y < Y.D; ++y) {
         const int32_t *c = &Y.coef[size_t(Y.row[size_t(y)]) * NY];
         const int f = Y.first[size_t(y)];
-        int lo = -1, hi = -1;
+        bool any = false;
         for (int i = 0; i < NY; ++i)
             if (c[i] != 0) {
                 const int row = f + i;
                 if (row < 0 || row >= Y.S) { r.why = "vertical tap outside the image with non-zero weight"; return; }
-                if (lo < 0) lo = row;
-                hi = row;
+                if (!any) rlo[size_t(y)] = row;
+                rhi[size_t(y)] = row;
+                any = true;
             }
-        int32_t *rec = &r.rowRec[size_t(y) * 8];
-        if (lo < 0) { rec[0] = 0; rec[1] = 0; continue; }  // all-zero row (cannot happen: the sum is the bias)
-        const int g0 = lo / 4, g1 = hi / 4;
+        if (!any) { r.why = "all-zero vertical row"; return; }
+    }
+    // the kernel parks source groups in order: the first group of a row may not lie before that of an
+    // earlier row (phases whose leading coefficients are zero would otherwise step back)
+    r.rowRec.assign(size_t(Y.D) * 8, 0);
+    int gmin = 1 << 30;
+    for (int64_t y = Y.D - 1; y >= 0; --y) {
+        gmin = std::min(gmin, rlo[size_t(y)] / 4);
+        const int g0 = gmin, g1 = rhi[size_t(y)] / 4;
         if (g1 - g0 + 1 > 4) { r.why = "vertical kernel spans more than four 4-row groups"; return; }
+        const int32_t *c = &Y.coef[size_t(Y.row[size_t(y)]) * NY];
+        const int f = Y.first[size_t(y)];
+        int32_t *rec = &r.rowRec[size_t(y) * 8];
         rec[0] = g0;
         rec[1] = g1 - g0 + 1;
         for (int i = 0; i < NY; ++i)

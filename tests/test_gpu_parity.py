@@ -279,6 +279,31 @@ def test_ratio_stream_kernel(case):
     assert bad.size == 0, (len(bad), bad[:8].tolist())
 
 
+def test_ratio_stream_sweep():
+    """X ratios the kernel is built for, arbitrary Y ratios (the vertical pass is record driven) and heights
+    that end bands and 8-row turns at odd places."""
+    rng = np.random.RandomState(5)
+    cases = 0
+    for (rs, rd, deg) in ((3, 2, 3), (3, 2, 2), (1, 2, 3), (3, 4, 3)):
+        for _ in range(5):
+            k = int(rng.randint(1, 12)) * 8
+            sw, dw = rs * k, rd * k
+            if dw < 8 or sw < 16:
+                continue
+            sh = int(rng.randint(24, 400))
+            dh = int(rng.randint(max(8, sh // 3), min(2 * sh, 600)))
+            src = lcg_image(sh, sw, seed=int(rng.randint(1, 1000)))
+            rc, want = oracle_resize(LANCZOS, src, dw, dh, deg)
+            if rc != 0:
+                continue
+            got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg)
+            if iqo.plan_kernel(LANCZOS, deg, sw, sh, dw, dh, 1)[0] == "ratio_stream":
+                assert kernel == "ratio_stream"
+                cases += 1
+            assert np.array_equal(got, want), (rs, rd, deg, sw, sh, dw, dh, kernel)
+    assert cases >= 8
+
+
 def test_ratio_stream_batch_and_extremes():
     torch = pytest.importorskip("torch")
     sw, sh, dw, dh, n = 960, 540, 640, 360, 5

@@ -1601,7 +1601,8 @@ __global__ void __launch_bounds__(128) resizeHalfSmallKernel(const __grid_consta
 // ---------------------------------------------------------------------------------------
 constexpr int kRatioRing = 8;                                   // transposed groups per lane
 constexpr int kRatioRingBytes = kRatioRing * 32 * 32;           // [slot][half A/B][lane][16 bytes]
-constexpr int kRatioSmem = kRatioRingBytes + 8 * kStreamRowBytes;
+constexpr int kRatioRecBytes = 2 * 8 * 32;                      // row records of two turns
+constexpr int kRatioSmem = kRatioRingBytes + 8 * kStreamRowBytes + kRatioRecBytes;
 
 template <int RS, int RD, int NX>
 __global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_constant__ RatioArgs a)
@@ -1665,16 +1666,25 @@ __global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_c
     const uint32_t rcp = (65536u + ngs - 1) / ngs;
     const bool left = tx0 < a.mbX, right = tx0 + 8 * ngs > a.meX;
 
-    // the record of the next row is loaded one row ahead
-    int4 n0 = __ldg(reinterpret_cast<const int4 *>(a.rowRec + 8 * y0));
-    int4 n1 = __ldg(reinterpret_cast<const int4 *>(a.rowRec + 8 * y0 + 4));
+    // The 8 row records of a turn (256 bytes) are staged in shared memory one turn ahead: lanes 0..15
+    // each carry 16 bytes of the next turn's records in a register while the current turn runs.
+    const uint32_t recBase = wBase + 8 * kStreamRowBytes;
+    const int recMax = 8 * a.DH - 4;  // last 16-byte piece of the table
+    auto recLoad = [&](int yTurn) -> int4 {
+        const int w = min(8 * yTurn + 4 * (lane & 15), recMax);
+        return __ldg(reinterpret_cast<const int4 *>(a.rowRec + w));
+    };
+    {
+        const int4 cur = recLoad(y0);
+        if (lane < 16) stsV4<0>(recBase + 16 * lane, make_uint4(cur.x, cur.y, cur.z, cur.w));
+        __syncwarp();
+    }
+    int4 recNext = recLoad(y0 + 8);
+    uint32_t recCur = recBase;  // records of the running turn
     for (int y = y0; y < y1; ++y) {
-        const int4 r0 = n0, r1 = n1;
-        {
-            const int yn = min(y + 1, a.DH - 1);
-            n0 = __ldg(reinterpret_cast<const int4 *>(a.rowRec + 8 * yn));
-            n1 = __ldg(reinterpret_cast<const int4 *>(a.rowRec + 8 * yn + 4));
-        }
+        const uint32_t ra = recCur + 32 * ((y - y0) & 7);
+        const uint4 u0 = ldsV4<0>(ra), u1 = ldsV4<16>(ra);
+        const int4 r0 = make_int4(u0.x, u0.y, u0.z, u0.w), r1 = make_int4(u1.x, u1.y, u1.z, u1.w);
         const int g0 = r0.x, ng = r0.y;
         while (gNext < g0 + ng) {  // uniform
             park(gNext);
@@ -1787,7 +1797,11 @@ __global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_c
                 }
             }
         }
-        __syncwarp();  // the W rows are free again
+        // next turn's records: register -> the other half of the record buffer, then fetch the turn after
+        recCur = recBase + (recCur == recBase ? 256 : 0);
+        if (lane < 16) stsV4<0>(recCur + 16 * lane, make_uint4(recNext.x, recNext.y, recNext.z, recNext.w));
+        recNext = recLoad(y + 9);
+        __syncwarp();  // the W rows are free again, the records are visible
     }
 }
 

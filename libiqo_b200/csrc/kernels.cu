@@ -1697,22 +1697,37 @@ __global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_c
         int v[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) v[i] = init;
+        // straight-line code per group count: all ring loads go out before the first dp4a
+        auto rowSum = [&](auto ngTag) {
+            constexpr int NGc = decltype(ngTag)::value;
+            uint4 qa[NGc], qb[NGc];
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-            if (t < ng) {
-                const uint32_t c = (uint32_t)(t == 0 ? r0.z : t == 1 ? r0.w : t == 2 ? r1.x : r1.y);
+            for (int t = 0; t < NGc; ++t) {
                 const uint32_t sa = ringBase + ((g0 + t) & (kRatioRing - 1)) * 1024;
-                const uint4 qa = ldsV4<0>(sa), qb = ldsV4<512>(sa);
-                v[0] = dp4a_us(qa.x, c, v[0]);
-                v[1] = dp4a_us(qa.y, c, v[1]);
-                v[2] = dp4a_us(qa.z, c, v[2]);
-                v[3] = dp4a_us(qa.w, c, v[3]);
-                v[4] = dp4a_us(qb.x, c, v[4]);
-                v[5] = dp4a_us(qb.y, c, v[5]);
-                v[6] = dp4a_us(qb.z, c, v[6]);
-                v[7] = dp4a_us(qb.w, c, v[7]);
+                qa[t] = ldsV4<0>(sa);
+                qb[t] = ldsV4<512>(sa);
             }
-        }
+#pragma unroll
+            for (int t = 0; t < NGc; ++t) {
+                const uint32_t c = (uint32_t)(t == 0 ? r0.z : t == 1 ? r0.w : t == 2 ? r1.x : r1.y);
+                v[0] = dp4a_us(qa[t].x, c, v[0]);
+                v[1] = dp4a_us(qa[t].y, c, v[1]);
+                v[2] = dp4a_us(qa[t].z, c, v[2]);
+                v[3] = dp4a_us(qa[t].w, c, v[3]);
+                v[4] = dp4a_us(qb[t].x, c, v[4]);
+                v[5] = dp4a_us(qb[t].y, c, v[5]);
+                v[6] = dp4a_us(qb[t].z, c, v[6]);
+                v[7] = dp4a_us(qb[t].w, c, v[7]);
+            }
+        };
+        if (ng == 3)
+            rowSum(std::integral_constant<int, 3>());
+        else if (ng == 2)
+            rowSum(std::integral_constant<int, 2>());
+        else if (ng == 4)
+            rowSum(std::integral_constant<int, 4>());
+        else
+            rowSum(std::integral_constant<int, 1>());
         if (deno) {
             // resizeYborder: see halfVerticalStrip
             auto bdiv = [&](int x) -> int {

@@ -60,8 +60,8 @@ enum {
     IQO_CUDA_PATH_NO_TMA = 2,  /* like NO_STREAM, but the tiled 2:1 Lanczos kernel reads the source
                                   with plain global loads instead of TMA (what AUTO itself does
                                   when the source pitch or base is not 8/16-byte aligned)          */
-    IQO_CUDA_PATH_NO_STREAM = 3 /* like AUTO, but 2:1 Lanczos uses the tiled (TMA) kernel instead of
-                                  the warp-streaming one                                           */
+    IQO_CUDA_PATH_NO_STREAM = 3 /* like AUTO, but without the warp-streaming kernels: 2:1 Lanczos uses
+                                  the tiled (TMA) kernel, other rational ratios the general one    */
 };
 
 /* Replaces: I{Lanczos,Area,Linear}ResizerImpl::init (reference src/IQOLanczosResizerImpl.hpp:17-22,

@@ -355,9 +355,9 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         const int boxRows = 4 * (h.tileRows / 2 + hp.NG - 1);
         const bool tmaOk = r->useTma && encodeTiled() != 0 && boxRows <= halfSourceRowsMax() &&
                            ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 && (nFrames == 1 || srcFrameStride % 16 == 0);
-        // streaming variant (a warp per column strip and row band): 8-byte aligned source rows
-        const bool streamOk = r->useStream && hp.sEligible && h.SW % 8 == 0 && ((uintptr_t)src % 8) == 0 && srcSt % 8 == 0 &&
-                              srcFrameStride % 8 == 0;
+        // streaming variant (a warp per column strip and row band): source rows are copied as aligned 16-byte chunks
+        const bool streamOk = r->useStream && hp.sEligible && h.SW % 8 == 0 && ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 &&
+                              (nFrames == 1 || srcFrameStride % 16 == 0);
         if (streamOk) {
             // bands: enough warps to fill the device several times over, but long enough that the
             // ring refill and the re-read halo rows of a band stay small

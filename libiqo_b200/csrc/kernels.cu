@@ -732,7 +732,7 @@ __device__ __forceinline__ uint2 halfGroupPixelsOdd(const HalfArgs &a, const uin
 //   borders     border rows: masked coefficient words + truncating division, in the turns that
 //               touch them.  Border columns: the few W words they need are parked in a side
 //               buffer and recomputed for 32 rows at a time by the whole warp.
-// Needs 8-byte aligned source rows and a source width that is a multiple of 8.
+// Needs 16-byte aligned source rows and a source width that is a multiple of 8.
 template <bool B>
 struct BoolTag {
     static constexpr bool value = B;

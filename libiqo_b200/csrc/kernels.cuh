@@ -82,7 +82,7 @@ struct HalfArgs {
 cudaError_t launchHalf(const HalfArgs &a, const CUtensorMap *tmap, int boxRows, cudaStream_t stream);
 int halfSourceRowsMax();
 // Streaming variant: a warp per (120-pixel column strip, band of a.bandPairs row pairs, frame).
-// Needs 8-byte aligned source rows and SW % 8 == 0; at most 65535 frames and bands per launch.
+// Needs 16-byte aligned source rows and SW % 8 == 0; at most 65535 frames and bands per launch.
 cudaError_t launchHalfStream(const HalfArgs &a, cudaStream_t stream);
 bool halfStreamHasKernel(int NG, int NXH);
 

@@ -230,7 +230,7 @@ def half_variant(kname, path, sw):
     """Name of the 2:1 Lanczos kernel a host image (staged with a 16-byte aligned pitch) runs on."""
     if kname not in ("half", "half_sym"):
         return kname
-    if path == iqo.PATH_AUTO and sw % 8 == 0:
+    if path == iqo.PATH_AUTO and sw % 8 == 0 and sw // 2 >= 32:
         return kname + "_stream"     # a warp per column strip: needs whole 8-column words
     if path in (iqo.PATH_AUTO, iqo.PATH_NO_STREAM):
         return kname + "_tma"        # tiled kernel, source window staged by TMA
@@ -277,6 +277,14 @@ def test_ratio_stream_kernel(case):
     assert kernel == kname
     bad = np.argwhere(got != want)
     assert bad.size == 0, (len(bad), bad[:8].tolist())
+
+
+def test_ratio_stream_can_be_switched_off():
+    src = lcg_image(270, 480, seed=3)
+    rc, want = oracle_resize(LANCZOS, src, 320, 180, 3)
+    got, kernel = gpu_resize(LANCZOS, src, 320, 180, 3, path=iqo.PATH_NO_STREAM)
+    assert kernel == "packed"
+    assert np.array_equal(got, want)
 
 
 def test_ratio_stream_sweep():
@@ -347,13 +355,14 @@ def test_half_kernel_extreme_values():
 
 
 def test_half_kernel_device_pitches():
-    """Device-resident frames: an 8-byte aligned pitch takes the streaming variant, one that is only
-    4-byte aligned the tiled global-load variant, an odd pitch falls back to the generic kernel;
+    """Device-resident frames: a 16-byte aligned pitch takes the streaming variant, one that is only
+    8- or 4-byte aligned the tiled global-load variant, an odd pitch falls back to the generic kernel;
     without the streaming variant a 16-byte aligned pitch takes the TMA variant."""
     torch = pytest.importorskip("torch")
     sw, sh, dw, dh, n = 488, 250, 244, 125, 3
     for pitch, path, expect in ((496, iqo.PATH_AUTO, "half_sym_stream"), (496, iqo.PATH_NO_STREAM, "half_sym_tma"),
-                                (504, iqo.PATH_NO_STREAM, "half_sym"), (492, iqo.PATH_AUTO, "half_sym"),
+                                (504, iqo.PATH_NO_STREAM, "half_sym"), (504, iqo.PATH_AUTO, "half_sym"),
+                                (492, iqo.PATH_AUTO, "half_sym"),
                                 (489, iqo.PATH_AUTO, "generic")):
         host = np.stack([lcg_image(sh, pitch, seed=40 + f) for f in range(n)])
         want = np.stack([oracle_resize(LANCZOS, host[f], dw, dh, 3, sw=sw)[1] for f in range(n)])

@@ -1331,70 +1331,93 @@ struct LinearUpArgs {
     uint32_t rcpWords;         // ceil(2^32 / wordsPerRow)
     const int32_t *firstY, *rowY, *coefY;   // generic vertical tables (two taps per row)
     uint32_t cwX[3];           // per phase: bytes (lo(q0), lo(q1), hi(q0), hi(q1))
+    int q1X[3];                // per phase: weight of the right column (the left one is 32768 - q1)
 };
+
+constexpr int kLinearUpRows = 4;  // destination rows per item: they mostly share their two source rows
 
 template <int K>
 __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constant__ LinearUpArgs a)
 {
-    // item = (destination row, source word), flattened so that rows whose word count is not a
-    // multiple of the block size do not leave threads idle
+    // item = (group of kLinearUpRows destination rows, source word), flattened so that rows whose word
+    // count is not a multiple of the block size do not leave threads idle
     const uint32_t item = blockIdx.x * 256u + threadIdx.x;
-    const int y = (a.wordsPerRow == 1) ? (int)item : (int)__umulhi(item, a.rcpWords);
-    const int j = (int)item - y * a.wordsPerRow;
-    if (y >= a.DH) return;
+    const int grp = (a.wordsPerRow == 1) ? (int)item : (int)__umulhi(item, a.rcpWords);
+    const int j = (int)item - grp * a.wordsPerRow;
+    const int y0 = grp * kLinearUpRows;
+    if (y0 >= a.DH) return;
     const uint8_t *__restrict__ src = a.src + (long long)blockIdx.y * a.srcFrameStride;
-    uint8_t *__restrict__ out = a.dst + (long long)blockIdx.y * a.dstFrameStride + (long long)y * a.dstPitch + 4 * K * j;
-
-    // vertical taps of this destination row (uniform over the block)
-    const int fy = __ldg(a.firstY + y);
-    const int ry = __ldg(a.rowY + y);
-    const uint32_t q0 = (uint32_t)__ldg(a.coefY + 2 * ry), q1 = (uint32_t)__ldg(a.coefY + 2 * ry + 1);
-    const int r0 = min(max(fy, 0), a.SH - 1), r1 = min(max(fy + 1, 0), a.SH - 1);
-    const uint32_t *row0 = reinterpret_cast<const uint32_t *>(src + (long long)r0 * a.srcPitch);
-    const uint32_t *row1 = reinterpret_cast<const uint32_t *>(src + (long long)r1 * a.srcPitch);
+    uint8_t *__restrict__ out = a.dst + (long long)blockIdx.y * a.dstFrameStride + (long long)y0 * a.dstPitch + 4 * K * j;
     const int jm = max(j - 1, 0), jp = min(j + 1, a.wordsPerRow - 1);
-    const uint32_t am = __ldg(row0 + jm), a0 = __ldg(row0 + j), ap = __ldg(row0 + jp);
-    const uint32_t bm = __ldg(row1 + jm), b0 = __ldg(row1 + j), bp = __ldg(row1 + jp);
 
-    // pair words (col 4j-1+n, col 4j+n) for n = 0..4 as two 16-bit lanes, vertically blended
-    const uint32_t ua = __funnelshift_r(am, a0, 24), ub = __funnelshift_r(bm, b0, 24);  // columns 4j-1 .. 4j+2
-    const uint32_t va = __funnelshift_r(a0, ap, 24), vb = __funnelshift_r(b0, bp, 24);  // columns 4j+3 .. 4j+6
-    uint32_t P[5];
-    P[0] = prmt(ua, 0u, 0x4140) * q0 + prmt(ub, 0u, 0x4140) * q1;
-    P[1] = prmt(a0, 0u, 0x4140) * q0 + prmt(b0, 0u, 0x4140) * q1;
-    P[2] = prmt(a0, 0u, 0x4241) * q0 + prmt(b0, 0u, 0x4241) * q1;
-    P[3] = prmt(a0, 0u, 0x4342) * q0 + prmt(b0, 0u, 0x4342) * q1;
-    P[4] = prmt(va, 0u, 0x4140) * q0 + prmt(vb, 0u, 0x4140) * q1;
-
-    uint32_t packed[K];
+    // pair words (col 4j-1+n, col 4j+n) for n = 0..4 as two 16-bit lanes, of the two source rows in use
+    uint32_t A[5], Bv[5];
+    int have = -(1 << 30);
 #pragma unroll
-    for (int quad = 0; quad < K; ++quad) {
-        int v[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const int i = 4 * quad + e;
-            // g(i) + 1 = floor((2 i + 1 + K) / (2 K))
-            const int n = (2 * i + 1 + K) / (2 * K);
-            const uint32_t cw = a.cwX[i % K];
-            int acc = 1 << 22;
-            acc = dp2a_lo_uu(P[n], cw, acc);
-            acc >>= 8;
-            acc = dp2a_hi_uu(P[n], cw, acc);
-            v[e] = acc >> 15;
+    for (int r = 0; r < kLinearUpRows; ++r) {
+        const int y = y0 + r;
+        if (y >= a.DH) break;
+        // vertical taps of this destination row (uniform over the rows of a block)
+        const int fy = __ldg(a.firstY + y);
+        const int ry = __ldg(a.rowY + y);
+        const uint32_t q0 = (uint32_t)__ldg(a.coefY + 2 * ry), q1 = (uint32_t)__ldg(a.coefY + 2 * ry + 1);
+        if (fy != have) {
+            have = fy;
+            const int r0 = min(max(fy, 0), a.SH - 1), r1 = min(max(fy + 1, 0), a.SH - 1);
+            const uint32_t *row0 = reinterpret_cast<const uint32_t *>(src + (long long)r0 * a.srcPitch);
+            const uint32_t *row1 = reinterpret_cast<const uint32_t *>(src + (long long)r1 * a.srcPitch);
+            const uint32_t am = __ldg(row0 + jm), a0 = __ldg(row0 + j), ap = __ldg(row0 + jp);
+            const uint32_t bm = __ldg(row1 + jm), b0 = __ldg(row1 + j), bp = __ldg(row1 + jp);
+            const uint32_t ua = __funnelshift_r(am, a0, 24), ub = __funnelshift_r(bm, b0, 24);  // columns 4j-1 .. 4j+2
+            const uint32_t va = __funnelshift_r(a0, ap, 24), vb = __funnelshift_r(b0, bp, 24);  // columns 4j+3 .. 4j+6
+            A[0] = prmt(ua, 0u, 0x4140), Bv[0] = prmt(ub, 0u, 0x4140);
+            A[1] = prmt(a0, 0u, 0x4140), Bv[1] = prmt(b0, 0u, 0x4140);
+            A[2] = prmt(a0, 0u, 0x4241), Bv[2] = prmt(b0, 0u, 0x4241);
+            A[3] = prmt(a0, 0u, 0x4342), Bv[3] = prmt(b0, 0u, 0x4342);
+            A[4] = prmt(va, 0u, 0x4140), Bv[4] = prmt(vb, 0u, 0x4140);
         }
-        packed[quad] = packSatU8(v[1], v[0], packSatU8(v[3], v[2], 0u));
-    }
-    // replicated edge columns
-    if (j == 0) {
-        const int v = (int)((P[1] & 0xffffu) + 128u) >> 8;
-        packed[0] = (packed[0] & 0xffffff00u) | (uint32_t)min(v, 255);
-    }
-    if (j == a.wordsPerRow - 1) {
-        const int v = (int)((P[4] & 0xffffu) + 128u) >> 8;  // low lane of the last pair = column S-1
-        packed[K - 1] = (packed[K - 1] & 0x00ffffffu) | ((uint32_t)min(v, 255) << 24);
-    }
+        // vertical blend (two IMAD per pair; <= 255 * 256 per lane, no carry)
+        // horizontal: the two weights of a phase sum to 32768, so
+        //   lo * q0 + hi * q1 + 2^22 == (lo << 15) + 2^22 + (hi - lo) * q1        (one IMAD per pixel);
+        // the result of a convex blend needs no saturation.
+        uint32_t P1 = 0, P4 = 0;
+        uint32_t baseN[5];
+        int diffN[5];
 #pragma unroll
-    for (int quad = 0; quad < K; ++quad) *reinterpret_cast<uint32_t *>(out + 4 * quad) = packed[quad];
+        for (int n = 0; n < 5; ++n) {
+            const uint32_t P = A[n] * q0 + Bv[n] * q1;
+            if (n == 1) P1 = P;
+            if (n == 4) P4 = P;
+            const uint32_t lo = P & 0xffffu, hi = P >> 16;
+            baseN[n] = lo * 32768u + (1u << 22);
+            diffN[n] = (int)hi - (int)lo;
+        }
+        uint32_t packed[K];
+#pragma unroll
+        for (int quad = 0; quad < K; ++quad) {
+            uint32_t v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = 4 * quad + e;
+                // g(i) + 1 = floor((2 i + 1 + K) / (2 K))
+                const int n = (2 * i + 1 + K) / (2 * K);
+                v[e] = (baseN[n] + (uint32_t)(diffN[n] * a.q1X[i % K])) >> 23;
+            }
+            packed[quad] = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+        }
+        // replicated edge columns
+        if (j == 0) {
+            const int v = (int)((P1 & 0xffffu) + 128u) >> 8;
+            packed[0] = (packed[0] & 0xffffff00u) | (uint32_t)min(v, 255);
+        }
+        if (j == a.wordsPerRow - 1) {
+            const int v = (int)((P4 & 0xffffu) + 128u) >> 8;  // low lane of the last pair = column S-1
+            packed[K - 1] = (packed[K - 1] & 0x00ffffffu) | ((uint32_t)min(v, 255) << 24);
+        }
+        uint8_t *o = out + (long long)r * a.dstPitch;
+#pragma unroll
+        for (int quad = 0; quad < K; ++quad) *reinterpret_cast<uint32_t *>(o + 4 * quad) = packed[quad];
+    }
 }
 
 
@@ -2050,9 +2073,12 @@ cudaError_t launchLinearUp(int K, const uint8_t *src, uint8_t *dst, long long sr
     a.firstY = firstY;
     a.rowY = rowY;
     a.coefY = coefY;
-    for (int i = 0; i < 3; ++i) a.cwX[i] = cwX[i];
+    for (int i = 0; i < 3; ++i) {
+        a.cwX[i] = cwX[i];
+        a.q1X[i] = int(((cwX[i] >> 8) & 0xffu) | ((cwX[i] >> 24) << 8));  // low and high byte plane of the second weight
+    }
     a.rcpWords = (uint32_t)((0x100000000ull + a.wordsPerRow - 1) / a.wordsPerRow);
-    const long long items = (long long)a.wordsPerRow * DH;
+    const long long items = (long long)a.wordsPerRow * ((DH + kLinearUpRows - 1) / kLinearUpRows);
     if (items >= (1ll << 31)) return cudaErrorInvalidConfiguration;
     dim3 grid((unsigned)((items + 255) / 256), nFrames);
     if (K == 2)

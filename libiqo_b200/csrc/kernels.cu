@@ -1334,7 +1334,7 @@ struct LinearUpArgs {
     int q1X[3];                // per phase: weight of the right column (the left one is 32768 - q1)
 };
 
-constexpr int kLinearUpRows = 4;  // destination rows per item: they mostly share their two source rows
+constexpr int kLinearUpRows = 6;  // destination rows per item: they mostly share their two source rows
 
 template <int K>
 __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constant__ LinearUpArgs a)

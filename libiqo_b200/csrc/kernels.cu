@@ -1613,7 +1613,7 @@ __global__ void __launch_bounds__(128) resizeHalfSmallKernel(const __grid_consta
 // walks down a column strip, dp4a vertical pass, dp2a horizontal pass on 8 pixels per lane --
 // but table-driven where the 2:1 kernel is hard-wired:
 //   vertical    a lane owns 8 source columns.  Every new group of four source rows is transposed
-//               once (2 x 8 PRMT) and parked in a lane-private ring of 8 groups in shared memory;
+//               once (2 x 8 PRMT) and parked in a lane-private ring of 4 groups in shared memory;
 //               a destination row reads the <= 4 groups its record names (2 LDS.128 + 8 dp4a each,
 //               coefficient words from the per-row record, so phases and border rows need no code).
 //   horizontal  every 8 destination rows: lane = (row, group of 8 pixels).  Pixel p of a group starts
@@ -1622,7 +1622,7 @@ __global__ void __launch_bounds__(128) resizeHalfSmallKernel(const __grid_consta
 //   borders     border rows: masked words + multiply-high division from the record; border columns
 //               are recomputed per pixel from the generic tables.
 // ---------------------------------------------------------------------------------------
-constexpr int kRatioRing = 8;                                   // transposed groups per lane
+constexpr int kRatioRing = 4;                                   // transposed groups per lane
 constexpr int kRatioRingBytes = kRatioRing * 32 * 32;           // [slot][half A/B][lane][16 bytes]
 constexpr int kRatioRecBytes = 2 * 8 * 32;                      // row records of two turns
 constexpr int kRatioSmem = kRatioRingBytes + 8 * kStreamRowBytes + kRatioRecBytes;

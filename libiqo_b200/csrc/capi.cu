@@ -468,6 +468,7 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         q.RS = rp.RS;
         q.RD = rp.RD;
         q.NX = rp.NX;
+        q.tailZeros = rp.tailZeros;
         q.groupsPerStrip = rp.groupsPerStrip;
         q.c0 = rp.c0;
         q.workBias = rp.workBias;

@@ -1627,7 +1627,7 @@ constexpr int kRatioRingBytes = kRatioRing * 32 * 32;           // [slot][half A
 constexpr int kRatioRecBytes = 2 * 8 * 32;                      // row records of two turns
 constexpr int kRatioSmem = kRatioRingBytes + 8 * kStreamRowBytes + kRatioRecBytes;
 
-template <int RS, int RD, int NX>
+template <int RS, int RD, int NX, int TZ>
 __global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_constant__ RatioArgs a)
 {
     extern __shared__ __align__(16) uint8_t ratioSmem[];
@@ -1778,16 +1778,23 @@ __global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_c
             const int r = (int)(((uint32_t)item * rcp) >> 16);
             const int q = item - r * ngs;
             const uint32_t wl = wBase + r * kStreamRowBytes + 2 * (i0 + GS * q);
-            constexpr int kWords = ((7 * RS / RD) >> 1) + NX / 2 + 1;  // pair words the 8 pixels span (at most)
+            constexpr int NXE = NX - TZ;  // taps left after the zero taps that end every phase
+            constexpr int kWords = (((7 * RS / RD) >> 1) + (NXE + 2) / 2 + 1) & ~1;  // pair words the 8 pixels span (even count)
             uint32_t n[kWords];
+            if ((wl & 7) == 0) {  // uniform: 8-byte aligned rows of words
 #pragma unroll
-            for (int j = 0; j < kWords; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(n[j]) : "r"(wl + 4 * j) : "memory");
+                for (int j = 0; j < kWords; j += 2)
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(n[j]), "=r"(n[j + 1]) : "r"(wl + 4 * j) : "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < kWords; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(n[j]) : "r"(wl + 4 * j) : "memory");
+            }
             int px[8];
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
                 const int off = (p * RS) / RD;
                 const int wp = off >> 1, par = off & 1, ph = p % RD;
-                const int nw = NX / 2 + par;
+                const int nw = (NXE + par + 1) / 2;
                 int acc = a.accInit;
 #pragma unroll
                 for (int j = 0; j < nw; ++j) acc = dp2a_lo_uu(n[wp + j], a.cwX[ph][par][j], acc);
@@ -1843,12 +1850,12 @@ __global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_c
     }
 }
 
-template <int RS, int RD, int NX>
+template <int RS, int RD, int NX, int TZ>
 cudaError_t launchRatioT(const RatioArgs &a, cudaStream_t stream)
 {
     const int strip = 8 * a.groupsPerStrip;
     dim3 grid((a.DW + strip - 1) / strip, (a.DH + a.bandRows - 1) / a.bandRows, a.nFrames);
-    resizeRatioStreamKernel<RS, RD, NX><<<grid, 32, kRatioSmem, stream>>>(a);
+    resizeRatioStreamKernel<RS, RD, NX, TZ><<<grid, 32, kRatioSmem, stream>>>(a);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -1958,10 +1965,10 @@ bool ratioHasKernel(int RS, int RD, int NX)
 
 cudaError_t launchRatio(const RatioArgs &a, cudaStream_t stream)
 {
-    if (a.RS == 3 && a.RD == 2 && a.NX == 10) return launchRatioT<3, 2, 10>(a, stream);
-    if (a.RS == 3 && a.RD == 2 && a.NX == 6) return launchRatioT<3, 2, 6>(a, stream);
-    if (a.RS == 1 && a.RD == 2 && a.NX == 6) return launchRatioT<1, 2, 6>(a, stream);
-    if (a.RS == 3 && a.RD == 4 && a.NX == 6) return launchRatioT<3, 4, 6>(a, stream);
+    if (a.RS == 3 && a.RD == 2 && a.NX == 10) return a.tailZeros ? launchRatioT<3, 2, 10, 1>(a, stream) : launchRatioT<3, 2, 10, 0>(a, stream);
+    if (a.RS == 3 && a.RD == 2 && a.NX == 6) return launchRatioT<3, 2, 6, 0>(a, stream);
+    if (a.RS == 1 && a.RD == 2 && a.NX == 6) return launchRatioT<1, 2, 6, 0>(a, stream);
+    if (a.RS == 3 && a.RD == 4 && a.NX == 6) return launchRatioT<3, 4, 6, 0>(a, stream);
     return cudaErrorInvalidValue;
 }
 

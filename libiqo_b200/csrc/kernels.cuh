@@ -156,6 +156,7 @@ struct RatioArgs {
     int SW, SH, DW, DH;
     int nFrames;
     int RS, RD, NX;
+    int tailZeros;             // the last tap of every phase is zero (the kernel skips it)
     int bandRows;              // destination rows per warp (multiple of 8)
     int groupsPerStrip, c0;
     int workBias, accInit;

@@ -880,6 +880,9 @@ void buildRatioPlan(const Plan &p, RatioPlan &r)
         if (s2 != sumX) { r.why = "phase tables with different sums"; return; }
     }
     r.accInit = int((1ll << (p.shift - 1)) - (long long)r.workBias * sumX);
+    r.tailZeros = 1;
+    for (int ph = 0; ph < r.RD; ++ph)
+        if (X.coef[size_t(ph) * NX + NX - 1] != 0) r.tailZeros = 0;
     r.eligible = true;
 }
 

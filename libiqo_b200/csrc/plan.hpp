@@ -175,6 +175,7 @@ struct RatioPlan {
     bool eligible;
     std::string why;
     int RS, RD, NX;              // gcd-reduced horizontal ratio, horizontal taps
+    int tailZeros;               // 1 when the last tap of every phase (border rows included) is zero
     int GS;                      // source columns per group of 8 destination pixels (8 RS / RD)
     int c0;                      // first[0] on X (destination pixel 8G + p starts at GS*G + floor(p RS / RD) + c0)
     int groupsPerStrip;          // 8-pixel groups per warp strip

@@ -1167,9 +1167,11 @@ __global__ void __launch_bounds__(256) resizePackedKernel(const __grid_constant_
 
     // ================= vertical pass: item = (row, 8 adjacent source columns) =================
     {
-        const uint32_t rcp = (65536u + ncd - 1) / ncd;  // items < 32 * 2^9: exact floor division
+        // floor(item / ncd) as a multiply-high by ceil(2^32 / ncd): exact for item < 2^32 / ncd
+        // (a 16-bit reciprocal is not: wide source windows of strong down-sampling broke it)
+        const uint32_t rcp = (uint32_t)((0x100000000ull + (uint32_t)ncd - 1) / (uint32_t)ncd);
         for (int item = threadIdx.x; item < th * ncd; item += blockDim.x) {
-            const int r = (int)(((uint32_t)item * rcp) >> 16);
+            const int r = ncd == 1 ? item : (int)__umulhi((uint32_t)item, rcp);
             const int cd = item - r * ncd;
             const int col = x0 + 8 * cd;
             const bool ok1 = ((col >> 2) + 1) < swWords;  // the second word still holds image bytes

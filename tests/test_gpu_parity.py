@@ -279,6 +279,17 @@ def test_ratio_stream_kernel(case):
     assert bad.size == 0, (len(bad), bad[:8].tolist())
 
 
+def test_packed_kernel_wide_source_window():
+    """Strong horizontal down-sampling: a 128-pixel tile spans the whole 566-column source row (71 eight-column
+    units per row of the vertical pass; found by the randomized fuzz, the row/unit split used a 16-bit reciprocal)."""
+    src = lcg_image(434, 582, seed=9)
+    rc, want = oracle_resize(LANCZOS, src, 115, 392, 1, 1, sw=566)
+    assert rc == 0
+    got, kernel = gpu_resize(LANCZOS, src, 115, 392, 1, 1, sw=566)
+    assert kernel == "packed"
+    assert np.array_equal(got, want)
+
+
 def test_ratio_stream_can_be_switched_off():
     src = lcg_image(270, 480, seed=3)
     rc, want = oracle_resize(LANCZOS, src, 320, 180, 3)

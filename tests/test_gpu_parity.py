@@ -406,7 +406,7 @@ def oracle_yuv420(kind, deg, frame, sw, sh, dw, dh):
     sx, sy, ssy, ssu = yuv_layout(sw, sh)
     dx, dy, dsy, dsu = yuv_layout(dw, dh)
     out = np.zeros(dsy + 2 * dsu, dtype=np.uint8)
-    rc, y = oracle_resize(kind, frame[:ssy].reshape(sy, sx), dw, dh, deg, 1, sw=sw, dst_stride=dx)
+    rc, y = oracle_resize(kind, frame[:ssy].reshape(sy, sx)[:sh], dw, dh, deg, 1, sw=sw, dst_stride=dx)
     assert rc == 0
     out[:dh * dx] = y.ravel()
     for p in range(2):

@@ -478,7 +478,8 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         memset(q.cwX, 0, sizeof q.cwX);
         for (int ph = 0; ph < rp.RD && ph < 4; ++ph)
             for (int par = 0; par < 2; ++par)
-                for (int j = 0; j < 6; ++j) q.cwX[ph][par][j] = rp.cwX[(size_t(ph) * 2 + par) * 6 + j];
+                for (int j = 0; j < 7; ++j) q.cwX[ph][par][j] = rp.cwX[(size_t(ph) * 2 + par) * 7 + j];
+        q.odd = rp.odd;
         q.mbX = int(r->plan.x.mainBegin);
         q.meX = int(r->plan.x.mainEnd);
         q.gx = a.x;
@@ -658,7 +659,7 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
         sp->small.eligible = false;
     }
     buildRatioPlan(sp->plan, sp->ratio);
-    if (sp->ratio.eligible && (!ratioHasKernel(sp->ratio.RS, sp->ratio.RD, sp->ratio.NX) || !uploadVec(sp->rRowRec, sp->ratio.rowRec))) {
+    if (sp->ratio.eligible && (!ratioHasKernel(sp->ratio.RS, sp->ratio.RD, sp->ratio.NX, sp->ratio.odd) || !uploadVec(sp->rRowRec, sp->ratio.rowRec))) {
         cudaGetLastError();
         sp->ratio.eligible = false;
     }
@@ -948,7 +949,7 @@ int iqo_cuda_plan_kernel(int kind, unsigned degree, size_t srcW, size_t srcH, si
     buildSmallPlan(p, sm);
     RatioPlan rt;
     buildRatioPlan(p, rt);
-    const bool ratio = rt.eligible && ratioHasKernel(rt.RS, rt.RD, rt.NX);
+    const bool ratio = rt.eligible && ratioHasKernel(rt.RS, rt.RD, rt.NX, rt.odd);
     const bool area2 = p.kind == kArea && p.x.rD == 1 && p.x.rS == 2 && p.y.rD == 1 && p.y.rS == 2 && p.x.N == 2 && p.y.N == 2 && p.x.S % 16 == 0;
     const long long kx = (p.x.D % p.x.S == 0) ? p.x.D / p.x.S : 0;
     const bool linup = p.kind == kLinear && (kx == 2 || kx == 3) && p.x.S % 4 == 0 && !p.y.identity;

@@ -1629,7 +1629,7 @@ constexpr int kRatioRingBytes = kRatioRing * 32 * 32;           // [slot][half A
 constexpr int kRatioRecBytes = 2 * 8 * 32;                      // row records of two turns
 constexpr int kRatioSmem = kRatioRingBytes + 8 * kStreamRowBytes + kRatioRecBytes;
 
-template <int RS, int RD, int NX, int TZ>
+template <int RS, int RD, int NX, int TZ, bool ODD>
 __global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_constant__ RatioArgs a)
 {
     extern __shared__ __align__(16) uint8_t ratioSmem[];
@@ -1642,8 +1642,9 @@ __global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_c
     uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
     const int ngs = min(a.groupsPerStrip, (a.DW - tx0) >> 3);   // 8-pixel groups of this strip
     const int first0 = GS * (tx0 >> 3) + a.c0;                  // first tap of pixel tx0
-    const int xs0 = first0 & ~7;                                 // source column of W element 0 (may be negative)
-    const int i0 = first0 - xs0;                                 // even
+    const int xs0 = first0 & ~7;                                 // first source column of lane 0 (may be negative)
+    // W element i is source column xs0 + i (ODD: xs0 + i - 1, so that the first tap sits on an even element)
+    const int i0 = first0 - xs0 + (ODD ? 1 : 0);
     const uint32_t ringBase = smemAddr(ratioSmem) + 16 * lane;
     const uint32_t wBase = smemAddr(ratioSmem) + kRatioRingBytes;
     const int B = a.workBias;
@@ -1765,10 +1766,19 @@ __global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_c
             for (int i = 0; i < 8; ++i) v[i] = bdiv(v[i]);
         }
         uint4 o;
-        o.x = prmt((uint32_t)v[0], (uint32_t)v[1], 0x5410);
-        o.y = prmt((uint32_t)v[2], (uint32_t)v[3], 0x5410);
-        o.z = prmt((uint32_t)v[4], (uint32_t)v[5], 0x5410);
-        o.w = prmt((uint32_t)v[6], (uint32_t)v[7], 0x5410);
+        if (ODD) {
+            // pair words (column 2m-1, column 2m): the lane's last column travels to its right neighbour
+            const uint32_t prev = __shfl_up_sync(0xffffffffu, (uint32_t)v[7], 1);
+            o.x = prmt(prev, (uint32_t)v[0], 0x5410);
+            o.y = prmt((uint32_t)v[1], (uint32_t)v[2], 0x5410);
+            o.z = prmt((uint32_t)v[3], (uint32_t)v[4], 0x5410);
+            o.w = prmt((uint32_t)v[5], (uint32_t)v[6], 0x5410);
+        } else {
+            o.x = prmt((uint32_t)v[0], (uint32_t)v[1], 0x5410);
+            o.y = prmt((uint32_t)v[2], (uint32_t)v[3], 0x5410);
+            o.z = prmt((uint32_t)v[4], (uint32_t)v[5], 0x5410);
+            o.w = prmt((uint32_t)v[6], (uint32_t)v[7], 0x5410);
+        }
         const int slot = (y - y0) & 7;
         stsV4<0>(wBase + slot * kStreamRowBytes + 16 * lane, o);
         if (slot != 7 && y != y1 - 1) continue;
@@ -1832,7 +1842,7 @@ __global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_c
                     const int r = item / nb, d = b0 + item - r * nb;
                     const int fx = __ldg(a.gx.first + d), rx = __ldg(a.gx.row + d);
                     const int32_t *cx = a.gx.coef + rx * NX;
-                    const uint32_t wr = wBase + r * kStreamRowBytes + 2 * (fx - xs0);
+                    const uint32_t wr = wBase + r * kStreamRowBytes + 2 * (fx - xs0 + (ODD ? 1 : 0));
                     int nume = 0;
 #pragma unroll
                     for (int i = 0; i < NX; ++i) {
@@ -1852,12 +1862,12 @@ __global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_c
     }
 }
 
-template <int RS, int RD, int NX, int TZ>
+template <int RS, int RD, int NX, int TZ, bool ODD>
 cudaError_t launchRatioT(const RatioArgs &a, cudaStream_t stream)
 {
     const int strip = 8 * a.groupsPerStrip;
     dim3 grid((a.DW + strip - 1) / strip, (a.DH + a.bandRows - 1) / a.bandRows, a.nFrames);
-    resizeRatioStreamKernel<RS, RD, NX, TZ><<<grid, 32, kRatioSmem, stream>>>(a);
+    resizeRatioStreamKernel<RS, RD, NX, TZ, ODD><<<grid, 32, kRatioSmem, stream>>>(a);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -1960,17 +1970,26 @@ cudaError_t launchHalfStream(const HalfArgs &a, cudaStream_t stream)
     return cudaErrorInvalidValue;
 }
 
-bool ratioHasKernel(int RS, int RD, int NX)
+// instantiated (RS, RD, NX) triples; the parity of the first tap follows from NX (NX / 2 odd: even)
+bool ratioHasKernel(int RS, int RD, int NX, int odd)
 {
-    return (RS == 3 && RD == 2 && (NX == 10 || NX == 6)) || (RS == 1 && RD == 2 && NX == 6) || (RS == 3 && RD == 4 && NX == 6);
+    if (odd != (((NX / 2) & 1) ? 0 : 1)) return false;
+    return (RS == 3 && RD == 2 && (NX == 10 || NX == 6 || NX == 12)) || (RS == 1 && RD == 2 && (NX == 6 || NX == 4)) ||
+           (RS == 3 && RD == 4 && NX == 6) || (RS == 2 && RD == 1 && (NX == 12 || NX == 8 || NX == 4));
 }
 
 cudaError_t launchRatio(const RatioArgs &a, cudaStream_t stream)
 {
-    if (a.RS == 3 && a.RD == 2 && a.NX == 10) return a.tailZeros ? launchRatioT<3, 2, 10, 1>(a, stream) : launchRatioT<3, 2, 10, 0>(a, stream);
-    if (a.RS == 3 && a.RD == 2 && a.NX == 6) return launchRatioT<3, 2, 6, 0>(a, stream);
-    if (a.RS == 1 && a.RD == 2 && a.NX == 6) return launchRatioT<1, 2, 6, 0>(a, stream);
-    if (a.RS == 3 && a.RD == 4 && a.NX == 6) return launchRatioT<3, 4, 6, 0>(a, stream);
+    if (a.RS == 3 && a.RD == 2 && a.NX == 10)
+        return a.tailZeros ? launchRatioT<3, 2, 10, 1, false>(a, stream) : launchRatioT<3, 2, 10, 0, false>(a, stream);
+    if (a.RS == 3 && a.RD == 2 && a.NX == 6) return launchRatioT<3, 2, 6, 0, false>(a, stream);
+    if (a.RS == 3 && a.RD == 2 && a.NX == 12) return launchRatioT<3, 2, 12, 0, true>(a, stream);
+    if (a.RS == 1 && a.RD == 2 && a.NX == 6) return launchRatioT<1, 2, 6, 0, false>(a, stream);
+    if (a.RS == 1 && a.RD == 2 && a.NX == 4) return launchRatioT<1, 2, 4, 0, true>(a, stream);
+    if (a.RS == 3 && a.RD == 4 && a.NX == 6) return launchRatioT<3, 4, 6, 0, false>(a, stream);
+    if (a.RS == 2 && a.RD == 1 && a.NX == 12) return launchRatioT<2, 1, 12, 0, true>(a, stream);
+    if (a.RS == 2 && a.RD == 1 && a.NX == 8) return launchRatioT<2, 1, 8, 0, true>(a, stream);
+    if (a.RS == 2 && a.RD == 1 && a.NX == 4) return launchRatioT<2, 1, 4, 0, true>(a, stream);
     return cudaErrorInvalidValue;
 }
 

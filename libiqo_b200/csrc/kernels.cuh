@@ -162,11 +162,12 @@ struct RatioArgs {
     int workBias, accInit;
     int dstVec;                // destination rows may be written with 8-byte stores
     const int32_t *rowRec;     // [DH][8]
-    uint32_t cwX[4][2][6];     // [phase][parity][pair word]
+    uint32_t cwX[4][2][7];     // [phase][parity][pair word]
+    int odd;                   // W pairs are columns (2m-1, 2m): first[0] is odd
     int mbX, meX;
     AxisDev gx, gy;            // generic tables: border columns are recomputed from them
 };
-bool ratioHasKernel(int RS, int RD, int NX);
+bool ratioHasKernel(int RS, int RD, int NX, int odd);
 cudaError_t launchRatio(const RatioArgs &a, cudaStream_t stream);
 
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D);

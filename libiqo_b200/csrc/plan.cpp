@@ -781,7 +781,7 @@ void buildRatioPlan(const Plan &p, RatioPlan &r)
     if (X.rD > 8 || 8 % X.rD != 0) { r.why = "horizontal period does not divide 8"; return; }
     if (X.D % 8 != 0 || X.S % 8 != 0) { r.why = "widths not multiples of 8"; return; }
     const int NX = X.N, NY = Y.N;
-    if (NX > 10 || (NX & 1)) { r.why = "horizontal kernel longer than 10 taps"; return; }
+    if (NX > 12 || (NX & 1)) { r.why = "horizontal kernel longer than 12 taps"; return; }
     if (Y.coefMin < -128 || Y.coefMax > 127) { r.why = "vertical coefficients do not fit int8"; return; }
     r.RS = int(X.rS);
     r.RD = int(X.rD);
@@ -789,15 +789,18 @@ void buildRatioPlan(const Plan &p, RatioPlan &r)
     r.GS = int(8 * X.rS / X.rD);
     if (r.GS & 1) { r.why = "odd source span per 8 pixels"; return; }
     r.c0 = X.first[0];
-    if (r.c0 & 1) { r.why = "first tap on an odd column"; return; }
+    r.odd = r.c0 & 1;
     // the compile-time tap pattern must hold for every destination column
     for (int64_t d = 0; d < X.D; ++d) {
         const int64_t G = d / 8, q = d % 8;
         if (X.first[size_t(d)] != r.GS * G + (q * X.rS) / X.rD + r.c0) { r.why = "first-tap pattern is not periodic in 8"; return; }
         if (d >= X.mainBegin && d < X.mainEnd && X.row[size_t(d)] != d % X.rD) { r.why = "unexpected coefficient row"; return; }
     }
+    // the last tap of the strip's last pixel must lie inside the 256 columns (255 with the one-column shift) of a warp
     const int i0 = ((r.c0 % 8) + 8) % 8;
-    r.groupsPerStrip = std::min(32, (256 - NX + 1 - i0) / r.GS);
+    const int off7 = int((7 * X.rS) / X.rD);
+    r.groupsPerStrip = std::min(32, (255 - r.odd - i0 - off7 - (NX - 1)) / r.GS + 1);
+    if (r.groupsPerStrip < 1) { r.why = "source window wider than a warp strip"; return; }
     while (r.groupsPerStrip > 1 && (r.GS * r.groupsPerStrip) % 8 != 0) --r.groupsPerStrip;  // strips start on whole 8-column words
     if ((r.GS * r.groupsPerStrip) % 8 != 0) { r.why = "no strip width keeps the source window 8-byte aligned"; return; }
 
@@ -862,13 +865,13 @@ void buildRatioPlan(const Plan &p, RatioPlan &r)
     }
 
     // ---- horizontal pair words: natural pairs (2m, 2m+1); parity = first tap on an odd W element ----
-    r.cwX.assign(size_t(r.RD) * 2 * 6, 0);
+    r.cwX.assign(size_t(r.RD) * 2 * 7, 0);
     for (int ph = 0; ph < r.RD; ++ph) {
         const int32_t *c = &X.coef[size_t(ph) * NX];
         for (int par = 0; par < 2; ++par)
-            for (int j = 0; j < 6; ++j) {
+            for (int j = 0; j < 7; ++j) {
                 const int ta = 2 * j - par, tb = 2 * j + 1 - par;  // taps in the low / high half of word j
-                r.cwX[(size_t(ph) * 2 + par) * 6 + j] =
+                r.cwX[(size_t(ph) * 2 + par) * 7 + j] =
                     pairWord(ta >= 0 && ta < NX ? c[ta] : 0, tb >= 0 && tb < NX ? c[tb] : 0);
             }
     }

@@ -176,13 +176,14 @@ struct RatioPlan {
     std::string why;
     int RS, RD, NX;              // gcd-reduced horizontal ratio, horizontal taps
     int tailZeros;               // 1 when the last tap of every phase (border rows included) is zero
+    int odd;                     // first[0] is odd: the kernel pairs columns (2m-1, 2m) instead of (2m, 2m+1)
     int GS;                      // source columns per group of 8 destination pixels (8 RS / RD)
     int c0;                      // first[0] on X (destination pixel 8G + p starts at GS*G + floor(p RS / RD) + c0)
     int groupsPerStrip;          // 8-pixel groups per warp strip
     int workBias;
     // vertical: per destination row {first 4-row group, groups (<= 4), 4 packed s8 words, denominator, magic}
     std::vector<int32_t> rowRec; // [DH][8]
-    // horizontal: [phase (RD)][parity (2)][6] pair words, bytes (lo_a, lo_b, hi_a, hi_b)
+    // horizontal: [phase (RD)][parity (2)][7] pair words, bytes (lo_a, lo_b, hi_a, hi_b)
     std::vector<uint32_t> cwX;
     int accInit;
 };

@@ -262,6 +262,10 @@ RATIO_CASES = [
     (3, 1, 384, 216, 512, 288, 0, 0, "ratio_stream"),      # Lanczos3 3:4 up-sampling
     (3, 1, 1920, 1080, 1280, 540, 0, 0, "ratio_stream"),   # 3:2 on X, 2:1 on Y
     (3, 1, 480, 270, 320, 180, 0, 4, "ratio_stream"),      # destination stride not a multiple of 8: byte stores
+    (3, 1, 1920, 1080, 960, 720, 0, 0, "ratio_stream"),    # 2:1 on X only (12 taps, first tap on an odd column)
+    (2, 1, 960, 540, 480, 333, 0, 0, "ratio_stream"),      # Lanczos2, 2:1 on X, arbitrary Y
+    (2, 1, 320, 180, 640, 360, 0, 0, "ratio_stream"),      # Lanczos2 2x up-sampling (4 taps, odd first column)
+    (4, 1, 960, 540, 640, 360, 0, 0, "ratio_stream"),      # Lanczos4 at 3:2 (12 taps)
     (3, 1, 480, 270, 320, 180, 4, 0, "ratio_stream"),      # host rows are staged with an aligned pitch
     (3, 1, 492, 270, 328, 180, 0, 0, "packed"),            # source width not a multiple of 8
 ]
@@ -303,7 +307,7 @@ def test_ratio_stream_sweep():
     that end bands and 8-row turns at odd places."""
     rng = np.random.RandomState(5)
     cases = 0
-    for (rs, rd, deg) in ((3, 2, 3), (3, 2, 2), (1, 2, 3), (3, 4, 3)):
+    for (rs, rd, deg) in ((3, 2, 3), (3, 2, 2), (1, 2, 3), (3, 4, 3), (2, 1, 3), (2, 1, 2), (1, 2, 2), (3, 2, 4)):
         for _ in range(5):
             k = int(rng.randint(1, 12)) * 8
             sw, dw = rs * k, rd * k
@@ -320,7 +324,7 @@ def test_ratio_stream_sweep():
                 assert kernel == "ratio_stream"
                 cases += 1
             assert np.array_equal(got, want), (rs, rd, deg, sw, sh, dw, dh, kernel)
-    assert cases >= 8
+    assert cases >= 16
 
 
 def test_ratio_stream_batch_and_extremes():

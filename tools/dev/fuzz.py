@@ -41,11 +41,11 @@ while time.time() - t0 < budget:
         dw, dh = int(rng.randint(2, 400)) * 2, int(rng.randint(8, 300))
         run(LANCZOS, int(rng.choice([1, 2, 3, 4])), int(rng.choice([1, 1, 2])), 2 * dw, 2 * dh, dw, dh, pad(), pad())
     elif fam == 1:    # ratio kernel families
-        rs, rd = [(3, 2), (1, 2), (3, 4)][rng.randint(0, 3)]
+        rs, rd = [(3, 2), (1, 2), (3, 4), (2, 1)][rng.randint(0, 4)]
         k = int(rng.randint(1, 60)) * 8
         sh = int(rng.randint(16, 500))
         dh = int(rng.randint(max(8, sh // 3), 2 * sh))
-        run(LANCZOS, int(rng.choice([2, 3])), 1, rs * k, sh, rd * k, dh, pad(), pad())
+        run(LANCZOS, int(rng.choice([1, 2, 3, 4])), 1, rs * k, sh, rd * k, dh, pad(), pad())
     elif fam == 2:    # linear up-sampling
         kx = int(rng.choice([2, 3]))
         sw, sh = int(rng.randint(2, 200)) * 4, int(rng.randint(4, 200))

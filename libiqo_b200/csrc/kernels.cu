@@ -1974,7 +1974,7 @@ cudaError_t launchHalfStream(const HalfArgs &a, cudaStream_t stream)
 bool ratioHasKernel(int RS, int RD, int NX, int odd)
 {
     if (odd != (((NX / 2) & 1) ? 0 : 1)) return false;
-    return (RS == 3 && RD == 2 && (NX == 10 || NX == 6 || NX == 12)) || (RS == 1 && RD == 2 && (NX == 6 || NX == 4)) ||
+    return (RS == 3 && RD == 2 && (NX == 10 || NX == 6 || NX == 12 || NX == 4)) || (RS == 1 && RD == 2 && (NX == 6 || NX == 4)) ||
            (RS == 3 && RD == 4 && NX == 6) || (RS == 2 && RD == 1 && (NX == 12 || NX == 8 || NX == 4));
 }
 
@@ -1984,6 +1984,7 @@ cudaError_t launchRatio(const RatioArgs &a, cudaStream_t stream)
         return a.tailZeros ? launchRatioT<3, 2, 10, 1, false>(a, stream) : launchRatioT<3, 2, 10, 0, false>(a, stream);
     if (a.RS == 3 && a.RD == 2 && a.NX == 6) return launchRatioT<3, 2, 6, 0, false>(a, stream);
     if (a.RS == 3 && a.RD == 2 && a.NX == 12) return launchRatioT<3, 2, 12, 0, true>(a, stream);
+    if (a.RS == 3 && a.RD == 2 && a.NX == 4) return launchRatioT<3, 2, 4, 0, true>(a, stream);
     if (a.RS == 1 && a.RD == 2 && a.NX == 6) return launchRatioT<1, 2, 6, 0, false>(a, stream);
     if (a.RS == 1 && a.RD == 2 && a.NX == 4) return launchRatioT<1, 2, 4, 0, true>(a, stream);
     if (a.RS == 3 && a.RD == 4 && a.NX == 6) return launchRatioT<3, 4, 6, 0, false>(a, stream);

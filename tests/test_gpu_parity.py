@@ -266,6 +266,7 @@ RATIO_CASES = [
     (2, 1, 960, 540, 480, 333, 0, 0, "ratio_stream"),      # Lanczos2, 2:1 on X, arbitrary Y
     (2, 1, 320, 180, 640, 360, 0, 0, "ratio_stream"),      # Lanczos2 2x up-sampling (4 taps, odd first column)
     (4, 1, 960, 540, 640, 360, 0, 0, "ratio_stream"),      # Lanczos4 at 3:2 (12 taps)
+    (3, 2, 960, 540, 640, 360, 0, 0, "ratio_stream"),      # chroma plane of a 1080p -> 720p YUV420 frame (4 taps)
     (3, 1, 480, 270, 320, 180, 4, 0, "ratio_stream"),      # host rows are staged with an aligned pitch
     (3, 1, 492, 270, 328, 180, 0, 0, "packed"),            # source width not a multiple of 8
 ]

@@ -718,20 +718,23 @@ __device__ __forceinline__ uint2 halfGroupPixelsOdd(const HalfArgs &a, const uin
 }
 
 // ---- variant 3: warp-autonomous streaming ----
-// A warp owns one 120-pixel column strip of one frame and walks down a band of destination row
-// pairs on its own: no CTA-wide barrier, no per-tile prologue, and the register ring of
-// transposed source groups lives for the whole band instead of being refilled per tile.
-//   source      a lane owns 8 adjacent source columns.  Its 8 bytes of each source row travel
-//               global -> shared with cp.async into a private FIFO (one turn = NG groups of four
-//               rows deep), so the loads of the next three row pairs are always in flight and
-//               cost no registers; nobody else reads a lane's FIFO, so no barrier is needed.
-//   vertical    2 x (4x4 byte transposes) per group, 8 x NG dp4a per destination row, one
-//               16-byte store per row into the warp's private double-buffered W rows;
+// A warp (one per CTA) owns one 120-pixel column strip of one frame and walks down a band of
+// destination row pairs on its own: no CTA-wide barrier, no per-tile prologue, and the register
+// ring of transposed source groups lives for the whole band instead of being refilled per tile.
+//   source      the 272 bytes of a source row that cover the strip's 256-byte window travel
+//               global -> shared as 17 aligned 16-byte cp.async.cg chunks (lanes 0..16; L1 is bypassed,
+//               chunks outside the image are zero-filled without a read).  Four rows form a group;
+//               the FIFO holds two turns of groups, so the loads of the next row pairs are always
+//               in flight and cost no registers.  (A variant fed by one cp.async.bulk.tensor per
+//               group was measured 5 % slower -- 2.64 vs 2.52 ms for cfg4 -- and dropped.)
+//   vertical    a lane owns 8 adjacent source columns: 2 x (4x4 byte transposes) per group,
+//               8 x NG dp4a per destination row, one 16-byte store per row into the warp's W rows;
+//               the loop runs in turns of NG row pairs (compile-time ring, FIFO and W positions);
 //   horizontal  after one __syncwarp: lane = (row of the pair, 8-pixel group), 30 of 32 lanes
-//               busy, same pre-added dp2a planes as the tiled variants (halfGroup).
+//               busy, pre-added dp2a planes on odd-aligned pair words (halfGroupPixelsOdd).
 //   borders     border rows: masked coefficient words + truncating division, in the turns that
-//               touch them.  Border columns: the few W words they need are parked in a side
-//               buffer and recomputed for 32 rows at a time by the whole warp.
+//               touch them.  Border columns: the few W chunks they read are parked in a side
+//               buffer and recomputed for up to 16 rows at a time, a lane per row.
 // Needs 16-byte aligned source rows and a source width that is a multiple of 8.
 template <bool B>
 struct BoolTag {

@@ -34,6 +34,8 @@ WORKLOADS = {
     "cfg3uv_lanczos2_px2_1080p_to_540p": (0, 2, 2, 1920, 1080, 960, 540, 4096),
     "cfg2a_area_2160p_to_1080p": (1, 0, 1, 3840, 2160, 1920, 1080, 768),
     "cfg2b_linear_720p_to_2160p": (2, 0, 1, 1280, 720, 3840, 2160, 768),
+    # cfg5's ratio (1024:375, Lanczos4, 22 taps, 375 phases) on a size that fits a batch
+    "cfg5s_lanczos4_8192_to_3000": (0, 4, 1, 8192, 8192, 3000, 3000, 16),
 }
 DEFAULT_WORKLOAD = "cfg4_lanczos3_1080p_to_540p"
 METRIC = "dst_mpix_per_s_lanczos3_u8_resize"

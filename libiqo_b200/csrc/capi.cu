@@ -100,6 +100,7 @@ struct SharedPlan {
     HalfPlan half;
     SmallPlan small;
     RatioPlan ratio;
+    LStreamPlan lstream;
     PackedPlan packed;
     GenericGeom geom;
     PackedGeom pgeom;
@@ -111,10 +112,11 @@ struct SharedPlan {
     int32_t *pFirstY, *pNtapY, *pCoefOffY, *pRecX;
     uint32_t *pMagicY, *pCwX;
     int32_t *rRowRec;     // rational-ratio streaming path
+    int32_t *gRowRec;     // general Lanczos streaming path
     int32_t *sRowsY;      // small-kernel path
     uint32_t *sMagicY;
     SharedPlan()
-        : device(0), dBorderY(0), dMagicY(0), dSBorderY(0), dBorderX(0), dBorderXo(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), rRowRec(0), sRowsY(0), sMagicY(0)
+        : device(0), dBorderY(0), dMagicY(0), dSBorderY(0), dBorderX(0), dBorderXo(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), rRowRec(0), gRowRec(0), sRowsY(0), sMagicY(0)
     {
     }
     ~SharedPlan();
@@ -202,6 +204,7 @@ SharedPlan::~SharedPlan()
     cudaFree(pRecX);
     cudaFree(sRowsY);
     cudaFree(rRowRec);
+    cudaFree(gRowRec);
     cudaFree(sMagicY);
     cudaFree(pMagicY);
     cudaFree(pCwX);
@@ -500,6 +503,40 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
             return IQO_CUDA_OK;
         }
     }
+    // Lanczos at any other ratio, row bands included: general streaming kernel
+    if (r->useStream && sp.lstream.eligible && ((uintptr_t)src % 8) == 0 && srcSt % 8 == 0 && srcFrameStride % 8 == 0) {
+        LStreamArgs q;
+        q.srcPitch = (long long)srcSt;
+        q.dstPitch = (long long)dstSt;
+        q.srcFrameStride = (long long)srcFrameStride;
+        q.dstFrameStride = (long long)dstFrameStride;
+        q.SW = int(r->plan.x.S);
+        q.DW = int(r->plan.x.D);
+        q.srcRow0 = int(srcRow0);
+        q.srcRows = int(srcRows);
+        q.dstRow0 = int(dstRow0);
+        q.dstRows = int(dstRows);
+        q.stripW = sp.lstream.stripW;
+        q.workBias = sp.packed.workBias;
+        q.rowRec = sp.gRowRec;
+        q.recX = reinterpret_cast<const int4 *>(sp.pRecX);
+        q.cwX = sp.pCwX;
+        q.NP = sp.packed.NP;
+        const long long strips = (q.DW + q.stripW - 1) / q.stripW;
+        int bandRows = 256;
+        while (bandRows > 32 && strips * ((q.dstRows + bandRows - 1) / bandRows) * (long long)nFrames < 6ll * 148 * 16) bandRows /= 2;
+        q.bandRows = bandRows;
+        if ((q.dstRows + bandRows - 1) / bandRows <= 65535) {
+            r->lastKernel = "lanczos_stream";
+            for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
+                q.nFrames = int(std::min<size_t>(65535, nFrames - f0));
+                q.src = src + f0 * srcFrameStride;
+                q.dst = dst + f0 * dstFrameStride;
+                CUDA_TRY(launchLStream(q, stream));
+            }
+            return IQO_CUDA_OK;
+        }
+    }
     if (r->path == IQO_CUDA_PATH_AUTO && sp.packed.eligible && ((uintptr_t)src % 4) == 0 && srcSt % 4 == 0 &&
         srcFrameStride % 4 == 0 && dstRows <= size_t(65535) * sp.pgeom.tileH) {
         PackedArgs q;
@@ -673,6 +710,14 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
         } else {
             sp->pgeom = choosePackedGeom(q.firstX.data(), sp->plan.x.N, int(sp->plan.x.S), int(sp->plan.x.D), q.NP, q.ntMax);
             if (sp->pgeom.smemBytes > 150 * 1024) sp->packed.eligible = false;  // extreme down-sampling: generic kernel
+        }
+    }
+    sp->lstream.eligible = false;
+    if (sp->packed.eligible) {
+        buildLStreamPlan(sp->plan, sp->packed, sp->lstream);
+        if (sp->lstream.eligible && (!lstreamHasKernel(sp->packed.NP) || !uploadVec(sp->gRowRec, sp->lstream.rowRec))) {
+            cudaGetLastError();
+            sp->lstream.eligible = false;
         }
     }
     out = sp;
@@ -950,12 +995,16 @@ int iqo_cuda_plan_kernel(int kind, unsigned degree, size_t srcW, size_t srcH, si
     RatioPlan rt;
     buildRatioPlan(p, rt);
     const bool ratio = rt.eligible && ratioHasKernel(rt.RS, rt.RD, rt.NX, rt.odd);
+    LStreamPlan ls;
+    ls.eligible = false;
+    if (q.eligible) buildLStreamPlan(p, q, ls);
+    const bool lstream = ls.eligible && lstreamHasKernel(q.NP);
     const bool area2 = p.kind == kArea && p.x.rD == 1 && p.x.rS == 2 && p.y.rD == 1 && p.y.rS == 2 && p.x.N == 2 && p.y.N == 2 && p.x.S % 16 == 0;
     const long long kx = (p.x.D % p.x.S == 0) ? p.x.D / p.x.S : 0;
     const bool linup = p.kind == kLinear && (kx == 2 || kx == 3) && p.x.S % 4 == 0 && !p.y.identity;
     if (kernel && kernelCap)
         snprintf(kernel, kernelCap, "%s", sm.eligible ? "half_small" : h.eligible ? (h.symmetric ? "half_sym" : "half") : area2 ? "area2"
-                                          : linup ? (kx == 2 ? "linear_up2" : "linear_up3") : ratio ? "ratio_stream" : q.eligible ? "packed" : "generic");
+                                          : linup ? (kx == 2 ? "linear_up2" : "linear_up3") : ratio ? "ratio_stream" : lstream ? "lanczos_stream" : q.eligible ? "packed" : "generic");
     if (why && whyCap)
         snprintf(why, whyCap, "%s%s%s%s%s", h.why.c_str(), rt.eligible ? "" : "; ratio: ", rt.eligible ? "" : rt.why.c_str(),
                  q.eligible ? "" : "; packed: ", q.eligible ? "" : q.why.c_str());

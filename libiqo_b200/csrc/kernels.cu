@@ -1875,6 +1875,187 @@ cudaError_t launchRatioT(const RatioArgs &a, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------
+// General Lanczos streaming kernel (plan.hpp LStreamPlan): any ratio, phase count and row band.
+// The record-driven dp4a vertical pass of resizeRatioStreamKernel (a warp walks down a strip whose
+// source window fits 256 columns; a lane owns 8 source columns; transposed 4-row groups in a
+// lane-private ring of 8) feeds the column-resident horizontal pass of resizePackedKernel: every 8
+// destination rows a lane takes the strip's destination columns lane, lane + 32, ..., loads the
+// column's record and its NPT coefficient pair words once and produces the column's 8 pixels
+// (NPT LDS + 2 NPT dp2a each; Lanczos border columns divide).
+// ---------------------------------------------------------------------------------------
+constexpr int kLStreamRing = 8;
+constexpr int kLStreamSmem = kLStreamRing * 1024 + 8 * kStreamRowBytes + 2 * 8 * 64;
+
+template <int NPT>
+__global__ void __launch_bounds__(32, 12) resizeLanczosStreamKernel(const __grid_constant__ LStreamArgs a)
+{
+    extern __shared__ __align__(16) uint8_t lsSmem[];
+    const int lane = threadIdx.x;
+    const int tx0 = blockIdx.x * a.stripW;
+    const int tw = min(a.stripW, a.DW - tx0);
+    const int y0 = a.dstRow0 + blockIdx.y * a.bandRows;
+    const int y1 = min(y0 + a.bandRows, a.dstRow0 + a.dstRows);
+    const uint8_t *__restrict__ src = a.src + (long long)blockIdx.z * a.srcFrameStride;
+    uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
+    const int x0 = __ldg(&a.recX[tx0].x) & ~7;  // source column of W element 0
+    const uint32_t ringBase = smemAddr(lsSmem) + 16 * lane;
+    const uint32_t wBase = smemAddr(lsSmem) + kLStreamRing * 1024;
+    const uint32_t recBase = wBase + 8 * kStreamRowBytes;
+    const int B = a.workBias;
+    const long long pitch = a.srcPitch;
+    const int rowsM1 = a.srcRows - 1;
+
+    // vertical role: 8 source columns; columns at and beyond the image edge only ever meet zero coefficients
+    const int col = x0 + 8 * lane;
+    const int colMode = col + 8 <= a.SW ? 0 : col < a.SW ? 1 : 2;  // whole word / straddles the edge / outside
+    const uint8_t *base = src + (colMode == 2 ? 0 : col);
+    uint2 raw[4];
+    auto fetch = [&](int g) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int row = min(max(4 * g + j - a.srcRow0, 0), rowsM1);
+            const uint8_t *p = base + (long long)row * pitch;
+            if (colMode != 1) {
+                raw[j] = __ldg(reinterpret_cast<const uint2 *>(p));
+            } else {  // the image ends inside this word: never read past the row
+                uint32_t lo = 0, hi = 0;
+                for (int b = 0; b < 8 && col + b < a.SW; ++b) {
+                    const uint32_t v = __ldg(p + b);
+                    if (b < 4) lo |= v << (8 * b);
+                    else hi |= v << (8 * (b - 4));
+                }
+                raw[j] = make_uint2(lo, hi);
+            }
+        }
+    };
+    auto park = [&](int g) {  // transposed group -> ring slot g mod 8
+        const uint32_t t0 = prmt(raw[0].x, raw[1].x, 0x5140), t1 = prmt(raw[0].x, raw[1].x, 0x7362);
+        const uint32_t t2 = prmt(raw[2].x, raw[3].x, 0x5140), t3 = prmt(raw[2].x, raw[3].x, 0x7362);
+        uint4 ca, cb;
+        ca.x = prmt(t0, t2, 0x5410);
+        ca.y = prmt(t0, t2, 0x7632);
+        ca.z = prmt(t1, t3, 0x5410);
+        ca.w = prmt(t1, t3, 0x7632);
+        const uint32_t u0 = prmt(raw[0].y, raw[1].y, 0x5140), u1 = prmt(raw[0].y, raw[1].y, 0x7362);
+        const uint32_t u2 = prmt(raw[2].y, raw[3].y, 0x5140), u3 = prmt(raw[2].y, raw[3].y, 0x7362);
+        cb.x = prmt(u0, u2, 0x5410);
+        cb.y = prmt(u0, u2, 0x7632);
+        cb.z = prmt(u1, u3, 0x5410);
+        cb.w = prmt(u1, u3, 0x7632);
+        const uint32_t sa = ringBase + (g & (kLStreamRing - 1)) * 1024;
+        stsV4<0>(sa, ca);
+        stsV4<512>(sa, cb);
+    };
+
+    // the 8 row records of a turn (512 bytes) are staged in shared memory one turn ahead (16 bytes per lane)
+    const int recMax = 16 * (a.dstRow0 + a.dstRows) - 4;
+    auto recLoad = [&](int yTurn) -> int4 {
+        const int w = min(16 * yTurn + 4 * lane, recMax);
+        return __ldg(reinterpret_cast<const int4 *>(a.rowRec + w));
+    };
+    {
+        const int4 cur = recLoad(y0);
+        stsV4<0>(recBase + 16 * lane, make_uint4(cur.x, cur.y, cur.z, cur.w));
+        __syncwarp();
+    }
+    int4 recNext = recLoad(y0 + 8);
+    uint32_t recCur = recBase;
+    int gNext = __ldg(a.rowRec + 16 * y0);  // groups are non-decreasing in y
+    fetch(gNext);
+
+    for (int y = y0; y < y1; ++y) {
+        const uint32_t ra = recCur + 64 * ((y - y0) & 7);
+        const uint4 r0 = ldsV4<0>(ra);
+        const int g0 = (int)r0.x, ng = (int)r0.y, deno = (int)r0.z;
+        const uint32_t magic = r0.w;
+        while (gNext < g0 + ng) {  // uniform
+            park(gNext);
+            ++gNext;
+            fetch(gNext);
+        }
+        const int init = deno ? 0 : B;
+        int v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = init;
+        for (int t = 0; t < ng; ++t) {  // uniform
+            uint32_t c;
+            asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(ra + 16 + 4 * t) : "memory");
+            const uint32_t sa = ringBase + ((g0 + t) & (kLStreamRing - 1)) * 1024;
+            const uint4 qa = ldsV4<0>(sa), qb = ldsV4<512>(sa);
+            v[0] = dp4a_us(qa.x, c, v[0]);
+            v[1] = dp4a_us(qa.y, c, v[1]);
+            v[2] = dp4a_us(qa.z, c, v[2]);
+            v[3] = dp4a_us(qa.w, c, v[3]);
+            v[4] = dp4a_us(qb.x, c, v[4]);
+            v[5] = dp4a_us(qb.y, c, v[5]);
+            v[6] = dp4a_us(qb.z, c, v[6]);
+            v[7] = dp4a_us(qb.w, c, v[7]);
+        }
+        if (deno) {
+            // resizeYborder: see halfVerticalStrip
+            auto bdiv = [&](int x) -> int {
+                const int n = (int)(short)x * 64;
+                const uint32_t m = (uint32_t)abs(n);
+                const int q = magic ? (int)__umulhi(m, magic) : (int)m;
+                return (int)(short)(n < 0 ? -q : q) + B;
+            };
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = bdiv(v[i]);
+        }
+        uint4 o;
+        o.x = prmt((uint32_t)v[0], (uint32_t)v[1], 0x5410);
+        o.y = prmt((uint32_t)v[2], (uint32_t)v[3], 0x5410);
+        o.z = prmt((uint32_t)v[4], (uint32_t)v[5], 0x5410);
+        o.w = prmt((uint32_t)v[6], (uint32_t)v[7], 0x5410);
+        const int slot = (y - y0) & 7;
+        stsV4<0>(wBase + slot * kStreamRowBytes + 16 * lane, o);
+        if (slot != 7 && y != y1 - 1) continue;
+
+        // ---- horizontal pass of the parked rows: a lane per destination column ----
+        __syncwarp();
+        const int nr = slot + 1, yt = y - slot;
+        for (int dx = lane; dx < tw; dx += 32) {
+            const int4 rec = __ldg(a.recX + tx0 + dx);  // {first column, coefficient word offset, accumulator init, divisor}
+            uint32_t cw[NPT];
+#pragma unroll
+            for (int j = 0; j < NPT; ++j) cw[j] = __ldg(a.cwX + rec.y + j);
+            uint32_t wp = wBase + 4 * ((rec.x - x0) >> 1);
+            uint8_t *out = dst + (long long)(yt - a.dstRow0) * a.dstPitch + tx0 + dx;
+            for (int r = 0; r < nr; ++r, wp += kStreamRowBytes, out += a.dstPitch) {
+                int lo = rec.z, hi = 0;
+#pragma unroll
+                for (int j = 0; j < NPT; ++j) {
+                    uint32_t w;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(wp + 4 * j) : "memory");
+                    lo = dp2a_lo_uu(w, cw[j], lo);
+                    hi = dp2a_hi_us(w, cw[j], hi);
+                }
+                const int total = lo + (hi << 8);
+                int px = total >> 20;
+                if (rec.w != 0) px = total / rec.w;  // resizeXborder: truncating division by deno * 64
+                px = (int)(short)px;
+                *out = (uint8_t)min(max(px, 0), 255);
+            }
+        }
+        // next turn's records: register -> the other half of the record buffer, then fetch the turn after
+        recCur = recBase + (recCur == recBase ? 512 : 0);
+        stsV4<0>(recCur + 16 * lane, make_uint4(recNext.x, recNext.y, recNext.z, recNext.w));
+        recNext = recLoad(y + 9);
+        __syncwarp();  // the W rows are free again, the records are visible
+    }
+}
+
+template <int NPT>
+cudaError_t launchLStreamT(const LStreamArgs &a, cudaStream_t stream)
+{
+    dim3 grid((a.DW + a.stripW - 1) / a.stripW, (a.dstRows + a.bandRows - 1) / a.bandRows, a.nFrames);
+    resizeLanczosStreamKernel<NPT><<<grid, 32, kLStreamSmem, stream>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
 }  // namespace
 
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D)
@@ -1994,6 +2175,24 @@ cudaError_t launchRatio(const RatioArgs &a, cudaStream_t stream)
     if (a.RS == 2 && a.RD == 1 && a.NX == 12) return launchRatioT<2, 1, 12, 0, true>(a, stream);
     if (a.RS == 2 && a.RD == 1 && a.NX == 8) return launchRatioT<2, 1, 8, 0, true>(a, stream);
     if (a.RS == 2 && a.RD == 1 && a.NX == 4) return launchRatioT<2, 1, 4, 0, true>(a, stream);
+    return cudaErrorInvalidValue;
+}
+
+bool lstreamHasKernel(int NP)
+{
+    return NP == 2 || NP == 3 || NP == 4 || NP == 6 || NP == 8 || NP == 12;
+}
+
+cudaError_t launchLStream(const LStreamArgs &a, cudaStream_t stream)
+{
+    switch (a.NP) {
+    case 2: return launchLStreamT<2>(a, stream);
+    case 3: return launchLStreamT<3>(a, stream);
+    case 4: return launchLStreamT<4>(a, stream);
+    case 6: return launchLStreamT<6>(a, stream);
+    case 8: return launchLStreamT<8>(a, stream);
+    case 12: return launchLStreamT<12>(a, stream);
+    }
     return cudaErrorInvalidValue;
 }
 

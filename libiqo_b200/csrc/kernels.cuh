@@ -170,6 +170,25 @@ struct RatioArgs {
 bool ratioHasKernel(int RS, int RD, int NX, int odd);
 cudaError_t launchRatio(const RatioArgs &a, cudaStream_t stream);
 
+// Arguments of the general Lanczos streaming kernel (plan.hpp LStreamPlan + PackedPlan's horizontal tables).
+struct LStreamArgs {
+    const uint8_t *src;            // buffer row 0 == global source row srcRow0
+    uint8_t *dst;                  // addresses global destination row dstRow0
+    long long srcPitch, dstPitch, srcFrameStride, dstFrameStride;
+    int SW, DW;
+    int nFrames;
+    int srcRow0, srcRows, dstRow0, dstRows;
+    int bandRows;                  // destination rows per warp (multiple of 8)
+    int stripW;
+    int workBias;
+    const int32_t *rowRec;         // [DH][16]
+    const int4 *recX;              // PackedPlan: {first column, coefficient word offset, accumulator init, divisor}
+    const uint32_t *cwX;
+    int NP;
+};
+bool lstreamHasKernel(int NP);
+cudaError_t launchLStream(const LStreamArgs &a, cudaStream_t stream);
+
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D);
 cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_t stream);
 cudaError_t initKernels();  // sets function attributes once per device

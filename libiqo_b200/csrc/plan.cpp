@@ -890,3 +890,76 @@ void buildRatioPlan(const Plan &p, RatioPlan &r)
 }
 
 }  // namespace iqo_b200
+
+// ---------------------------------------------------------------------------------------------
+// Plan of the general Lanczos streaming kernel
+// ---------------------------------------------------------------------------------------------
+namespace iqo_b200 {
+
+void buildLStreamPlan(const Plan &p, const PackedPlan &q, LStreamPlan &g)
+{
+    g.eligible = false;
+    g.why.clear();
+    const AxisPlan &X = p.x, &Y = p.y;
+    if (p.kind != kLanczos) { g.why = "not Lanczos"; return; }
+    if (!q.eligible) { g.why = "packed tables unavailable: " + q.why; return; }
+    if (X.identity || Y.identity) { g.why = "pass-through axis"; return; }
+    if (Y.coefMin < -128 || Y.coefMax > 127) { g.why = "vertical coefficients do not fit int8"; return; }
+    const int NX = X.N, NY = Y.N;
+    // strip width: the source window [firstX[t0] & ~7, firstX[t1] + NX) of every strip must fit 256 columns
+    int w = 256;
+    for (;;) {
+        bool ok = true;
+        for (int64_t t0 = 0; t0 < X.D && ok; t0 += w) {
+            const int64_t t1 = std::min<int64_t>(X.D, t0 + w) - 1;
+            const int lo = q.firstX[size_t(t0)] & ~7, hi = q.firstX[size_t(t1)] + NX - 1;
+            if (hi - lo > 255) ok = false;
+        }
+        if (ok) break;
+        w -= 8;
+        if (w < 8) { g.why = "horizontal kernel wider than a warp strip"; return; }
+    }
+    g.stripW = w;
+    // vertical records (see buildRatioPlan)
+    std::vector<int> rlo(size_t(Y.D), 0), rhi(size_t(Y.D), -1);
+    for (int64_t y = 0; y < Y.D; ++y) {
+        const int32_t *c = &Y.coef[size_t(Y.row[size_t(y)]) * NY];
+        const int f = Y.first[size_t(y)];
+        bool any = false;
+        for (int i = 0; i < NY; ++i)
+            if (c[i] != 0) {
+                const int row = f + i;
+                if (row < 0 || row >= Y.S) { g.why = "vertical tap outside the image with non-zero weight"; return; }
+                if (!any) rlo[size_t(y)] = row;
+                rhi[size_t(y)] = row;
+                any = true;
+            }
+        if (!any) { g.why = "all-zero vertical row"; return; }
+    }
+    g.rowRec.assign(size_t(Y.D) * 16, 0);
+    g.maxGroups = 1;
+    int gmin = 1 << 30;
+    for (int64_t y = Y.D - 1; y >= 0; --y) {
+        gmin = std::min(gmin, rlo[size_t(y)] / 4);
+        const int g0 = gmin, g1 = rhi[size_t(y)] / 4;
+        if (g1 - g0 + 1 > 8) { g.why = "vertical kernel spans more than eight 4-row groups"; return; }
+        g.maxGroups = std::max(g.maxGroups, g1 - g0 + 1);
+        const int32_t *c = &Y.coef[size_t(Y.row[size_t(y)]) * NY];
+        const int f = Y.first[size_t(y)];
+        int32_t *rec = &g.rowRec[size_t(y) * 16];
+        rec[0] = g0;
+        rec[1] = g1 - g0 + 1;
+        const int den = Y.deno[size_t(Y.row[size_t(y)])];
+        if (den < 0 || den > 255) { g.why = "border denominator out of range"; return; }
+        rec[2] = den;
+        rec[3] = den > 1 ? int32_t(uint32_t((1ull << 32) / uint64_t(den) + 1)) : 0;
+        for (int i = 0; i < NY; ++i)
+            if (c[i] != 0) {
+                const int pos = f + i - 4 * g0;
+                rec[4 + (pos >> 2)] |= int32_t((uint32_t(c[i]) & 0xffu) << (8 * (pos & 3)));
+            }
+    }
+    g.eligible = true;
+}
+
+}  // namespace iqo_b200

@@ -191,3 +191,21 @@ struct RatioPlan {
 void buildRatioPlan(const Plan &plan, RatioPlan &r);
 
 }  // namespace iqo_b200
+
+namespace iqo_b200 {
+
+// Lanczos at any ratio (kernels.cu: resizeLanczosStreamKernel): the record-driven dp4a vertical pass of the
+// rational-ratio kernel with the column-resident horizontal pass (and tables: recX, cwX, workBias) of the packed one.
+struct LStreamPlan {
+    bool eligible;
+    std::string why;
+    int stripW;                   // destination columns per warp strip (its source window fits 256 columns)
+    int maxGroups;                // most 4-row groups a destination row reads (<= 8)
+    // per destination row, 16 words: first 4-row group, groups, border denominator, multiply-high constant,
+    // 8 packed s8 coefficient words, 4 unused
+    std::vector<int32_t> rowRec;
+};
+
+void buildLStreamPlan(const Plan &plan, const PackedPlan &packed, LStreamPlan &g);
+
+}  // namespace iqo_b200

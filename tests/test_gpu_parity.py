@@ -268,7 +268,7 @@ RATIO_CASES = [
     (4, 1, 960, 540, 640, 360, 0, 0, "ratio_stream"),      # Lanczos4 at 3:2 (12 taps)
     (3, 2, 960, 540, 640, 360, 0, 0, "ratio_stream"),      # chroma plane of a 1080p -> 720p YUV420 frame (4 taps)
     (3, 1, 480, 270, 320, 180, 4, 0, "ratio_stream"),      # host rows are staged with an aligned pitch
-    (3, 1, 492, 270, 328, 180, 0, 0, "packed"),            # source width not a multiple of 8
+    (3, 1, 492, 270, 328, 180, 0, 0, "lanczos_stream"),    # source width not a multiple of 8: general streaming kernel
 ]
 
 
@@ -290,8 +290,11 @@ def test_packed_kernel_wide_source_window():
     src = lcg_image(434, 582, seed=9)
     rc, want = oracle_resize(LANCZOS, src, 115, 392, 1, 1, sw=566)
     assert rc == 0
-    got, kernel = gpu_resize(LANCZOS, src, 115, 392, 1, 1, sw=566)
+    got, kernel = gpu_resize(LANCZOS, src, 115, 392, 1, 1, sw=566, path=iqo.PATH_NO_STREAM)
     assert kernel == "packed"
+    assert np.array_equal(got, want)
+    got, kernel = gpu_resize(LANCZOS, src, 115, 392, 1, 1, sw=566)
+    assert kernel == "lanczos_stream"
     assert np.array_equal(got, want)
 
 

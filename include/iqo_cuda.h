@@ -60,8 +60,11 @@ enum {
     IQO_CUDA_PATH_NO_TMA = 2,  /* like NO_STREAM, but the tiled 2:1 Lanczos kernel reads the source
                                   with plain global loads instead of TMA (what AUTO itself does
                                   when the source pitch or base is not 8/16-byte aligned)          */
-    IQO_CUDA_PATH_NO_STREAM = 3 /* like AUTO, but without the warp-streaming kernels: 2:1 Lanczos uses
-                                  the tiled (TMA) kernel, other rational ratios the general one    */
+    IQO_CUDA_PATH_NO_STREAM = 3, /* like AUTO, but without the warp-streaming kernels: 2:1 Lanczos uses
+                                  the tiled (TMA) kernel, other Lanczos ratios the general packed one */
+    IQO_CUDA_PATH_STREAM = 4    /* like AUTO, but the warp-streaming kernels also take launches that are
+                                  too small to fill the GPU with one warp per strip (AUTO gives those
+                                  to the tiled / packed kernels, which start faster)                */
 };
 
 /* Replaces: I{Lanczos,Area,Linear}ResizerImpl::init (reference src/IQOLanczosResizerImpl.hpp:17-22,

@@ -18,10 +18,10 @@ import ctypes as C
 import os
 
 __all__ = ["LanczosResizer", "AreaResizer", "LinearResizer", "Yuv420Resizer", "IqoCudaError", "lib", "build",
-           "LANCZOS", "AREA", "LINEAR", "PATH_AUTO", "PATH_GENERIC", "PATH_NO_TMA", "PATH_NO_STREAM", "exported_symbols"]
+           "LANCZOS", "AREA", "LINEAR", "PATH_AUTO", "PATH_GENERIC", "PATH_NO_TMA", "PATH_NO_STREAM", "PATH_STREAM", "exported_symbols"]
 
 LANCZOS, AREA, LINEAR = 0, 1, 2
-PATH_AUTO, PATH_GENERIC, PATH_NO_TMA, PATH_NO_STREAM = 0, 1, 2, 3
+PATH_AUTO, PATH_GENERIC, PATH_NO_TMA, PATH_NO_STREAM, PATH_STREAM = 0, 1, 2, 3, 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libiqo_cuda.so")

@@ -149,7 +149,7 @@ struct iqo_cuda_resizer {
     cudaStream_t *stream;
     uint8_t **dSrc, **dDst;
     int device;
-    bool useTma, useStream;
+    bool useTma, useStream, forceStream;
     int path;
     const char *lastKernel;
     size_t srcPitch, dstPitch;  // device pitches of the staging frames
@@ -158,7 +158,7 @@ struct iqo_cuda_resizer {
     iqo_cuda_resizer(const std::shared_ptr<SharedPlan> &s, Workspace *w)
         : sp(s), ws(w), plan(s->plan), half(s->half), tx(s->tx), ty(s->ty), geom(s->geom), dBorderY(s->dBorderY),
           dMagicY(s->dMagicY), dBorderX(s->dBorderX), stream(w->stream), dSrc(w->dSrc), dDst(w->dDst), device(s->device),
-          useTma(true), useStream(true), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
+          useTma(true), useStream(true), forceStream(false), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
     {
     }
 };
@@ -359,8 +359,11 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         const bool tmaOk = r->useTma && encodeTiled() != 0 && boxRows <= halfSourceRowsMax() &&
                            ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 && (nFrames == 1 || srcFrameStride % 16 == 0);
         // streaming variant (a warp per column strip and row band): source rows are copied as aligned 16-byte chunks
+        // A warp per strip needs a big launch to fill the GPU (measured cross-over against the tiled kernel: about 8000
+        // warps at the shortest band, i.e. ~64 frames of 1080p); smaller launches start faster on the tiled kernel.
+        const long long warpsMin = (long long)((h.DW + 119) / 120) * (((h.DH + 1) / 2 + 23) / 24) * (long long)nFrames;
         const bool streamOk = r->useStream && hp.sEligible && h.SW % 8 == 0 && ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 &&
-                              (nFrames == 1 || srcFrameStride % 16 == 0);
+                              (nFrames == 1 || srcFrameStride % 16 == 0) && (r->forceStream || warpsMin >= 8000);
         if (streamOk) {
             // bands: enough warps to fill the device several times over, but long enough that the
             // ring refill and the re-read halo rows of a band stay small
@@ -457,7 +460,10 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         }
     }
     // Lanczos at 3:2, 1:2, 3:4 ...: rational-ratio streaming kernel
-    if (r->useStream && sp.ratio.eligible && whole && ((uintptr_t)src % 8) == 0 && srcSt % 8 == 0 && srcFrameStride % 8 == 0) {
+    // (cross-over against the packed kernel: about 600 warps at the shortest band, three 1080p -> 720p frames)
+    if (r->useStream && sp.ratio.eligible && whole && ((uintptr_t)src % 8) == 0 && srcSt % 8 == 0 && srcFrameStride % 8 == 0 &&
+        (r->forceStream || (long long)((r->plan.x.D + 8 * sp.ratio.groupsPerStrip - 1) / (8 * sp.ratio.groupsPerStrip)) *
+                                   ((r->plan.y.D + 31) / 32) * (long long)nFrames >= 600)) {
         const RatioPlan &rp = sp.ratio;
         RatioArgs q;
         q.srcPitch = (long long)srcSt;
@@ -504,7 +510,10 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         }
     }
     // Lanczos at any other ratio, row bands included: general streaming kernel
-    if (r->useStream && sp.lstream.eligible && ((uintptr_t)src % 8) == 0 && srcSt % 8 == 0 && srcFrameStride % 8 == 0) {
+    // (cross-over against the packed kernel: about 8000 warps at the shortest band)
+    if (r->useStream && sp.lstream.eligible && ((uintptr_t)src % 8) == 0 && srcSt % 8 == 0 && srcFrameStride % 8 == 0 &&
+        (r->forceStream || (long long)((r->plan.x.D + sp.lstream.stripW - 1) / sp.lstream.stripW) * ((dstRows + 31) / 32) *
+                                   (long long)nFrames >= 8000)) {
         LStreamArgs q;
         q.srcPitch = (long long)srcSt;
         q.dstPitch = (long long)dstSt;
@@ -932,9 +941,10 @@ int iqo_cuda_sync(iqo_cuda_resizer *r)
 
 int iqo_cuda_set_path(iqo_cuda_resizer *r, int path)
 {
-    if (!r || path < 0 || path > IQO_CUDA_PATH_NO_STREAM) return fail(IQO_CUDA_E_ARG, "bad path");
+    if (!r || path < 0 || path > IQO_CUDA_PATH_STREAM) return fail(IQO_CUDA_E_ARG, "bad path");
     r->useTma = (path != IQO_CUDA_PATH_NO_TMA);
-    r->useStream = (path == IQO_CUDA_PATH_AUTO);
+    r->useStream = (path == IQO_CUDA_PATH_AUTO || path == IQO_CUDA_PATH_STREAM);
+    r->forceStream = (path == IQO_CUDA_PATH_STREAM);
     r->path = (path == IQO_CUDA_PATH_GENERIC) ? IQO_CUDA_PATH_GENERIC : IQO_CUDA_PATH_AUTO;
     return IQO_CUDA_OK;
 }

@@ -227,17 +227,17 @@ HALF_CASES = [
 
 
 def half_variant(kname, path, sw):
-    """Name of the 2:1 Lanczos kernel a host image (staged with a 16-byte aligned pitch) runs on."""
+    """Name of the 2:1 Lanczos kernel a single small host image (staged with a 16-byte aligned pitch) runs on."""
     if kname not in ("half", "half_sym"):
         return kname
-    if path == iqo.PATH_AUTO and sw % 8 == 0 and sw // 2 >= 32:
-        return kname + "_stream"     # a warp per column strip: needs whole 8-column words
-    if path in (iqo.PATH_AUTO, iqo.PATH_NO_STREAM):
+    if path == iqo.PATH_STREAM and sw % 8 == 0 and sw // 2 >= 32:
+        return kname + "_stream"     # a warp per column strip: needs whole 8-column words (AUTO: big launches only)
+    if path in (iqo.PATH_AUTO, iqo.PATH_STREAM, iqo.PATH_NO_STREAM):
         return kname + "_tma"        # tiled kernel, source window staged by TMA
     return kname                     # tiled kernel, plain global loads
 
 
-@pytest.mark.parametrize("path", [iqo.PATH_AUTO, iqo.PATH_NO_STREAM, iqo.PATH_NO_TMA])
+@pytest.mark.parametrize("path", [iqo.PATH_AUTO, iqo.PATH_STREAM, iqo.PATH_NO_STREAM, iqo.PATH_NO_TMA])
 @pytest.mark.parametrize("case", HALF_CASES)
 def test_half_kernel(case, path):
     deg, px, sw, sh, spad, dpad, kname = case
@@ -278,10 +278,14 @@ def test_ratio_stream_kernel(case):
     src = lcg_image(sh, sw + spad, seed=23)
     rc, want = oracle_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
     assert rc == 0
-    got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+    got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad, path=iqo.PATH_STREAM)
     assert kernel == kname
     bad = np.argwhere(got != want)
     assert bad.size == 0, (len(bad), bad[:8].tolist())
+    # AUTO gives single small images to the packed kernel (a warp per strip cannot fill the GPU)
+    got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+    assert kernel in (kname, "packed")
+    assert np.array_equal(got, want)
 
 
 def test_packed_kernel_wide_source_window():
@@ -293,7 +297,7 @@ def test_packed_kernel_wide_source_window():
     got, kernel = gpu_resize(LANCZOS, src, 115, 392, 1, 1, sw=566, path=iqo.PATH_NO_STREAM)
     assert kernel == "packed"
     assert np.array_equal(got, want)
-    got, kernel = gpu_resize(LANCZOS, src, 115, 392, 1, 1, sw=566)
+    got, kernel = gpu_resize(LANCZOS, src, 115, 392, 1, 1, sw=566, path=iqo.PATH_STREAM)
     assert kernel == "lanczos_stream"
     assert np.array_equal(got, want)
 
@@ -323,7 +327,7 @@ def test_ratio_stream_sweep():
             rc, want = oracle_resize(LANCZOS, src, dw, dh, deg)
             if rc != 0:
                 continue
-            got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg)
+            got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg, path=iqo.PATH_STREAM)
             if iqo.plan_kernel(LANCZOS, deg, sw, sh, dw, dh, 1)[0] == "ratio_stream":
                 assert kernel == "ratio_stream"
                 cases += 1
@@ -341,6 +345,7 @@ def test_ratio_stream_batch_and_extremes():
     dsrc = torch.from_numpy(host).cuda()
     ddst = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
     with iqo.LanczosResizer(3, sw, sh, dw, dh) as r:
+        r.set_path(iqo.PATH_STREAM)
         r.resize_batch(n, sw, sw * sh, dsrc, dw, dw * dh, ddst, torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         assert r.last_kernel() == "ratio_stream"
@@ -374,13 +379,14 @@ def test_half_kernel_extreme_values():
 
 
 def test_half_kernel_device_pitches():
-    """Device-resident frames: a 16-byte aligned pitch takes the streaming variant, one that is only
-    8- or 4-byte aligned the tiled global-load variant, an odd pitch falls back to the generic kernel;
-    without the streaming variant a 16-byte aligned pitch takes the TMA variant."""
+    """Device-resident frames: a 16-byte aligned pitch can take the streaming variant (AUTO: big launches only)
+    or the TMA variant, one that is only 8- or 4-byte aligned the tiled global-load variant, an odd pitch
+    falls back to the generic kernel."""
     torch = pytest.importorskip("torch")
     sw, sh, dw, dh, n = 488, 250, 244, 125, 3
-    for pitch, path, expect in ((496, iqo.PATH_AUTO, "half_sym_stream"), (496, iqo.PATH_NO_STREAM, "half_sym_tma"),
-                                (504, iqo.PATH_NO_STREAM, "half_sym"), (504, iqo.PATH_AUTO, "half_sym"),
+    for pitch, path, expect in ((496, iqo.PATH_STREAM, "half_sym_stream"), (496, iqo.PATH_AUTO, "half_sym_tma"),
+                                (496, iqo.PATH_NO_STREAM, "half_sym_tma"),
+                                (504, iqo.PATH_NO_STREAM, "half_sym"), (504, iqo.PATH_STREAM, "half_sym"),
                                 (492, iqo.PATH_AUTO, "half_sym"),
                                 (489, iqo.PATH_AUTO, "generic")):
         host = np.stack([lcg_image(sh, pitch, seed=40 + f) for f in range(n)])

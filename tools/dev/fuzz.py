@@ -1,5 +1,5 @@
 """One-off randomized parity fuzz of the specialised kernels against the oracle (not part of the test suite)."""
-import sys, time
+import os, sys, time
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np
 import libiqo_b200 as iqo
@@ -8,6 +8,7 @@ from oracle_lib import oracle_resize, lcg_image, LANCZOS, AREA, LINEAR
 rng = np.random.RandomState(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
 VERBOSE = len(sys.argv) > 3
+PATH = iqo.PATH_STREAM if os.environ.get("FUZZ_STREAM") else iqo.PATH_AUTO  # FUZZ_STREAM=1: streaming kernels on small launches too
 t0 = time.time()
 stats = {}
 bad = 0
@@ -25,6 +26,7 @@ def run(kind, deg, px, sw, sh, dw, dh, spad=0, dpad=0):
     if VERBOSE:
         print("case", kind, deg, px, sw, sh, dw, dh, spad, dpad, iqo.plan_kernel(kind, deg, sw, sh, dw, dh, px)[0], flush=True)
     with iqo.make_resizer(kind, deg, sw, sh, dw, dh, px) as r:
+        r.set_path(PATH)
         r.resize(sw + spad, src, dw + dpad, dst)
         k = r.last_kernel()
     stats[k] = stats.get(k, 0) + 1

@@ -1,5 +1,5 @@
 """One-off randomized parity fuzz of device-resident batches with random pitches / frame strides / base offsets."""
-import sys, time
+import os, sys, time
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np, torch
 import libiqo_b200 as iqo
@@ -7,6 +7,7 @@ from oracle_lib import oracle_resize, lcg_image, LANCZOS, AREA, LINEAR
 
 rng = np.random.RandomState(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 60.0
+PATH = iqo.PATH_STREAM if os.environ.get("FUZZ_STREAM") else iqo.PATH_AUTO  # FUZZ_STREAM=1: streaming kernels on small launches too
 t0 = time.time()
 stats, bad = {}, 0
 while time.time() - t0 < budget:
@@ -37,6 +38,7 @@ while time.time() - t0 < budget:
     dsrc = torch.from_numpy(host).cuda()
     ddst = torch.full((doff + n * dfs + 64,), 0xA5, dtype=torch.uint8, device="cuda")
     with iqo.make_resizer(kind, deg, sw, sh, dw, dh, px) as r:
+        r.set_path(PATH)
         r.resize_batch(n, spitch, sfs, dsrc[soff:], dpitch, dfs, ddst[doff:], torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
         k = r.last_kernel()

@@ -104,6 +104,7 @@ struct SharedPlan {
     PackedPlan packed;
     GenericGeom geom;
     PackedGeom pgeom;
+    int sms;              // multiprocessors of the device (launch-size heuristics; 148 on B200)
     int device;
     AxisTables tx, ty;
     uint32_t *dBorderY, *dMagicY, *dSBorderY;
@@ -360,17 +361,17 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
                            ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 && (nFrames == 1 || srcFrameStride % 16 == 0);
         // streaming variant (a warp per column strip and row band): source rows are copied as aligned 16-byte chunks
         // A warp per strip needs a big launch to fill the GPU (measured cross-over against the tiled kernel: about 8000
-        // warps at the shortest band, i.e. ~64 frames of 1080p); smaller launches start faster on the tiled kernel.
+        // warps at the shortest band = 54 per SM, i.e. ~64 frames of 1080p); smaller launches start faster on the tiled kernel.
         const long long warpsMin = (long long)((h.DW + 119) / 120) * (((h.DH + 1) / 2 + 23) / 24) * (long long)nFrames;
         const bool streamOk = r->useStream && hp.sEligible && h.SW % 8 == 0 && ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 &&
-                              (nFrames == 1 || srcFrameStride % 16 == 0) && (r->forceStream || warpsMin >= 8000);
+                              (nFrames == 1 || srcFrameStride % 16 == 0) && (r->forceStream || warpsMin >= 54ll * r->sp->sms);
         if (streamOk) {
             // bands: enough warps to fill the device several times over, but long enough that the
             // ring refill and the re-read halo rows of a band stay small
             const long long strips = (h.DW + 119) / 120, pairs = (h.DH + 1) / 2;
             int bandPairs = 144;
             if (const char *e = getenv("IQO_CUDA_STREAM_BAND_PAIRS")) bandPairs = std::max(1, atoi(e));
-            const long long wantWarps = 6ll * 148 * 20;
+            const long long wantWarps = 6ll * r->sp->sms * 20;
             while (bandPairs > 24 && strips * ((pairs + bandPairs - 1) / bandPairs) * (long long)nFrames < wantWarps) bandPairs /= 2;
             const long long bands = (pairs + bandPairs - 1) / bandPairs;
             h.bandPairs = int((pairs + bands - 1) / bands);
@@ -463,7 +464,7 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
     // (cross-over against the packed kernel: about 600 warps at the shortest band, three 1080p -> 720p frames)
     if (r->useStream && sp.ratio.eligible && whole && ((uintptr_t)src % 8) == 0 && srcSt % 8 == 0 && srcFrameStride % 8 == 0 &&
         (r->forceStream || (long long)((r->plan.x.D + 8 * sp.ratio.groupsPerStrip - 1) / (8 * sp.ratio.groupsPerStrip)) *
-                                   ((r->plan.y.D + 31) / 32) * (long long)nFrames >= 600)) {
+                                   ((r->plan.y.D + 31) / 32) * (long long)nFrames >= 4ll * sp.sms)) {
         const RatioPlan &rp = sp.ratio;
         RatioArgs q;
         q.srcPitch = (long long)srcSt;
@@ -496,7 +497,7 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         // bands of whole 8-row turns: enough warps to fill the device several times over
         const long long strips = (q.DW + 8 * q.groupsPerStrip - 1) / (8 * q.groupsPerStrip);
         int bandRows = 256;
-        while (bandRows > 32 && strips * ((q.DH + bandRows - 1) / bandRows) * (long long)nFrames < 6ll * 148 * 16) bandRows /= 2;
+        while (bandRows > 32 && strips * ((q.DH + bandRows - 1) / bandRows) * (long long)nFrames < 6ll * sp.sms * 16) bandRows /= 2;
         q.bandRows = bandRows;
         if ((q.DH + bandRows - 1) / bandRows <= 65535) {
             r->lastKernel = "ratio_stream";
@@ -513,7 +514,7 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
     // (cross-over against the packed kernel: about 8000 warps at the shortest band)
     if (r->useStream && sp.lstream.eligible && ((uintptr_t)src % 8) == 0 && srcSt % 8 == 0 && srcFrameStride % 8 == 0 &&
         (r->forceStream || (long long)((r->plan.x.D + sp.lstream.stripW - 1) / sp.lstream.stripW) * ((dstRows + 31) / 32) *
-                                   (long long)nFrames >= 8000)) {
+                                   (long long)nFrames >= 54ll * sp.sms)) {
         LStreamArgs q;
         q.srcPitch = (long long)srcSt;
         q.dstPitch = (long long)dstSt;
@@ -533,7 +534,7 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         q.NP = sp.packed.NP;
         const long long strips = (q.DW + q.stripW - 1) / q.stripW;
         int bandRows = 256;
-        while (bandRows > 32 && strips * ((q.dstRows + bandRows - 1) / bandRows) * (long long)nFrames < 6ll * 148 * 16) bandRows /= 2;
+        while (bandRows > 32 && strips * ((q.dstRows + bandRows - 1) / bandRows) * (long long)nFrames < 6ll * sp.sms * 16) bandRows /= 2;
         q.bandRows = bandRows;
         if ((q.dstRows + bandRows - 1) / bandRows <= 65535) {
             r->lastKernel = "lanczos_stream";
@@ -671,6 +672,11 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
 {
     std::shared_ptr<SharedPlan> sp(new SharedPlan());
     sp->device = device;
+    sp->sms = 148;
+    if (cudaDeviceGetAttribute(&sp->sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess || sp->sms <= 0) {
+        cudaGetLastError();
+        sp->sms = 148;
+    }
     int rc = buildPlan(sp->plan, kind, degree, srcW, srcH, dstW, dstH, pxScale);
     if (rc != kPlanOk) return fail(rc, "%s", sp->plan.error.c_str());  // PlanError values equal the IQO_CUDA_E_* codes
     {

@@ -325,7 +325,8 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         // tile height: the image is cut into equal tiles of at most maxRows rows (64 -> 256-thread
         // CTAs with 4 strips, 32 -> 128-thread CTAs with 2 strips)
         int maxRows = 32;  // measured on B200: 3.24 ms vs 3.67 ms per 4096 1080p frames
-        if (const char *e = getenv("IQO_CUDA_HALF_TILE_ROWS")) maxRows = (atoi(e) <= 32) ? 32 : 64;
+        static const int envTileRows = [] { const char *e = getenv("IQO_CUDA_HALF_TILE_ROWS"); return e ? atoi(e) : 0; }();
+        if (envTileRows > 0) maxRows = (envTileRows <= 32) ? 32 : 64;  // tuning knob, read once
         const int tiles = (h.DH + maxRows - 1) / maxRows;
         h.tileRows = 2 * ((h.DH + 2 * tiles - 1) / (2 * tiles));
         h.dstVec = ((uintptr_t)dst % 8) == 0 && dstSt % 8 == 0 && dstFrameStride % 8 == 0;
@@ -370,7 +371,8 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
             // ring refill and the re-read halo rows of a band stay small
             const long long strips = (h.DW + 119) / 120, pairs = (h.DH + 1) / 2;
             int bandPairs = 144;
-            if (const char *e = getenv("IQO_CUDA_STREAM_BAND_PAIRS")) bandPairs = std::max(1, atoi(e));
+            static const int envBandPairs = [] { const char *e = getenv("IQO_CUDA_STREAM_BAND_PAIRS"); return e ? atoi(e) : 0; }();
+            if (envBandPairs > 0) bandPairs = envBandPairs;  // tuning knob, read once
             const long long wantWarps = 6ll * r->sp->sms * 20;
             while (bandPairs > 24 && strips * ((pairs + bandPairs - 1) / bandPairs) * (long long)nFrames < wantWarps) bandPairs /= 2;
             const long long bands = (pairs + bandPairs - 1) / bandPairs;

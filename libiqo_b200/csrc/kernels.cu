@@ -1337,7 +1337,7 @@ struct LinearUpArgs {
     uint32_t rcpWords;         // ceil(2^32 / wordsPerRow)
     const int32_t *firstY, *rowY, *coefY;   // generic vertical tables (two taps per row)
     uint32_t cwX[3];           // per phase: bytes (lo(q0), lo(q1), hi(q0), hi(q1))
-    int q1X[3];                // per phase: weight of the right column (the left one is 32768 - q1)
+    int q1X[3];                // per phase: twice the weight of the right column (the left one is 32768 - q1)
 };
 
 constexpr int kLinearUpRows = 6;  // destination rows per item: they mostly share their two source rows
@@ -1356,8 +1356,8 @@ __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constan
     uint8_t *__restrict__ out = a.dst + (long long)blockIdx.y * a.dstFrameStride + (long long)y0 * a.dstPitch + 4 * K * j;
     const int jm = max(j - 1, 0), jp = min(j + 1, a.wordsPerRow - 1);
 
-    // pair words (col 4j-1+n, col 4j+n) for n = 0..4 as two 16-bit lanes, of the two source rows in use
-    uint32_t A[5], Bv[5];
+    // the six source columns 4j-1 .. 4j+4 of the two source rows in use
+    uint32_t A[6], Bv[6];
     int have = -(1 << 30);
 #pragma unroll
     for (int r = 0; r < kLinearUpRows; ++r) {
@@ -1374,29 +1374,24 @@ __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constan
             const uint32_t *row1 = reinterpret_cast<const uint32_t *>(src + (long long)r1 * a.srcPitch);
             const uint32_t am = __ldg(row0 + jm), a0 = __ldg(row0 + j), ap = __ldg(row0 + jp);
             const uint32_t bm = __ldg(row1 + jm), b0 = __ldg(row1 + j), bp = __ldg(row1 + jp);
-            const uint32_t ua = __funnelshift_r(am, a0, 24), ub = __funnelshift_r(bm, b0, 24);  // columns 4j-1 .. 4j+2
-            const uint32_t va = __funnelshift_r(a0, ap, 24), vb = __funnelshift_r(b0, bp, 24);  // columns 4j+3 .. 4j+6
-            A[0] = prmt(ua, 0u, 0x4140), Bv[0] = prmt(ub, 0u, 0x4140);
-            A[1] = prmt(a0, 0u, 0x4140), Bv[1] = prmt(b0, 0u, 0x4140);
-            A[2] = prmt(a0, 0u, 0x4241), Bv[2] = prmt(b0, 0u, 0x4241);
-            A[3] = prmt(a0, 0u, 0x4342), Bv[3] = prmt(b0, 0u, 0x4342);
-            A[4] = prmt(va, 0u, 0x4140), Bv[4] = prmt(vb, 0u, 0x4140);
+            A[0] = am >> 24, Bv[0] = bm >> 24;
+            A[1] = a0 & 0xffu, Bv[1] = b0 & 0xffu;
+            A[2] = prmt(a0, 0u, 0x4441), Bv[2] = prmt(b0, 0u, 0x4441);
+            A[3] = prmt(a0, 0u, 0x4442), Bv[3] = prmt(b0, 0u, 0x4442);
+            A[4] = a0 >> 24, Bv[4] = b0 >> 24;
+            A[5] = ap & 0xffu, Bv[5] = bp & 0xffu;
         }
-        // vertical blend (two IMAD per pair; <= 255 * 256 per lane, no carry)
-        // horizontal: the two weights of a phase sum to 32768, so
-        //   lo * q0 + hi * q1 + 2^22 == (lo << 15) + 2^22 + (hi - lo) * q1        (one IMAD per pixel);
-        // the result of a convex blend needs no saturation.
-        uint32_t P1 = 0, P4 = 0;
-        uint32_t baseN[5];
-        int diffN[5];
+        // vertical blend per column (<= 255 * 256), then per pixel, with the two horizontal weights of a phase
+        // summing to 32768:   2 * (lo * q0 + hi * q1 + 2^22) == (lo << 16) + 2^23 + (hi - lo) * 2 q1
+        // -- one multiply-add per pixel; the doubled sum has the pixel in its top byte (a convex blend needs no
+        // saturation, and 65280 * 65536 + 2^23 still fits 32 bits)
+        uint32_t V[6], baseN[5], diffN[5];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) V[c] = A[c] * q0 + Bv[c] * q1;
 #pragma unroll
         for (int n = 0; n < 5; ++n) {
-            const uint32_t P = A[n] * q0 + Bv[n] * q1;
-            if (n == 1) P1 = P;
-            if (n == 4) P4 = P;
-            const uint32_t lo = P & 0xffffu, hi = P >> 16;
-            baseN[n] = lo * 32768u + (1u << 22);
-            diffN[n] = (int)hi - (int)lo;
+            baseN[n] = V[n] * 65536u + (1u << 23);
+            diffN[n] = V[n + 1] - V[n];
         }
         uint32_t packed[K];
 #pragma unroll
@@ -1405,19 +1400,19 @@ __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constan
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int i = 4 * quad + e;
-                // g(i) + 1 = floor((2 i + 1 + K) / (2 K))
+                // pixel i blends the columns (4j-1+n, 4j+n), n = g(i) + 1 = floor((2 i + 1 + K) / (2 K))
                 const int n = (2 * i + 1 + K) / (2 * K);
-                v[e] = (baseN[n] + (uint32_t)(diffN[n] * a.q1X[i % K])) >> 23;
+                v[e] = baseN[n] + diffN[n] * (uint32_t)a.q1X[i % K];  // q1X holds 2 * q1
             }
-            packed[quad] = v[0] | (v[1] << 8) | (v[2] << 16) | (v[3] << 24);
+            packed[quad] = prmt(prmt(v[0], v[1], 0x0073), prmt(v[2], v[3], 0x0073), 0x5410);  // the four top bytes
         }
         // replicated edge columns
         if (j == 0) {
-            const int v = (int)((P1 & 0xffffu) + 128u) >> 8;
+            const int v = (int)(V[1] + 128u) >> 8;  // column 0
             packed[0] = (packed[0] & 0xffffff00u) | (uint32_t)min(v, 255);
         }
         if (j == a.wordsPerRow - 1) {
-            const int v = (int)((P4 & 0xffffu) + 128u) >> 8;  // low lane of the last pair = column S-1
+            const int v = (int)(V[4] + 128u) >> 8;  // column S-1
             packed[K - 1] = (packed[K - 1] & 0x00ffffffu) | ((uint32_t)min(v, 255) << 24);
         }
         uint8_t *o = out + (long long)r * a.dstPitch;
@@ -2307,7 +2302,7 @@ cudaError_t launchLinearUp(int K, const uint8_t *src, uint8_t *dst, long long sr
     a.coefY = coefY;
     for (int i = 0; i < 3; ++i) {
         a.cwX[i] = cwX[i];
-        a.q1X[i] = int(((cwX[i] >> 8) & 0xffu) | ((cwX[i] >> 24) << 8));  // low and high byte plane of the second weight
+        a.q1X[i] = 2 * int(((cwX[i] >> 8) & 0xffu) | ((cwX[i] >> 24) << 8));  // low and high byte plane of the second weight
     }
     a.rcpWords = (uint32_t)((0x100000000ull + a.wordsPerRow - 1) / a.wordsPerRow);
     const long long items = (long long)a.wordsPerRow * ((DH + kLinearUpRows - 1) / kLinearUpRows);

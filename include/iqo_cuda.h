@@ -168,10 +168,12 @@ IQO_CUDA_API int iqo_cuda_plan_query(int kind, unsigned degree,
                                      long long *mainBegin, long long *mainEnd,
                                      int32_t *coefs, size_t coefCap,
                                      int32_t *first, int32_t *row, size_t indexCap);
-/* Host-only: which kernel IQO_CUDA_PATH_AUTO selects for this shape when the buffers are
- * suitably aligned ("half_small", "half_sym", "half", "area2", "linear_up2", "linear_up3", "packed",
- * "generic"), and why the more specialised
- * kernels are not eligible.  Both strings are copied NUL-terminated into the caller's buffers. */
+/* Host-only: which kernel family IQO_CUDA_PATH_AUTO selects for this shape when the buffers are
+ * suitably aligned and the launch is large ("half_small", "half_sym", "half", "area2", "linear_up2",
+ * "linear_up3", "ratio_stream", "lanczos_stream", "packed", "generic"), and why the more specialised
+ * kernels are not eligible.  iqo_cuda_last_kernel() adds the variant that actually ran ("_stream",
+ * "_tma"); small launches of the streaming families run on the tiled / packed kernels instead.
+ * Both strings are copied NUL-terminated into the caller's buffers. */
 IQO_CUDA_API int iqo_cuda_plan_kernel(int kind, unsigned degree,
                                       size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale,
                                       char *kernel, size_t kernelCap, char *why, size_t whyCap);

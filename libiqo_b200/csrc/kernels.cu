@@ -1340,7 +1340,10 @@ struct LinearUpArgs {
     int q1X[3];                // per phase: twice the weight of the right column (the left one is 32768 - q1)
 };
 
-constexpr int kLinearUpRows = 6;  // destination rows per item: they mostly share their two source rows
+#ifndef IQO_LINEAR_UP_ROWS
+#define IQO_LINEAR_UP_ROWS 12
+#endif
+constexpr int kLinearUpRows = IQO_LINEAR_UP_ROWS;  // destination rows per item: they mostly share their two source rows
 
 template <int K>
 __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constant__ LinearUpArgs a)

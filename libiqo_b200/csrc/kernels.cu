@@ -1631,8 +1631,11 @@ constexpr int kRatioRingBytes = kRatioRing * 32 * 32;           // [slot][half A
 constexpr int kRatioRecBytes = 2 * 8 * 32;                      // row records of two turns
 constexpr int kRatioSmem = kRatioRingBytes + 8 * kStreamRowBytes + kRatioRecBytes;
 
+#ifndef IQO_RATIO_MINB
+#define IQO_RATIO_MINB 24
+#endif
 template <int RS, int RD, int NX, int TZ, bool ODD>
-__global__ void __launch_bounds__(32, 12) resizeRatioStreamKernel(const __grid_constant__ RatioArgs a)
+__global__ void __launch_bounds__(32, IQO_RATIO_MINB) resizeRatioStreamKernel(const __grid_constant__ RatioArgs a)
 {
     extern __shared__ __align__(16) uint8_t ratioSmem[];
     constexpr int GS = 8 * RS / RD;

@@ -1890,8 +1890,11 @@ cudaError_t launchRatioT(const RatioArgs &a, cudaStream_t stream)
 constexpr int kLStreamRing = 8;
 constexpr int kLStreamSmem = kLStreamRing * 1024 + 8 * kStreamRowBytes + 2 * 8 * 64;
 
+#ifndef IQO_LSTREAM_MINB
+#define IQO_LSTREAM_MINB 12
+#endif
 template <int NPT>
-__global__ void __launch_bounds__(32, 12) resizeLanczosStreamKernel(const __grid_constant__ LStreamArgs a)
+__global__ void __launch_bounds__(32, IQO_LSTREAM_MINB) resizeLanczosStreamKernel(const __grid_constant__ LStreamArgs a)
 {
     extern __shared__ __align__(16) uint8_t lsSmem[];
     const int lane = threadIdx.x;

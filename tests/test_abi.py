@@ -109,3 +109,22 @@ def test_planner_index_maps():
     # identity axis is a single tap of weight one
     q = iqo.plan_query(LANCZOS, 3, 64, 48, 64, 30, 1, 0)
     assert q["numCoefs"] == 1 and q["coefs"].tolist() == [[16384]] and np.array_equal(q["first"], np.arange(64))
+
+
+def test_kernel_family_of_the_baseline_configs():
+    """Host-only planner view: the kernel family each BASELINE config maps to (large, aligned launches)."""
+    L, A, Li = iqo.LANCZOS, iqo.AREA, iqo.LINEAR
+    expect = [
+        ((L, 3, 1920, 1080, 1280, 720, 1), "ratio_stream"),      # cfg1
+        ((A, 0, 3840, 2160, 1920, 1080, 1), "area2"),            # cfg2a
+        ((Li, 0, 1280, 720, 3840, 2160, 1), "linear_up3"),       # cfg2b
+        ((L, 2, 3840, 2160, 1920, 1080, 1), "half_sym"),         # cfg3 luma
+        ((L, 2, 1920, 1080, 960, 540, 2), "half_small"),         # cfg3 chroma
+        ((L, 3, 1920, 1080, 960, 540, 1), "half_sym"),           # cfg4
+        ((L, 4, 32768, 32768, 12000, 12000, 1), "lanczos_stream"),  # cfg5
+        ((L, 3, 1000, 700, 333, 500, 1), "lanczos_stream"),      # arbitrary Lanczos ratio
+        ((A, 0, 1920, 1080, 1280, 720, 1), "packed"),            # Area at 3:2
+        ((L, 3, 1920, 1080, 960, 720, 1), "ratio_stream"),       # 2:1 on X only
+    ]
+    for args, name in expect:
+        assert iqo.plan_kernel(*args)[0] == name, args

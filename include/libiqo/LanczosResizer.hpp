@@ -1,67 +1,38 @@
-#pragma once
+// iqo::LanczosResizer on the B200 / CUDA backend.
+//
+// Drop-in for the reference's include/libiqo/LanczosResizer.hpp:14-59: constructor and resize()
+// have the reference's parameter lists, so programs written against libiqo compile unchanged.
+// The private pointer is a handle of the C ABI in include/iqo_cuda.h instead of a CPUID-selected
+// ILanczosResizerImpl.
+#ifndef LIBIQO_LANCZOS_RESIZER_HPP
+#define LIBIQO_LANCZOS_RESIZER_HPP
 
-//! @file
-//! @brief Lanczos image resampler (B200 / CUDA backend)
-//!
-//! Same public interface as the reference's include/libiqo/LanczosResizer.hpp:14-59, so code
-//! written against libiqo compiles unchanged.  The pimpl no longer points at a CPUID-selected
-//! I*ResizerImpl but at a handle of the CUDA backend (include/iqo_cuda.h).
-
-#include <stddef.h>
-
-struct iqo_cuda_resizer;
-
-#if !defined(IQO_EXPORT)
-    #if defined(__GNUC__)
-        #define IQO_EXPORT __attribute__((visibility("default")))
-    #else
-        #define IQO_EXPORT
-    #endif
-#endif
+#include "detail/backend.hpp"
 
 namespace iqo {
 
-    class IQO_EXPORT LanczosResizer
-    {
-    public:
-        //! @param degree   Window size of Lanczos (ex. A=2 means Lanczos2)
-        //! @param srcW     Width of source image
-        //! @param srcH     Height of source image
-        //! @param dstW     Width of destination image
-        //! @param dstH     Height of destination image
-        //! @param pxScale  Scale of a pixel (ex. 2 when U plane of YUV420 image)
-        //!
-        //! Builds the coefficient tables and uploads them to the current CUDA device.
-        //! On failure (no device, unsupported size) prints the reason and aborts: like the
-        //! reference the class has no error channel, and there is no CPU fallback.
-        LanczosResizer(
-            unsigned int degree,
-            size_t srcW,
-            size_t srcH,
-            size_t dstW,
-            size_t dstH,
-            size_t pxScale=1
-        );
+class IQO_EXPORT LanczosResizer {
+public:
+    // degree: Lanczos window (2 = Lanczos2, 3 = Lanczos3, ...); srcW x srcH -> dstW x dstH pixels;
+    // pxScale: size of one sample in luma pixels (2 for the chroma planes of YUV420).
+    // Plans the coefficient tables and uploads them to the current CUDA device.  The class has no
+    // error channel (neither has the reference) and there is no CPU fallback: without a device,
+    // or for a size the reference leaves undefined, the reason is printed and the process aborts.
+    LanczosResizer(unsigned int degree, size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale = 1);
+    ~LanczosResizer();
 
-        ~LanczosResizer();
+    // One U8 plane: rows of srcSt / dstSt bytes, of which srcW / dstW are pixels.  src and dst may
+    // each be host or device memory.  Only dstW bytes of a destination row are written.
+    // Not re-entrant per object (like the reference); distinct objects are independent.
+    void resize(size_t srcSt, const unsigned char *src, size_t dstSt, unsigned char *dst);
 
-        //! @param srcSt  Stride of src (in byte)
-        //! @param src    Source image (host or device memory)
-        //! @param dstSt  Stride of dst (in byte)
-        //! @param dst    Destination image (host or device memory)
-        void resize(
-            size_t srcSt,
-            const unsigned char * src,
-            size_t dstSt,
-            unsigned char * dst
-        );
+private:
+    LanczosResizer(const LanczosResizer &);             // not copyable (declared, never defined)
+    LanczosResizer &operator=(const LanczosResizer &);
 
-    private:
-        // no copy
-        LanczosResizer(const LanczosResizer &);
-        LanczosResizer & operator=(const LanczosResizer &);
+    iqo_cuda_resizer *m_Impl;
+};
 
-        iqo_cuda_resizer * m_Impl;
-    };
+}  // namespace iqo
 
-}
+#endif

@@ -1,57 +1,32 @@
-#pragma once
+// iqo::LinearResizer on the B200 / CUDA backend: bilinear up-sampling (the reference defines it up to 3x).
+//
+// Drop-in for the reference's include/libiqo/LinearResizer.hpp:14-56 (same constructor and
+// resize() parameter lists); the private pointer is a handle of the C ABI in include/iqo_cuda.h.
+#ifndef LIBIQO_LINEAR_RESIZER_HPP
+#define LIBIQO_LINEAR_RESIZER_HPP
 
-//! @file
-//! @brief Linear image resampler (B200 / CUDA backend)
-//!
-//! Same public interface as the reference's include/libiqo/LinearResizer.hpp:14-56.
-
-#include <stddef.h>
-
-struct iqo_cuda_resizer;
-
-#if !defined(IQO_EXPORT)
-    #if defined(__GNUC__)
-        #define IQO_EXPORT __attribute__((visibility("default")))
-    #else
-        #define IQO_EXPORT
-    #endif
-#endif
+#include "detail/backend.hpp"
 
 namespace iqo {
 
-    class IQO_EXPORT LinearResizer
-    {
-    public:
-        //! @param srcW     Width of source image
-        //! @param srcH     Height of source image
-        //! @param dstW     Width of destination image
-        //! @param dstH     Height of destination image
-        LinearResizer(
-            size_t srcW,
-            size_t srcH,
-            size_t dstW,
-            size_t dstH
-        );
+class IQO_EXPORT LinearResizer {
+public:
+    // srcW x srcH -> dstW x dstH pixels.  Plans the weight tables and uploads them to the current
+    // CUDA device; prints the reason and aborts when that is impossible (no CPU fallback).
+    LinearResizer(size_t srcW, size_t srcH, size_t dstW, size_t dstH);
+    ~LinearResizer();
 
-        ~LinearResizer();
+    // One U8 plane: rows of srcSt / dstSt bytes, of which srcW / dstW are pixels.  src and dst may
+    // each be host or device memory.  Only dstW bytes of a destination row are written.
+    void resize(size_t srcSt, const unsigned char *src, size_t dstSt, unsigned char *dst);
 
-        //! @param srcSt  Stride of src (in byte)
-        //! @param src    Source image (host or device memory)
-        //! @param dstSt  Stride of dst (in byte)
-        //! @param dst    Destination image (host or device memory)
-        void resize(
-            size_t srcSt,
-            const unsigned char * src,
-            size_t dstSt,
-            unsigned char * dst
-        );
+private:
+    LinearResizer(const LinearResizer &);                   // not copyable (declared, never defined)
+    LinearResizer &operator=(const LinearResizer &);
 
-    private:
-        // no copy
-        LinearResizer(const LinearResizer &);
-        LinearResizer & operator=(const LinearResizer &);
+    iqo_cuda_resizer *m_Impl;
+};
 
-        iqo_cuda_resizer * m_Impl;
-    };
+}  // namespace iqo
 
-}
+#endif

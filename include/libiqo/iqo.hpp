@@ -1,8 +1,9 @@
-#pragma once
+// Everything libiqo's users include with <libiqo/iqo.hpp> (reference: include/libiqo/iqo.hpp).
+#ifndef LIBIQO_IQO_HPP
+#define LIBIQO_IQO_HPP
 
-//! @file
-//! @brief umbrella header (same name as the reference's include/libiqo/iqo.hpp)
-
+#include "LanczosResizer.hpp"
 #include "AreaResizer.hpp"
 #include "LinearResizer.hpp"
-#include "LanczosResizer.hpp"
+
+#endif

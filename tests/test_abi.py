@@ -128,3 +128,30 @@ def test_kernel_family_of_the_baseline_configs():
     ]
     for args, name in expect:
         assert iqo.plan_kernel(*args)[0] == name, args
+
+
+def test_cxx98_user_program_builds_against_the_public_headers(tmp_path):
+    """A program written the way libiqo's users write theirs (reference: sample/resize_yuv420p.cpp:125-162,
+    `#include <libiqo/iqo.hpp>`, C++98, default pxScale) compiles and links against include/libiqo + the library.
+    When the reference tree is present (the build container) its own sample is compiled unchanged as well."""
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    src = tmp_path / "user.cpp"
+    src.write_text(
+        "#include <vector>\n#include <libiqo/iqo.hpp>\n"
+        "int main(int argc, char **) {\n"
+        "    if (argc < 100) return 0;  // link check only: never constructs a resizer on a box without a GPU\n"
+        "    std::vector<unsigned char> s(64 * 48), d(32 * 24);\n"
+        "    iqo::LanczosResizer l(3, 64, 48, 32, 24), c(2, 64, 48, 32, 24, 2);\n"
+        "    iqo::AreaResizer a(64, 48, 32, 24);\n"
+        "    iqo::LinearResizer u(32, 24, 64, 48);\n"
+        "    l.resize(64, &s[0], 32, &d[0]); c.resize(64, &s[0], 32, &d[0]);\n"
+        "    a.resize(64, &s[0], 32, &d[0]); u.resize(32, &d[0], 64, &s[0]);\n"
+        "    return 0;\n}\n")
+    exe = tmp_path / "user"
+    libdir = os.path.dirname(iqo.LIB_PATH)
+    subprocess.check_call([cxx, "-std=c++98", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-liqo_cuda", "-Wl,-rpath," + libdir])
+    assert subprocess.call([str(exe)]) == 0
+    sample = "/root/reference/sample/resize_yuv420p.cpp"
+    if os.path.exists(sample):
+        subprocess.check_call([cxx, "-std=c++98", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), sample])

@@ -513,10 +513,11 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         }
     }
     // Lanczos at any other ratio, row bands included: general streaming kernel
-    // (cross-over against the packed kernel: about 8000 warps at the shortest band)
+    // (cross-over against the packed kernel, warm back-to-back launches of cfg5's row bands, tools/gigapixel.py --bands:
+    //  42 warps per SM at the shortest band 0.154 vs 0.280 ms, 11 per SM 48 vs 61 us, 5.4 per SM 35 vs 31 us)
     if (r->useStream && sp.lstream.eligible && ((uintptr_t)src % 8) == 0 && srcSt % 8 == 0 && srcFrameStride % 8 == 0 &&
         (r->forceStream || (long long)((r->plan.x.D + sp.lstream.stripW - 1) / sp.lstream.stripW) * ((dstRows + 31) / 32) *
-                                   (long long)nFrames >= 54ll * sp.sms)) {
+                                   (long long)nFrames >= 12ll * sp.sms)) {
         LStreamArgs q;
         q.srcPitch = (long long)srcSt;
         q.dstPitch = (long long)dstSt;

@@ -61,6 +61,42 @@ def parse_args():
     return ap.parse_args()
 
 
+# ----------------------------------------------------------------------------- parity of the timed batch
+
+def golden_positions(frames):
+    return sorted(set([0, frames // 2, frames - 1]))
+
+
+def plant_golden_frames(src, work):
+    """Overwrite three frames of the (frames, sh, sw) batch with the SURVEY 8c LCG image (seed 1), whose
+    reference output hash is committed in tests/golden/cases.json.  Returns the hash (hex) or None when the
+    workload has no golden vector.  Uses libiqo_b200.vectors (numpy), nothing under oracle/."""
+    import torch
+    from libiqo_b200 import vectors
+    kind, deg, px, sw, sh, dw, dh, _ = work
+    want = vectors.golden_hash(kind, deg, px, sw, sh, dw, dh, seed=1)
+    if want is None or src.shape[0] == 0:
+        return None
+    frame = torch.from_numpy(vectors.lcg_image(sh, sw, seed=1)).to(src.device)
+    for f in golden_positions(src.shape[0]):
+        src[f].copy_(frame)
+    return want
+
+
+def check_golden_frames(dst, want):
+    """The planted frames of the timed batch against the reference's Generic output: the first one by its
+    FNV-1a-64 hash, the others by equality with the first (same source, same result)."""
+    import torch
+    from libiqo_b200 import vectors
+    pos = golden_positions(dst.shape[0])
+    got = "%016x" % vectors.fnv1a64(dst[pos[0]].cpu().numpy())
+    same = all(bool(torch.equal(dst[f], dst[pos[0]])) for f in pos[1:])
+    ok = (got == want) and same
+    return {"frames_checked": len(pos), "mismatches": 0 if ok else None, "max_abs_diff": 0 if ok else None,
+            "fnv1a64": got, "golden": want, "bit_exact": ok,
+            "against": "reference Generic output hash (tests/golden/cases.json, LCG source seed 1 planted in the timed batch)"}
+
+
 # ----------------------------------------------------------------------------- CPU arms
 
 def host_cores():
@@ -248,6 +284,11 @@ def _run_cuda(args, json_fd):
     gen = torch.Generator(device=dev)
     gen.manual_seed(1234 + rank)
     src = torch.randint(0, 256, (frames, sh, sw), dtype=torch.uint8, device=dev, generator=gen)
+    try:
+        golden = plant_golden_frames(src, work)   # three frames with a known reference result (parity below)
+    except Exception as e:  # the parity report must never cost the measurement
+        golden = None
+        print("bench: golden frames not planted: %r" % (e,), file=sys.stderr)
     dst = torch.zeros((frames, dh, dw), dtype=torch.uint8, device=dev)
     r = iqo.make_resizer(kind, deg, sw, sh, dw, dh, px, device=local)
     r.set_path({"generic": iqo.PATH_GENERIC, "no_tma": iqo.PATH_NO_TMA, "no_stream": iqo.PATH_NO_STREAM,
@@ -293,19 +334,14 @@ def _run_cuda(args, json_fd):
     value = total_px / (ms_step * 1e-3) / 1e6
     kernel_name = r.last_kernel()
 
-    # ---- parity of the timed configuration (outside the timed region): a few frames vs the oracle
+    # ---- parity of the timed configuration (outside the timed region): the planted frames of the batch the
+    # timed launches wrote, against the committed hash of the reference's output (no oracle on this arm)
     parity = None
     if rank == 0:
-        import oracle_lib as O
-        bad, maxdiff, checked = 0, 0, 0
-        for f in sorted(set([0, frames // 2, frames - 1])):
-            rc, want = O.oracle_resize(kind, src[f].cpu().numpy(), dw, dh, deg, px)
-            got = dst[f].cpu().numpy()
-            d = np.abs(got.astype(np.int16) - want.astype(np.int16))
-            bad += int((d != 0).sum())
-            maxdiff = max(maxdiff, int(d.max()))
-            checked += 1
-        parity = {"frames_checked": checked, "mismatches": bad, "max_abs_diff": maxdiff, "against": "oracle"}
+        try:
+            parity = check_golden_frames(dst, golden) if golden else {"frames_checked": 0, "against": "no golden vector for this workload"}
+        except Exception as e:
+            parity = {"frames_checked": 0, "error": repr(e)}
 
     # ---- end to end: host (pinned) buffers through the public host-pointer call
     e2e = None

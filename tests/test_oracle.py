@@ -45,6 +45,23 @@ def test_oracle_matches_the_gigapixel_hash():
     assert "%016x" % fnv1a(dst) == "0ec3dba9ab1194ca"
 
 
+@pytest.mark.parametrize("case", [(LANCZOS, 3, 1920, 1080, 1280, 720, "7625cae131094002"),
+                                  (LANCZOS, 3, 1920, 1080, 960, 540, "9ccaee019da3eea2"),
+                                  (AREA, 0, 3840, 2160, 1920, 1080, "d2e341d3c900d384"),
+                                  (LINEAR, 0, 1280, 720, 3840, 2160, "3d4846274d6ae615")])
+def test_oracle_matches_the_benchmark_fill_hashes(case):
+    """SURVEY 8c also recorded the reference's Generic output for the source image its own benchmark makes
+    (benchmark/benchmark.cpp:51-59: std::mt19937(0) + uniform_int_distribution<int>(0, 255), which libstdc++
+    evaluates as the generator's 32-bit output >> 24).  numpy's legacy RandomState(0) is the same init_genrand(0)
+    stream, so the input is reproduced here without the reference."""
+    kind, deg, sw, sh, dw, dh, want = case
+    raw = np.random.RandomState(0).randint(0, 2 ** 32, size=sh * sw, dtype=np.uint64)
+    src = (raw >> 24).astype(np.uint8).reshape(sh, sw)
+    rc, dst = oracle_resize(kind, src, dw, dh, deg, 1)
+    assert rc == 0
+    assert "%016x" % fnv1a(dst) == want
+
+
 def test_coefficient_kats():
     # SURVEY 8c / 8a a5: cfg1 (3:2) phases 0/1, cfg4 and cfg3 tables
     tx = oracle_table(LANCZOS, 0, 1920, 1280, 3)

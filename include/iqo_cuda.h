@@ -85,7 +85,20 @@ IQO_CUDA_API void iqo_cuda_destroy(iqo_cuda_resizer *r);
 
 /* Replaces: I*ResizerImpl::resize (reference src/IQOLanczosResizerImpl.hpp:24-28).
  * src/dst may each be a host pointer (pageable or pinned) or a device pointer; strides are in
- * bytes.  Only dstW bytes of each destination row are written.  Returns after dst is complete. */
+ * bytes.  Only dstW bytes of each destination row are written.  Returns after dst is complete.
+ *
+ * Ordering contract for device pointers: when src or dst is device memory the call runs on the
+ * legacy default stream (stream 0).  It is therefore ordered after all work previously enqueued
+ * on the default stream and on any *blocking* stream (cudaStreamCreate), e.g. the kernel or
+ * copy that produced src.  Work on cudaStreamNonBlocking streams is NOT ordered with it: a
+ * caller that produces src on such a stream must synchronise that stream first, or use
+ * iqo_cuda_resize_batch(r, 1, ..., stream), which enqueues on the caller's own stream.
+ * Host-to-host calls use a private stream of the handle.
+ *
+ * Readable extent of device inputs: source rows are read in aligned 4/8/16-byte words inside
+ * the row pitch, so srcSt * srcH bytes from src must be readable (a buffer that ends right
+ * after the last row's srcW-th byte with srcSt > srcW is too short).  The same holds for the
+ * batch and band entry points; host inputs are staged and have no such requirement. */
 IQO_CUDA_API int iqo_cuda_resize(iqo_cuda_resizer *r, size_t srcSt, const uint8_t *src,
                                  size_t dstSt, uint8_t *dst);
 

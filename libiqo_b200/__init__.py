@@ -152,7 +152,12 @@ class _Resizer(object):
 
     # -- the reference's interface --------------------------------------------------------
     def resize(self, srcSt, src, dstSt, dst):
-        """resize(srcStride, src, dstStride, dst): strides in bytes, host or device buffers."""
+        """resize(srcStride, src, dstStride, dst): strides in bytes, host or device buffers.
+
+        Device buffers (torch CUDA tensors): the call runs on the legacy default stream, i.e. after
+        everything torch has enqueued on its default current stream, and returns when dst is complete.
+        If `src` is produced on a side stream created as non-blocking, synchronise it first or use
+        resize_batch(1, ..., stream=that_stream)."""
         _check(lib().iqo_cuda_resize(self._h, srcSt, _address(src), dstSt, _address(dst)))
 
     # -- batched / sharded forms ----------------------------------------------------------

@@ -12,6 +12,8 @@
 #include <map>
 #include <memory>
 #include <mutex>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <tuple>
@@ -36,6 +38,24 @@ int fail(int code, const char *fmt, ...)
     t_lastError = buf;
     return code;
 }
+
+// C++ exceptions (std::bad_alloc from the planner's vectors, std::system_error from std::thread) must not
+// unwind through the C ABI: IQO_GUARD_BEGIN / IQO_GUARD_END map them to status codes.
+#define IQO_GUARD_BEGIN try {
+#define IQO_GUARD_END                                                                          \
+    }                                                                                          \
+    catch (const std::bad_alloc &)                                                             \
+    {                                                                                          \
+        return fail(IQO_CUDA_E_NOMEM, "host allocation failed (std::bad_alloc)");              \
+    }                                                                                          \
+    catch (const std::exception &e_)                                                           \
+    {                                                                                          \
+        return fail(IQO_CUDA_E_CUDA, "unexpected C++ exception: %s", e_.what());               \
+    }                                                                                          \
+    catch (...)                                                                                \
+    {                                                                                          \
+        return fail(IQO_CUDA_E_CUDA, "unexpected C++ exception");                              \
+    }
 
 #define CUDA_TRY(expr)                                                                         \
     do {                                                                                       \
@@ -708,6 +728,9 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
         }
     }
     sp->geom = chooseGenericGeom(sp->plan.x.first.data(), sp->plan.x.N, int(sp->plan.x.S), int(sp->plan.x.D));
+    if (sp->geom.smemBytes > 200 * 1024)  // the last-resort kernel cannot hold one row of the source window
+        return fail(IQO_CUDA_E_TOO_LARGE, "horizontal source window of %d columns per 8 destination pixels exceeds the kernels' shared memory",
+                    sp->geom.workW);
     buildSmallPlan(sp->plan, sp->small);
     if (sp->small.eligible && (!uploadVec(sp->sRowsY, sp->small.rowsY) || !uploadVec(sp->sMagicY, sp->small.magicY))) {
         cudaGetLastError();
@@ -828,6 +851,7 @@ void iqo_cuda_host_free(void *p)
 int iqo_cuda_create_on(iqo_cuda_resizer **out, int device, int kind, unsigned degree,
                        size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale)
 {
+    IQO_GUARD_BEGIN
     if (!out) return fail(IQO_CUDA_E_ARG, "NULL output handle");
     *out = 0;
     if (kind != IQO_CUDA_LANCZOS) {
@@ -888,6 +912,7 @@ int iqo_cuda_create_on(iqo_cuda_resizer **out, int device, int kind, unsigned de
     if (rc != IQO_CUDA_OK) return rc;
     *out = new iqo_cuda_resizer(sp, ws);
     return IQO_CUDA_OK;
+    IQO_GUARD_END
 }
 
 int iqo_cuda_create(iqo_cuda_resizer **out, int kind, unsigned degree,
@@ -965,6 +990,7 @@ const char *iqo_cuda_last_kernel(const iqo_cuda_resizer *r)
 
 int iqo_cuda_get_table(const iqo_cuda_resizer *r, int axis, int *numCoefs, int *numTables, int32_t *out, size_t cap)
 {
+    IQO_GUARD_BEGIN
     if (!r || axis < 0 || axis > 1) return fail(IQO_CUDA_E_ARG, "bad argument");
     const AxisPlan &a = axis ? r->plan.y : r->plan.x;
     if (numCoefs) *numCoefs = a.N;
@@ -974,12 +1000,14 @@ int iqo_cuda_get_table(const iqo_cuda_resizer *r, int axis, int *numCoefs, int *
         for (size_t i = 0; i < n && i < cap; ++i) out[i] = a.coef[i];
     }
     return IQO_CUDA_OK;
+    IQO_GUARD_END
 }
 
 int iqo_cuda_plan_query(int kind, unsigned degree, size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale,
                         int axis, int *numCoefs, int *numTables, int *numRows, long long *mainBegin, long long *mainEnd,
                         int32_t *coefs, size_t coefCap, int32_t *first, int32_t *row, size_t indexCap)
 {
+    IQO_GUARD_BEGIN
     if (axis < 0 || axis > 1) return fail(IQO_CUDA_E_ARG, "bad axis");
     Plan p;
     int rc = buildPlan(p, kind, degree, srcW, srcH, dstW, dstH, pxScale);
@@ -997,11 +1025,13 @@ int iqo_cuda_plan_query(int kind, unsigned degree, size_t srcW, size_t srcH, siz
         if (row) row[i] = a.row[i];
     }
     return IQO_CUDA_OK;
+    IQO_GUARD_END
 }
 
 int iqo_cuda_plan_kernel(int kind, unsigned degree, size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale,
                          char *kernel, size_t kernelCap, char *why, size_t whyCap)
 {
+    IQO_GUARD_BEGIN
     Plan p;
     int rc = buildPlan(p, kind, degree, srcW, srcH, dstW, dstH, pxScale);
     if (rc != kPlanOk) return fail(rc, "%s", p.error.c_str());
@@ -1028,12 +1058,14 @@ int iqo_cuda_plan_kernel(int kind, unsigned degree, size_t srcW, size_t srcH, si
         snprintf(why, whyCap, "%s%s%s%s%s", h.why.c_str(), rt.eligible ? "" : "; ratio: ", rt.eligible ? "" : rt.why.c_str(),
                  q.eligible ? "" : "; packed: ", q.eligible ? "" : q.why.c_str());
     return IQO_CUDA_OK;
+    IQO_GUARD_END
 }
 
 int iqo_cuda_resize_batch(iqo_cuda_resizer *r, size_t nFrames,
                           size_t srcSt, size_t srcFrameStride, const uint8_t *src,
                           size_t dstSt, size_t dstFrameStride, uint8_t *dst, void *stream)
 {
+    IQO_GUARD_BEGIN
     int rc = checkStrides(r, srcSt, src, dstSt, dst);
     if (rc) return rc;
     if (nFrames == 0) return IQO_CUDA_OK;
@@ -1044,6 +1076,7 @@ int iqo_cuda_resize_batch(iqo_cuda_resizer *r, size_t nFrames,
     cudaStream_t s = (cudaStream_t)stream;  // NULL = the legacy default stream, as everywhere in CUDA
     return launch(r, nFrames, 0, size_t(r->plan.y.D), 0, size_t(r->plan.y.S),
                   srcSt, srcFrameStride, src, dstSt, dstFrameStride, dst, s);
+    IQO_GUARD_END
 }
 
 int iqo_cuda_band_src_rows(const iqo_cuda_resizer *r, size_t dstRow0, size_t dstRows, size_t *srcRow0, size_t *srcRows)
@@ -1063,6 +1096,7 @@ int iqo_cuda_band_src_rows(const iqo_cuda_resizer *r, size_t dstRow0, size_t dst
 int iqo_cuda_resize_band(iqo_cuda_resizer *r, size_t dstRow0, size_t dstRows, size_t srcRow0, size_t srcRows,
                          size_t srcSt, const uint8_t *src, size_t dstSt, uint8_t *dst, void *stream)
 {
+    IQO_GUARD_BEGIN
     int rc = checkStrides(r, srcSt, src, dstSt, dst);
     if (rc) return rc;
     size_t need0, needN;
@@ -1076,12 +1110,14 @@ int iqo_cuda_resize_band(iqo_cuda_resizer *r, size_t dstRow0, size_t dstRows, si
         return fail(IQO_CUDA_E_ARG, "iqo_cuda_resize_band needs device pointers");
     cudaStream_t s = (cudaStream_t)stream;  // NULL = the legacy default stream, as everywhere in CUDA
     return launch(r, 1, dstRow0, dstRows, srcRow0, srcRows, srcSt, 0, src, dstSt, 0, dst, s);
+    IQO_GUARD_END
 }
 
 int iqo_cuda_resize_batch_host(iqo_cuda_resizer *r, size_t nFrames,
                                size_t srcSt, size_t srcFrameStride, const uint8_t *src,
                                size_t dstSt, size_t dstFrameStride, uint8_t *dst)
 {
+    IQO_GUARD_BEGIN
     int rc = checkStrides(r, srcSt, src, dstSt, dst);
     if (rc) return rc;
     if (nFrames == 0) return IQO_CUDA_OK;
@@ -1130,17 +1166,24 @@ int iqo_cuda_resize_batch_host(iqo_cuda_resizer *r, size_t nFrames,
     CUDA_TRY(cudaStreamSynchronize(r->stream[0]));
     CUDA_TRY(cudaStreamSynchronize(r->stream[1]));
     return IQO_CUDA_OK;
+    IQO_GUARD_END
 }
 
 int iqo_cuda_resize(iqo_cuda_resizer *r, size_t srcSt, const uint8_t *src, size_t dstSt, uint8_t *dst)
 {
+    IQO_GUARD_BEGIN
     int rc = checkStrides(r, srcSt, src, dstSt, dst);
     if (rc) return rc;
     DeviceGuard guard(r->device);
     const size_t SW = size_t(r->plan.x.S), SH = size_t(r->plan.y.S);
     const size_t DW = size_t(r->plan.x.D), DH = size_t(r->plan.y.D);
     const bool srcDev = isDevicePointer(src), dstDev = isDevicePointer(dst);
-    cudaStream_t s = r->stream[0];
+    // Stream ordering (see iqo_cuda.h): host-to-host calls run on the handle's private non-blocking stream.  As soon
+    // as a device pointer is involved the work is enqueued on the legacy default stream instead, which is ordered
+    // after everything already enqueued on the default stream and on every blocking stream -- so a source that
+    // a previous kernel / copy is still producing (torch's current stream is the default stream unless changed)
+    // is complete before it is read, and a destination still being read is not overwritten early.
+    cudaStream_t s = (srcDev || dstDev) ? (cudaStream_t)0 : r->stream[0];
     const uint8_t *ksrc = src;
     uint8_t *kdst = dst;
     size_t kSrcSt = srcSt, kDstSt = dstSt;
@@ -1162,6 +1205,7 @@ int iqo_cuda_resize(iqo_cuda_resizer *r, size_t srcSt, const uint8_t *src, size_
     if (!dstDev) CUDA_TRY(cudaMemcpy2DAsync(dst, dstSt, r->dDst[0], r->dstPitch, DW, DH, cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     return IQO_CUDA_OK;
+    IQO_GUARD_END
 }
 
 // ---- planar YUV420 ----
@@ -1204,6 +1248,7 @@ extern "C" {
 
 int iqo_cuda_yuv420_create(iqo_cuda_yuv420 **out, int kind, unsigned degree, size_t srcW, size_t srcH, size_t dstW, size_t dstH)
 {
+    IQO_GUARD_BEGIN
     if (!out) return fail(IQO_CUDA_E_ARG, "NULL output handle");
     *out = 0;
     if (!srcW || !srcH || !dstW || !dstH) return fail(IQO_CUDA_E_ARG, "image sizes must be non-zero");
@@ -1239,6 +1284,7 @@ int iqo_cuda_yuv420_create(iqo_cuda_yuv420 **out, int kind, unsigned degree, siz
     }
     *out = h;
     return IQO_CUDA_OK;
+    IQO_GUARD_END
 }
 
 void iqo_cuda_yuv420_destroy(iqo_cuda_yuv420 *h)
@@ -1275,6 +1321,7 @@ int iqo_cuda_yuv420_frame_bytes(const iqo_cuda_yuv420 *h, size_t *srcBytes, size
 
 int iqo_cuda_yuv420_resize(iqo_cuda_yuv420 *h, size_t nFrames, const uint8_t *src, uint8_t *dst, void *stream)
 {
+    IQO_GUARD_BEGIN
     if (!h) return fail(IQO_CUDA_E_ARG, "NULL handle");
     if (!src || !dst) return fail(IQO_CUDA_E_ARG, "NULL image pointer");
     if (nFrames == 0) return IQO_CUDA_OK;
@@ -1312,6 +1359,7 @@ int iqo_cuda_yuv420_resize(iqo_cuda_yuv420 *h, size_t nFrames, const uint8_t *sr
     CUDA_TRY(cudaStreamSynchronize(h->luma->stream[0]));
     CUDA_TRY(cudaStreamSynchronize(h->luma->stream[1]));
     return IQO_CUDA_OK;
+    IQO_GUARD_END
 }
 
 // ---- multi-device drivers: one host thread + one handle per device, no collectives ----
@@ -1323,6 +1371,7 @@ int iqo_cuda_resize_batch_multi(int kind, unsigned degree,
                                 size_t dstSt, size_t dstFrameStride, uint8_t *dst,
                                 int nDevices, const int *devices)
 {
+    IQO_GUARD_BEGIN
     if (nDevices <= 0) return fail(IQO_CUDA_E_ARG, "nDevices must be positive");
     if (!src || !dst) return fail(IQO_CUDA_E_ARG, "NULL image pointer");
     std::vector<int> rcs(nDevices, IQO_CUDA_OK);
@@ -1347,6 +1396,7 @@ int iqo_cuda_resize_batch_multi(int kind, unsigned degree,
     for (int i = 0; i < nDevices; ++i)
         if (rcs[i] != IQO_CUDA_OK) return fail(rcs[i], "device %d: %s", devices ? devices[i] : i, msgs[i].c_str());
     return IQO_CUDA_OK;
+    IQO_GUARD_END
 }
 
 int iqo_cuda_resize_bands_multi(int kind, unsigned degree,
@@ -1354,6 +1404,7 @@ int iqo_cuda_resize_bands_multi(int kind, unsigned degree,
                                 size_t srcSt, const uint8_t *src, size_t dstSt, uint8_t *dst,
                                 int nDevices, const int *devices)
 {
+    IQO_GUARD_BEGIN
     if (nDevices <= 0) return fail(IQO_CUDA_E_ARG, "nDevices must be positive");
     if (!src || !dst) return fail(IQO_CUDA_E_ARG, "NULL image pointer");
     if (srcSt < srcW || dstSt < dstW) return fail(IQO_CUDA_E_ARG, "stride smaller than width");
@@ -1399,6 +1450,7 @@ int iqo_cuda_resize_bands_multi(int kind, unsigned degree,
     for (int i = 0; i < nDevices; ++i)
         if (rcs[i] != IQO_CUDA_OK) return fail(rcs[i], "device %d: %s", devices ? devices[i] : i, msgs[i].c_str());
     return IQO_CUDA_OK;
+    IQO_GUARD_END
 }
 
 }  // extern "C"

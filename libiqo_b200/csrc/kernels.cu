@@ -2078,8 +2078,15 @@ GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D)
         }
         g.workW = (widest + 7) & ~7;
         g.smemBytes = size_t(g.tileH) * g.workW * 2;
-        if (g.smemBytes <= 96 * 1024 || g.tileW <= 8) break;
-        g.tileW /= 2;  // extreme down-sampling ratios: narrower tile
+        if (g.smemBytes <= 96 * 1024) break;
+        // extreme down-sampling ratios: narrower tile first, then fewer rows (capi.cu rejects the shape at
+        // create time if even an 8 x 1 tile does not fit the 200 KB opt-in limit)
+        if (g.tileW > 8)
+            g.tileW /= 2;
+        else if (g.tileH > 1)
+            g.tileH /= 2;
+        else
+            break;
     }
     return g;
 }

@@ -172,8 +172,14 @@ int lanczosAxis(AxisPlan &a, int degree, uint64_t px, std::string &err, const ch
     a.mainBegin = ((half - 1) * a.D + a.S - 1) / a.S;
     a.mainEnd = std::max<int64_t>(0, (a.S - half) * a.D / a.S);
     if (a.mainBegin > a.mainEnd) {
-        err = std::string("Lanczos ") + name + " axis: source shorter than the kernel (reference unsupported)";
-        return kPlanUnsupported;
+        // Y: the reference's row loops share their iterators and desynchronise (:390-453).  X: resizeXborder
+        // re-seeds its iterator (:547-549), so an empty main range is well defined while the first border
+        // loop stays inside the row (mainBegin <= D): every column takes the border formula.
+        if (name[0] != 'X' || a.mainBegin > a.D) {
+            err = std::string("Lanczos ") + name + " axis: source shorter than the kernel (reference unsupported)";
+            return kPlanUnsupported;
+        }
+        a.mainBegin = a.mainEnd = 0;
     }
     a.deno.assign(size_t(a.rD), 0);
     a.numRows = int(a.rD);
@@ -380,6 +386,7 @@ void buildHalfPlan(const Plan &p, HalfPlan &h)
     h.why.clear();
     const AxisPlan &X = p.x, &Y = p.y;
     if (p.kind != kLanczos) { h.why = "not Lanczos"; return; }
+    if (!X.identity && X.mainBegin >= X.mainEnd) { h.why = "no main columns (source narrower than the kernel)"; return; }
     if (X.rD != 1 || X.rS != 2 || Y.rD != 1 || Y.rS != 2) { h.why = "not 2:1 on both axes"; return; }
     if (X.S % 4 != 0) { h.why = "source width not a multiple of 4"; return; }
     const int NY = Y.N, NX = X.N;
@@ -578,6 +585,7 @@ void buildPackedPlan(const Plan &p, PackedPlan &q, int padNP)
     q.why.clear();
     const AxisPlan &X = p.x, &Y = p.y;
     const bool isSigned = p.workSigned;
+    if (p.kind == kLanczos && !X.identity && X.mainBegin >= X.mainEnd) { q.why = "no main columns (source narrower than the kernel)"; return; }
 
     // ---- vertical: every out-of-image tap must be weightless; trim them off ----
     q.firstY.assign(size_t(Y.D), 0);
@@ -704,6 +712,7 @@ void buildSmallPlan(const Plan &p, SmallPlan &s)
     s.why.clear();
     const AxisPlan &X = p.x, &Y = p.y;
     if (p.kind != kLanczos) { s.why = "not Lanczos"; return; }
+    if (!X.identity && X.mainBegin >= X.mainEnd) { s.why = "no main columns (source narrower than the kernel)"; return; }
     if (X.rD != 1 || X.rS != 2 || Y.rD != 1 || Y.rS != 2) { s.why = "not 2:1 on both axes"; return; }
     if (X.S % 16 != 0) { s.why = "source width not a multiple of 16"; return; }
     // trimmed main-phase taps
@@ -777,6 +786,7 @@ void buildRatioPlan(const Plan &p, RatioPlan &r)
     r.why.clear();
     const AxisPlan &X = p.x, &Y = p.y;
     if (p.kind != kLanczos) { r.why = "not Lanczos"; return; }
+    if (!X.identity && X.mainBegin >= X.mainEnd) { r.why = "no main columns (source narrower than the kernel)"; return; }
     if (X.identity || Y.identity) { r.why = "pass-through axis"; return; }
     if (X.rD > 8 || 8 % X.rD != 0) { r.why = "horizontal period does not divide 8"; return; }
     if (X.D % 8 != 0 || X.S % 8 != 0) { r.why = "widths not multiples of 8"; return; }

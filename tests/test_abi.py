@@ -155,3 +155,17 @@ def test_cxx98_user_program_builds_against_the_public_headers(tmp_path):
     sample = "/root/reference/sample/resize_yuv420p.cpp"
     if os.path.exists(sample):
         subprocess.check_call([cxx, "-std=c++98", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), sample])
+
+
+def test_narrow_source_plans_are_accepted_on_x_only():
+    """mainBegin > mainEnd: defined on X while mainBegin <= dstW (every column a border column), rejected on Y."""
+    q = iqo.plan_query(0, 3, 10, 20, 3, 20, 1, 0)
+    assert q["mainBegin"] == 0 and q["mainEnd"] == 0
+    assert (q["row"] >= q["numTables"]).all()          # planner-made border rows only
+    assert iqo.plan_kernel(0, 3, 10, 20, 3, 20, 1)[0] == "generic"
+    with pytest.raises(iqo.IqoCudaError) as e:
+        iqo.plan_query(0, 3, 7, 30, 2, 30, 1, 0)       # mainBegin (3) > dstW (2): the reference writes past the row
+    assert e.value.code == -2
+    with pytest.raises(iqo.IqoCudaError) as e:
+        iqo.plan_query(0, 3, 30, 10, 30, 3, 1, 1)
+    assert e.value.code == -2

@@ -1,0 +1,163 @@
+"""Row-band (gigapixel) path on the GPU: the general Lanczos streaming kernel driven through
+iqo_cuda_resize_band with srcRow0 != 0 at cfg5's 1024:375 ratio, the full-size BASELINE config 5
+(32768^2 -> 12000^2, hash recorded from the reference's Generic code), and the multi-device
+drivers on distinct ordinals when the box has more than one GPU.
+Replaces the reference's single loop over all rows (src/IQOLanczosResizerImpl_Generic.cpp:369-454)."""
+import numpy as np
+import pytest
+
+import libiqo_b200 as iqo
+from libiqo_b200 import sharding
+from oracle_lib import AREA, LANCZOS, LINEAR, fnv1a, lcg_image, oracle_resize
+
+pytestmark = pytest.mark.gpu
+
+
+def run_bands(r, src, dw, dh, bands, pitch_pad=0, expect_kernel=None):
+    """Destination rows in `bands` [(y0, rows)], each from a device buffer that holds only band + halo."""
+    import torch
+    sh, sw = src.shape
+    out = np.full((dh, dw), 0xEE, dtype=np.uint8)
+    for y0, n in bands:
+        s0, sn = r.band_src_rows(y0, n)
+        host = np.zeros((sn, sw + pitch_pad), dtype=np.uint8)
+        host[:, :sw] = src[s0:s0 + sn]
+        dsrc = torch.from_numpy(host).cuda()
+        ddst = torch.full((n, dw + 8), 0xA5, dtype=torch.uint8, device="cuda")
+        r.resize_band(y0, n, s0, sn, sw + pitch_pad, dsrc, dw + 8, ddst, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        if expect_kernel:
+            assert r.last_kernel() == expect_kernel, (y0, n, r.last_kernel())
+        got = ddst.cpu().numpy()
+        assert (got[:, dw:] == 0xA5).all()
+        out[y0:y0 + n] = got[:, :dw]
+    return out
+
+
+@pytest.mark.parametrize("path,kernel", [(iqo.PATH_STREAM, "lanczos_stream"), (iqo.PATH_AUTO, None), (iqo.PATH_NO_STREAM, "packed")])
+def test_cfg5_ratio_ragged_bands_golden(path, kernel):
+    """4096x1024 -> 1500x375 Lanczos4 (cfg5's 1024:375, 22 taps, 375 phases) in three ragged bands with
+    srcRow0 != 0, against the committed golden hash and the oracle."""
+    pytest.importorskip("torch")
+    sw, sh, dw, dh = 4096, 1024, 1500, 375
+    src = lcg_image(sh, sw, seed=4)
+    rc, want = oracle_resize(LANCZOS, src, dw, dh, 4, 1)
+    assert rc == 0 and "%016x" % fnv1a(want) == "eb104bb1ff7eb33f"
+    with iqo.LanczosResizer(4, sw, sh, dw, dh) as r:
+        r.set_path(path)
+        out = run_bands(r, src, dw, dh, [(0, 5), (5, 123), (128, 200), (328, 47)], expect_kernel=kernel)
+        s0, _ = r.band_src_rows(128, 200)
+        assert s0 > 0
+    bad = np.argwhere(out != want)
+    assert bad.size == 0, (len(bad), bad[:8].tolist())
+    assert "%016x" % fnv1a(out) == "eb104bb1ff7eb33f"
+
+
+@pytest.mark.parametrize("case", [(LANCZOS, 4, 1, 2048, 700, 750, 257), (LANCZOS, 3, 1, 1000, 900, 777, 1234),
+                                  (LANCZOS, 2, 2, 1600, 600, 1111, 401), (LANCZOS, 4, 1, 1536, 512, 600, 200),
+                                  (LANCZOS, 3, 1, 1920, 1080, 1280, 720), (LANCZOS, 3, 1, 1920, 1080, 960, 540)])
+def test_stream_bands_every_split(case):
+    """Bands of 1 ... many rows at offsets that cut 8-row turns, phases and the border rows, with padded pitches;
+    streaming kernels forced.  The 3:2 and 2:1 shapes run whole images on their own kernels and bands on the
+    general streaming kernel: both must agree with the oracle."""
+    pytest.importorskip("torch")
+    kind, deg, px, sw, sh, dw, dh = case
+    src = lcg_image(sh, sw, seed=17)
+    rc, want = oracle_resize(kind, src, dw, dh, deg, px)
+    assert rc == 0
+    rng = np.random.RandomState(7)
+    with iqo.make_resizer(kind, deg, sw, sh, dw, dh, px) as r:
+        r.set_path(iqo.PATH_STREAM)
+        cuts = sorted(set([0, 1, 2, 9, dh - 3, dh - 1, dh] + [int(v) for v in rng.randint(1, dh, 6)]))
+        bands = [(a, b - a) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+        out = run_bands(r, src, dw, dh, bands, pitch_pad=8, expect_kernel="lanczos_stream")
+    bad = np.argwhere(out != want)
+    assert bad.size == 0, (case, len(bad), bad[:8].tolist())
+
+
+def test_gigapixel_full_size_hash():
+    """BASELINE config 5 at full size on one GPU: 32768 x 32768 -> 12000 x 12000 Lanczos4 as eight row bands
+    (what eight GPUs would each do), only band + halo rows uploaded per band; the gathered result must hash to
+    the value SURVEY 8c recorded from the reference (0ec3dba9ab1194ca).  ~1.3 GB of host memory."""
+    torch = pytest.importorskip("torch")
+    free, _ = torch.cuda.mem_get_info()
+    if free < 3 << 30:
+        pytest.skip("less than 3 GB of device memory free")
+    sw = sh = 32768
+    dw = dh = 12000
+    src = lcg_image(sh, sw, seed=1)
+    out = np.zeros((dh, dw), dtype=np.uint8)
+    uploaded = 0
+    with iqo.LanczosResizer(4, sw, sh, dw, dh) as r:
+        for rank in range(8):
+            y0, rows = sharding.band_shard(dh, 8, rank)
+            s0, sn = r.band_src_rows(y0, rows)
+            assert (s0, sn) == sharding.band_source_rows(LANCZOS, 4, sw, sh, dw, dh, 1, y0, rows)
+            uploaded += sn * sw
+            dsrc = torch.from_numpy(src[s0:s0 + sn]).cuda()
+            ddst = torch.zeros((rows, dw), dtype=torch.uint8, device="cuda")
+            r.resize_band(y0, rows, s0, sn, sw, dsrc, dw, ddst, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert r.last_kernel() == "lanczos_stream"
+            out[y0:y0 + rows] = ddst.cpu().numpy()
+            del dsrc, ddst
+    assert out[0, :4].tolist() == [125, 123, 132, 113]
+    assert "%016x" % fnv1a(out) == "0ec3dba9ab1194ca"
+    assert uploaded < 1.02 * sw * sh   # halo rows only: 7 x 22 extra rows
+
+
+def test_multi_device_drivers_distinct_devices():
+    """iqo_cuda_resize_bands_multi / _batch_multi (one host thread + stream per device).  With two or more GPUs
+    the shards run on distinct ordinals (all of them, up to 8); on a one-GPU box this is skipped -- the same
+    calls with both shards on device 0 are covered by test_gpu_parity.py."""
+    ndev = iqo.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two CUDA devices")
+    devices = list(range(min(ndev, 8)))
+    sw, sh, dw, dh = 4096, 1024, 1500, 375
+    src = lcg_image(sh, sw, seed=4)
+    out = np.zeros((dh, dw), dtype=np.uint8)
+    iqo.resize_bands_multi(LANCZOS, 4, sw, sh, dw, dh, 1, sw, src, dw, out, devices)
+    assert "%016x" % fnv1a(out) == "eb104bb1ff7eb33f"
+    n, sw, sh, dw, dh = 3 * len(devices) + 1, 640, 480, 320, 240
+    frames = np.stack([lcg_image(sh, sw, seed=50 + f) for f in range(n)])
+    outs = np.zeros((n, dh, dw), dtype=np.uint8)
+    iqo.resize_batch_multi(LANCZOS, 3, sw, sh, dw, dh, 1, n, sw, sw * sh, frames, dw, dw * dh, outs, devices)
+    for f in range(n):
+        assert np.array_equal(outs[f], oracle_resize(LANCZOS, frames[f], dw, dh, 3)[1]), f
+
+
+@pytest.mark.parametrize("case", [(AREA, 0, 1, 1000, 600, 333, 211), (LINEAR, 0, 1, 300, 200, 777, 555)])
+def test_bands_area_linear(case):
+    pytest.importorskip("torch")
+    kind, deg, px, sw, sh, dw, dh = case
+    src = lcg_image(sh, sw, seed=23)
+    rc, want = oracle_resize(kind, src, dw, dh, deg, px)
+    assert rc == 0
+    with iqo.make_resizer(kind, deg, sw, sh, dw, dh, px) as r:
+        out = run_bands(r, src, dw, dh, [(0, 1), (1, 100), (101, dh - 102), (dh - 1, 1)])
+    assert np.array_equal(out, want)
+
+
+@pytest.mark.parametrize("sw,sh,dw,dh", [(64, 40, 256, 160), (50, 30, 250, 211), (33, 21, 241, 150), (8, 6, 100, 100)])
+def test_linear_beyond_3x_clamps_to_edge(sw, sh, dw, dh):
+    """Linear at D/S > 3: the reference reads outside the image with non-zero weight in the rows / columns next
+    to the borders (undefined).  This implementation and the oracle define those taps as clamped
+    to the edge: every pixel must agree with the oracle, and the pixels whose taps all lie inside the image are
+    the reference-defined ones."""
+    src = lcg_image(sh, sw, seed=29)
+    rc, want = oracle_resize(LINEAR, src, dw, dh)
+    assert rc == 0
+    for path in (iqo.PATH_AUTO, iqo.PATH_GENERIC):
+        dst = np.zeros((dh, dw), dtype=np.uint8)
+        with iqo.LinearResizer(sw, sh, dw, dh) as r:
+            r.set_path(path)
+            r.resize(sw, src, dw, dst)
+        qx = iqo.plan_query(LINEAR, 0, sw, sh, dw, dh, 1, 0)
+        qy = iqo.plan_query(LINEAR, 0, sw, sh, dw, dh, 1, 1)
+        inx = (qx["first"] >= 0) & (qx["first"] + qx["numCoefs"] - 1 < sw)
+        iny = (qy["first"] >= 0) & (qy["first"] + qy["numCoefs"] - 1 < sh)
+        defined = np.outer(iny, inx)
+        assert defined.sum() > 0.5 * dw * dh
+        assert np.array_equal(dst[defined], want[defined])
+        assert np.array_equal(dst, want)   # the clamp-to-edge definition of the remaining pixels

@@ -61,7 +61,7 @@ def test_random_sweep_against_oracle(path):
         if rng.random() < 0.15:
             dh = sh
         deg = rng.randint(1, 9) if kind == LANCZOS else 0
-        px = rng.choice([1, 1, 2]) if kind == LANCZOS else 1
+        px = rng.choice([1, 1, 2, 3]) if kind == LANCZOS else 1
         src = lcg_image(sh, sw + rng.randint(0, 5), seed=rng.randint(1, 1 << 30))
         dpad = rng.randint(0, 5)
         rc, want = oracle_resize(kind, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
@@ -550,3 +550,66 @@ def test_linear_integer_upsampling_kernel(case):
         assert kernel == kname
         bad = np.argwhere(got != want)
         assert bad.size == 0, (len(bad), bad[:6].tolist())
+
+
+def test_resize_is_ordered_after_the_producer_of_a_device_source():
+    """iqo_cuda_resize with device pointers runs on the legacy default stream: a source that torch is still
+    producing on its (default) current stream must be complete before the kernel reads it (the call
+    used to launch on a private non-blocking stream)."""
+    torch = pytest.importorskip("torch")
+    sw, sh, dw, dh = 1920, 1080, 960, 540
+    base = torch.from_numpy(lcg_image(sh, sw, seed=1)).cuda()
+    want = "bc3ae031361c0774"
+    big = torch.zeros((64, sh, sw), dtype=torch.uint8, device="cuda")
+    dst = torch.zeros((dh, dw), dtype=torch.uint8, device="cuda")
+    with iqo.LanczosResizer(3, sw, sh, dw, dh) as r:
+        for rep in range(5):
+            src = torch.zeros((sh, sw), dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            # a few milliseconds of queued work, then the producer of `src`, then resize() without any sync
+            for _ in range(20):
+                big.add_(1)
+            src.copy_(base)
+            r.resize(sw, src, dw, dst)
+            assert "%016x" % fnv1a(dst.cpu().numpy()) == want, rep
+
+
+def test_narrow_sources_all_border_columns():
+    """Source narrower than the horizontal kernel (mainBegin > mainEnd on X, every column a border column):
+    defined by the reference, used to be rejected with -2."""
+    rng = random.Random(5)
+    done = 0
+    for _ in range(60):
+        deg = rng.randint(1, 6)
+        sw, sh = rng.randint(2, 14), rng.randint(30, 60)
+        dw, dh = rng.randint(1, sw), rng.choice([sh, rng.randint(20, 80)])
+        src = lcg_image(sh, sw, seed=rng.randint(1, 1 << 30))
+        rc, want = oracle_resize(LANCZOS, src, dw, dh, deg, 1)
+        if rc != 0:
+            with pytest.raises(iqo.IqoCudaError) as e:
+                iqo.LanczosResizer(deg, sw, sh, dw, dh)
+            assert e.value.code == rc
+            continue
+        for path in PATHS:
+            got, _ = gpu_resize(LANCZOS, src, dw, dh, deg, 1, path=path)
+            assert np.array_equal(got, want), (deg, sw, sh, dw, dh, path)
+        done += 1
+    assert done > 15
+    got, _ = gpu_resize(LANCZOS, lcg_image(20, 10, seed=3), 3, 20, 3)
+    assert np.array_equal(got, oracle_resize(LANCZOS, lcg_image(20, 10, seed=3), 3, 20, 3)[1])
+
+
+def test_extreme_downsampling_uses_a_smaller_generic_tile():
+    """Area 16000 -> 8 wide: the source window of an 8-pixel tile is 16000 columns; the generic kernel shrinks its
+    tile height instead of failing at launch."""
+    src = lcg_image(40, 16000, seed=2)
+    rc, want = oracle_resize(AREA, src, 8, 20)
+    assert rc == 0
+    got, kernel = gpu_resize(AREA, src, 8, 20)
+    assert kernel == "generic"
+    assert np.array_equal(got, want)
+    src = lcg_image(64, 9000, seed=3)
+    rc, want = oracle_resize(LANCZOS, src, 5, 32, 2)
+    assert rc == 0
+    got, kernel = gpu_resize(LANCZOS, src, 5, 32, 2)
+    assert np.array_equal(got, want)

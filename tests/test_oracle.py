@@ -154,3 +154,32 @@ def test_oracle_matches_reference_sweep():
         assert np.array_equal(dst, ref), (kind, deg, px, sw, sh, dw, dh)
         checked += 1
     assert checked > 1000
+
+
+@pytest.mark.skipif(ref_generic() is None, reason="oracle/_ref not built (needs /root/reference)")
+def test_narrow_sources_all_border_columns():
+    """Source narrower than the horizontal kernel: mainBegin > mainEnd on X.  The reference is well defined there
+    (resizeXborder re-seeds its iterator, src/IQOLanczosResizerImpl_Generic.cpp:547-549) as long as
+    mainBegin <= dstW: every column takes the border formula.  The same condition on Y desynchronises the
+    reference's iterators and stays rejected (-2)."""
+    rng = random.Random(77)
+    defined = 0
+    for _ in range(400):
+        deg = rng.randint(1, 6)
+        sw, sh = rng.randint(2, 14), rng.randint(30, 60)
+        dw, dh = rng.randint(1, sw), rng.choice([sh, rng.randint(20, 80)])
+        src = lcg_image(sh, sw, seed=rng.randint(1, 1 << 30))
+        rc, dst = oracle_resize(LANCZOS, src, dw, dh, deg, 1)
+        if rc != 0:
+            continue
+        rc2, ref = ref_resize(LANCZOS, src, dw, dh, deg, 1)
+        assert rc2 == 0 and np.array_equal(dst, ref), (deg, sw, sh, dw, dh)
+        defined += 1
+    assert defined > 100
+    for sw, sh, dw, dh in ((10, 20, 3, 20), (10, 20, 4, 20), (10, 40, 3, 40)):   # the advisor's cases
+        src = lcg_image(sh, sw, seed=3)
+        rc, dst = oracle_resize(LANCZOS, src, dw, dh, 3)
+        assert rc == 0 and np.array_equal(dst, ref_resize(LANCZOS, src, dw, dh, 3)[1])
+    # mainBegin > dstW: the reference's first border loop writes past the row -> still rejected; so is the Y axis
+    assert oracle_resize(LANCZOS, lcg_image(30, 7), 2, 30, 3)[0] == -2
+    assert oracle_resize(LANCZOS, lcg_image(10, 30), 30, 3, 3)[0] == -2

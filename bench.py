@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the libiqo resize hot path on B200.
 
-Workload (BASELINE.json configs[3], the configuration the metric is quoted on):
+Headline workload (BASELINE.json configs[3], the configuration the metric is quoted on):
     a batch of independent 1920x1080 U8 frames, Lanczos3 -> 960x540, frames sharded over the
     GPUs (one process per GPU, no collective: nothing reduces across devices).
 One "step" = one pass of the hot path over the whole per-GPU batch (4096 frames, 8.5 GB in +
@@ -13,6 +13,16 @@ One "step" = one pass of the hot path over the whole per-GPU batch (4096 frames,
 One JSON line on stdout (rank 0).  `value` is device-resident throughput (CUDA events, max
 over ranks); `e2e` is the same metric through the host-pointer C-ABI call
 (iqo_cuda_resize_batch_host) with the H2D / D2H copies inside the timed region.
+
+Outside the headline timed region the CUDA arm also reports (extra keys of the same line):
+    workloads   every other BASELINE config device-resident (cfg1, cfg2a, cfg2b, cfg3 as 256 YUV420
+                frames through Yuv420Resizer, cfg5's ratio): ms, Gpix/s, roofline fraction, kernel,
+                parity against the committed golden hash of the reference's output
+    cfg5        BASELINE configs[4] at full size (32768^2 -> 12000^2 Lanczos4): destination row
+                bands sharded over the ranks, every rank uploads its band + halo from host memory,
+                resizes, downloads; rank 0 gathers and compares the hash with the reference's
+    e2e_single  the drop-in call itself -- resize() on ONE pageable host image -- for cfg1/cfg2a/cfg2b
+    multi_device  (N > 1) iqo_cuda_resize_bands_multi / _batch_multi from rank 0 over all N devices
 """
 import argparse
 import ctypes
@@ -38,8 +48,17 @@ WORKLOADS = {
     "cfg5s_lanczos4_8192_to_3000": (0, 4, 1, 8192, 8192, 3000, 3000, 16),
 }
 DEFAULT_WORKLOAD = "cfg4_lanczos3_1080p_to_540p"
+# the other BASELINE configs, reported in `workloads` (cfg3 is added as whole YUV420 frames)
+EXTRA_WORKLOADS = ["cfg1_lanczos3_1080p_to_720p", "cfg2a_area_2160p_to_1080p", "cfg2b_linear_720p_to_2160p",
+                   "cfg5s_lanczos4_8192_to_3000"]
+CFG3 = (0, 2, 3840, 2160, 1920, 1080, 256)   # kind, degree, srcW, srcH, dstW, dstH, frames
+CFG5 = (0, 4, 1, 32768, 32768, 12000, 12000)
 METRIC = "dst_mpix_per_s_lanczos3_u8_resize"
 UNIT = "Mpix/s"
+# measured issue rates of the scalar pipes in lanes per clock per SM (tools/microbench.cu on B200,
+# profiles/r1_microbench_pipe_rates.txt): FFMA 126.7; IMAD, dp4a, dp2a 64.0
+PIPE_RATES = {"ffma": 126.7, "imad": 64.0, "dp4a": 64.0, "dp2a": 64.0}
+SMS = 148
 
 
 def parse_args():
@@ -54,11 +73,21 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 5)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=10.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-extras", action="store_true", help="skip workloads / cfg5 / e2e_single / multi_device")
     ap.add_argument("--path", default="auto", choices=["auto", "generic", "no_tma", "no_stream", "stream"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU gets the workload's frame count; strong: that count is sharded over the GPUs")
     return ap.parse_args()
+
+
+def workload_config(name, frames_per_gpu):
+    """The `config` object of the JSON line: identical for the CUDA arm and the reference arm (the driver compares
+    them).  The reference arm processes a bounded sample of this workload per step; its `cpu_baseline.sample` says so."""
+    kind, deg, px, sw, sh, dw, dh, _ = WORKLOADS[name]
+    return {"workload": name, "frames_per_gpu": frames_per_gpu, "src": [sw, sh], "dst": [dw, dh],
+            "resizer": {0: "lanczos%d" % deg, 1: "area", 2: "linear"}[kind], "px_scale": px,
+            "sharding": "independent frames per GPU, no collective",
+            "cache": "inputs %.1f GB per GPU exceed the 126 MB L2 (no flush needed)" % (frames_per_gpu * sw * sh / 1e9)}
 
 
 # ----------------------------------------------------------------------------- parity of the timed batch
@@ -70,7 +99,7 @@ def golden_positions(frames):
 def plant_golden_frames(src, work):
     """Overwrite three frames of the (frames, sh, sw) batch with the SURVEY 8c LCG image (seed 1), whose
     reference output hash is committed in tests/golden/cases.json.  Returns the hash (hex) or None when the
-    workload has no golden vector.  Uses libiqo_b200.vectors (numpy), nothing under oracle/."""
+    workload has no golden vector.  Uses libiqo_b200.vectors, nothing under oracle/."""
     import torch
     from libiqo_b200 import vectors
     kind, deg, px, sw, sh, dw, dh, _ = work
@@ -106,30 +135,36 @@ def host_cores():
         return os.cpu_count() or 1
 
 
-def time_cpu(work, seconds, steps=None, warmup=1, max_frames=256):
-    """Time the reference's CPU implementation of the path on a bounded sample of `work`.
-    Returns dict(value Mpix/s, cores, kind, sample, ms_per_step).  Uses oracle/_ref's full
-    reference library (SIMD dispatch + OpenMP, all host threads) when it is present, otherwise
-    the scalar oracle port.  This is the checker being *timed as a baseline*, never the product."""
-    import numpy as np
+def _cpu_runner(work):
+    """(run(n, src, dst), label, threads, close) for the reference's CPU implementation of `work`: oracle/_ref's full
+    reference library (SIMD dispatch + OpenMP, all host threads) when present, else the scalar oracle port."""
     import oracle_lib as O
-    kind, deg, px, sw, sh, dw, dh, _ = work
+    kind, deg, px, sw, sh, dw, dh = work[:7]
     full = O.ref_full()
-    cores = host_cores()
     if full is not None:
-        full.iqo_ref_set_threads(cores)   # torchrun exports OMP_NUM_THREADS=1
+        full.iqo_ref_set_threads(host_cores())   # torchrun exports OMP_NUM_THREADS=1
         h = full.iqo_ref_public_new(kind, deg, sw, sh, dw, dh, px)
 
         def run(n, src, dst):
             full.iqo_ref_public_resize_batch(h, n, sw, sw * sh, src.ctypes.data, dw, dw * dh, dst.ctypes.data)
-        label, used = "reference", full.iqo_ref_threads()
-    else:
-        def run(n, src, dst):
-            rc = O.oracle().iqo_oracle_resize_batch(kind, deg, sw, sh, dw, dh, px, n, sw, sw * sh,
-                                                    src.ctypes.data, dw, dw * dh, dst.ctypes.data)
-            assert rc == 0
-        label, used = "port", 1
-    # calibrate the sample so that one step is ~seconds/(steps+warmup)
+        return run, "reference", full.iqo_ref_threads(), lambda: full.iqo_ref_public_delete(h)
+
+    def run(n, src, dst):
+        rc = O.oracle().iqo_oracle_resize_batch(kind, deg, sw, sh, dw, dh, px, n, sw, sw * sh,
+                                                src.ctypes.data, dw, dw * dh, dst.ctypes.data)
+        assert rc == 0
+    return run, "port", 1, lambda: None
+
+
+def time_cpu(work, steps, warmup, seconds=60.0, max_frames=256):
+    """Time the reference's CPU implementation of the path on a bounded sample of `work`: `steps` timed passes
+    (after `warmup` untimed ones) over min(max_frames, what fits `seconds`) frames.  Both arms of bench.py call
+    this with the same protocol, so cpu_baseline (CUDA arm) and the reference arm's value are the same measurement.
+    This is the checker being *timed as a baseline*, never the product."""
+    import numpy as np
+    import oracle_lib as O
+    kind, deg, px, sw, sh, dw, dh = work[:7]
+    run, label, used, close = _cpu_runner(work)
     probe = 4
     src = np.stack([O.lcg_image(sh, sw, seed=1 + f) for f in range(probe)])
     dst = np.zeros((probe, dh, dw), dtype=np.uint8)
@@ -137,27 +172,34 @@ def time_cpu(work, seconds, steps=None, warmup=1, max_frames=256):
     t = time.perf_counter()
     run(probe, src, dst)
     per_frame = (time.perf_counter() - t) / probe
-    nsteps = steps if steps else 3
-    frames = int(max(1, min(max_frames, seconds / max(per_frame, 1e-9) / (nsteps + warmup))))
+    frames = int(max(1, min(max_frames, seconds / max(per_frame, 1e-9) / (steps + warmup))))
     reps = -(-frames // probe)
     src = np.concatenate([src] * reps)[:frames].copy()
     dst = np.zeros((frames, dh, dw), dtype=np.uint8)
     for _ in range(warmup):
         run(frames, src, dst)
     times = []
-    for _ in range(nsteps):
+    for _ in range(steps):
         t = time.perf_counter()
         run(frames, src, dst)
         times.append(time.perf_counter() - t)
-    if full is not None:
-        full.iqo_ref_public_delete(h)
+    # one image per call, the way the reference's own benchmark loops (benchmark/benchmark.cpp:1017-1033)
+    one_s, one_d = src[:1].copy(), dst[:1].copy()
+    for _ in range(5):
+        run(1, one_s, one_d)
+    calls = []
+    for _ in range(30):
+        t = time.perf_counter()
+        run(1, one_s, one_d)
+        calls.append(time.perf_counter() - t)
+    close()
     mean = sum(times) / len(times)
     return dict(value=round(frames * dw * dh / mean / 1e6, 1), unit=UNIT, cores=used, kind=label,
                 sample="%d frames/step x %d steps (+%d warm-up) of %dx%d->%dx%d, host memory, %s"
-                       % (frames, nsteps, warmup, sw, sh, dw, dh,
+                       % (frames, steps, warmup, sw, sh, dw, dh,
                           "reference public API, CPUID dispatch + OpenMP (oracle/_ref)" if label == "reference"
                           else "scalar oracle port (oracle/iqo_oracle.c)"),
-                ms_per_step=mean * 1e3, frames=frames)
+                ms_per_step=mean * 1e3, frames=frames, us_per_call=round(sorted(calls)[len(calls) // 2] * 1e6, 1))
 
 
 def run_reference(args):
@@ -166,15 +208,15 @@ def run_reference(args):
         return 0
     os.environ["OMP_NUM_THREADS"] = str(host_cores())
     work = WORKLOADS[args.workload]
-    kind, deg, px, sw, sh, dw, dh, _ = work
-    res = time_cpu(work, seconds=60.0, steps=args.steps, warmup=args.warmup, max_frames=256)
+    frames = args.frames or work[7]
+    res = time_cpu(work, steps=args.steps, warmup=max(args.warmup, 3))
     line = {
         "impl": "reference", "metric": METRIC, "value": res["value"], "unit": UNIT,
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(res["ms_per_step"], 3), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-        "config": {"workload": args.workload, "frames_per_step": res["frames"],
-                   "src": [sw, sh], "dst": [dw, dh], "device": "host CPU"},
+        "config": workload_config(args.workload, frames),
+        "detail": {"device": "host CPU", "frames_per_step": res["frames"], "us_per_single_image_call": res["us_per_call"]},
         "cpu_baseline": {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": res["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -245,6 +287,271 @@ def visible_physical_index(local_rank):
     return local_rank
 
 
+# ----------------------------------------------------------------------------- roofline helpers
+
+def hbm_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        return float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def macs_per_dst_px(iqo, kind, deg, px, sw, sh, dw, dh):
+    """SURVEY 8d: N_Y * srcW * dstH + N_X * dstW * dstH multiply-adds, all taps counted, per destination pixel;
+    also the split (vertical, horizontal) so that the packed-instruction bound can be stated."""
+    ny = iqo.plan_query(kind, deg, sw, sh, dw, dh, px, 1)["numCoefs"] if sh != dh else 1
+    nx = iqo.plan_query(kind, deg, sw, sh, dw, dh, px, 0)["numCoefs"] if sw != dw else 1
+    v = ny * sw * dh / float(dw * dh)
+    h = nx * dw * dh / float(dw * dh)
+    return v, h
+
+
+def both_bounds(bytes_total, px_total, macs_v, macs_h, ms, sm_mhz, peak_gbs):
+    """The two rooflines north_star names -- bytes over the measured HBM peak and multiply-adds over the measured FP32
+    FMA issue rate (tools/microbench.cu: 126.7 lanes/clk/SM) -- plus the bound of the instructions the kernels
+    actually issue: dp4a does 4 MACs of the vertical pass per lane-instruction and dp2a 2 of the horizontal pass, both
+    at the measured 64 lanes/clk/SM.  Clock: the SM clock sampled during the timed region (else the maximum)."""
+    clk = (sm_mhz or 1965.0) * 1e6
+    hbm_ms = bytes_total / (peak_gbs * 1e9) * 1e3
+    macs = (macs_v + macs_h) * px_total
+    fma_ms = macs / (PIPE_RATES["ffma"] * SMS * clk) * 1e3
+    idp_ms = (macs_v / 4.0 + macs_h / 2.0 * 2.0) * px_total / (PIPE_RATES["dp4a"] * SMS * clk) * 1e3  # dp2a: lo + hi plane
+    slower = max(hbm_ms, idp_ms)
+    return {"hbm_ms": round(hbm_ms, 4), "fp32_fma_ms": round(fma_ms, 4), "int_dot_ms": round(idp_ms, 4),
+            "bound": "hbm" if hbm_ms >= idp_ms else "int_dot",
+            "frac_of_hbm": round(hbm_ms / ms, 4), "frac_of_fp32_fma": round(fma_ms / ms, 4),
+            "frac_of_int_dot": round(idp_ms / ms, 4), "frac_of_slower": round(slower / ms, 4),
+            "sm_clock_mhz_used": round(clk / 1e6, 1),
+            "note": "fp32_fma_ms is north_star's FMA roofline at one MAC per lane-instruction (measured FFMA rate); the "
+                    "kernels issue packed integer dot products instead, whose bound is int_dot_ms; frac (HBM) is the headline"}
+
+
+def time_launches(torch, fn, warmup, steps):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / steps
+
+
+# ----------------------------------------------------------------------------- extra legs of the CUDA arm
+
+def run_extra_workload(torch, iqo, name, dev, local, peak, sm_mhz):
+    """One BASELINE config device-resident: batch of random frames (frame 0 and the last one carry the LCG image
+    whose reference output hash is committed), 3 warm-up + 5 timed launches."""
+    from libiqo_b200 import vectors
+    work = WORKLOADS[name]
+    kind, deg, px, sw, sh, dw, dh, frames = work
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(99)
+    src = torch.randint(0, 256, (frames, sh, sw), dtype=torch.uint8, device=dev, generator=gen)
+    want = plant_golden_frames(src, work)
+    dst = torch.zeros((frames, dh, dw), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    with iqo.make_resizer(kind, deg, sw, sh, dw, dh, px, device=local) as r:
+        ms = time_launches(torch, lambda: r.resize_batch(frames, sw, sw * sh, src, dw, dw * dh, dst, stream), 3, 5)
+        kernel = r.last_kernel()
+        # one image alone, device resident (cfg1 / cfg2 are "one image" configs): launch-latency bound
+        one_us = time_launches(torch, lambda: r.resize_batch(1, sw, sw * sh, src, dw, dw * dh, dst, stream), 5, 50) * 1e3
+        one_kernel = r.last_kernel()
+    parity = check_golden_frames(dst, want) if want else None
+    byts = float(frames) * (sw * sh + dw * dh)
+    mv, mh = macs_per_dst_px(iqo, kind, deg, px, sw, sh, dw, dh)
+    out = {"workload": name, "frames": frames, "src": [sw, sh], "dst": [dw, dh], "kernel": kernel,
+           "ms": round(ms, 4), "gpix_s": round(frames * dw * dh / ms / 1e6, 1),
+           "bytes_per_dst_px": round((sw * sh + dw * dh) / float(dw * dh), 3),
+           "achieved_gbs": round(byts / ms / 1e6, 1), "frac": round(byts / ms / 1e6 / peak, 4),
+           "macs_per_dst_px": round(mv + mh, 2),
+           "bounds": both_bounds(byts, float(frames) * dw * dh, mv, mh, ms, sm_mhz, peak),
+           "single_image_us": round(one_us, 2), "single_image_kernel": one_kernel,
+           "parity": None if parity is None else {"bit_exact": parity["bit_exact"], "fnv1a64": parity["fnv1a64"],
+                                                  "golden": parity["golden"], "frames_checked": parity["frames_checked"]}}
+    del src, dst
+    return out
+
+
+def run_cfg3(torch, iqo, dev, peak, sm_mhz):
+    """BASELINE configs[2]: 256 planar YUV420 frames 4K -> 1080p, Lanczos2 on all three planes, through the
+    YUV420 frame API (sample/resize_yuv420p.cpp's layout).  The config north_star's 70 % target is stated on."""
+    from libiqo_b200 import vectors
+    kind, deg, sw, sh, dw, dh, frames = CFG3
+    with iqo.Yuv420Resizer(kind, deg, sw, sh, dw, dh) as r:
+        gen = torch.Generator(device=dev)
+        gen.manual_seed(98)
+        src = torch.randint(0, 256, (frames, r.src_frame_bytes), dtype=torch.uint8, device=dev, generator=gen)
+        dst = torch.zeros((frames, r.dst_frame_bytes), dtype=torch.uint8, device=dev)
+        # golden frame: Y = LCG(2160 x 3840, seed 1), U = V = LCG(1080 x 1920, seed 1)
+        ysz, usz = sw * sh, (sw // 2) * (sh // 2)
+        yimg = torch.from_numpy(vectors.lcg_image(sh, sw, seed=1).reshape(-1)).to(dev)
+        uimg = torch.from_numpy(vectors.lcg_image(sh // 2, sw // 2, seed=1).reshape(-1)).to(dev)
+        for f in (0, frames - 1):
+            src[f, :ysz] = yimg
+            src[f, ysz:ysz + usz] = uimg
+            src[f, ysz + usz:ysz + 2 * usz] = uimg
+        stream = torch.cuda.current_stream().cuda_stream
+        ms = time_launches(torch, lambda: r.resize(frames, src, dst, stream), 3, 5)
+        byts = float(frames) * (r.src_frame_bytes + r.dst_frame_bytes)
+        dysz, dusz = dw * dh, (dw // 2) * (dh // 2)
+        want_y = vectors.golden_hash(0, deg, 1, sw, sh, dw, dh)
+        want_c = vectors.golden_hash(0, deg, 2, sw // 2, sh // 2, dw // 2, dh // 2)
+        ok = True
+        for f in (0, frames - 1):
+            host = dst[f].cpu().numpy()
+            ok = ok and "%016x" % vectors.fnv1a64(host[:dysz]) == want_y
+            ok = ok and "%016x" % vectors.fnv1a64(host[dysz:dysz + dusz]) == want_c
+            ok = ok and "%016x" % vectors.fnv1a64(host[dysz + dusz:dysz + 2 * dusz]) == want_c
+    px = float(frames) * (dysz + 2 * dusz)
+    out = {"workload": "cfg3_yuv420_lanczos2_2160p_to_1080p", "frames": frames, "src": [sw, sh], "dst": [dw, dh],
+           "kernel": "half_sym_stream (Y) + half_small (U, V), chroma forked onto side streams",
+           "api": "iqo_cuda_yuv420_resize (Yuv420Resizer), device-resident frames",
+           "ms": round(ms, 4), "gpix_s": round(px / ms / 1e6, 1), "bytes_per_dst_px": 5.0,
+           "achieved_gbs": round(byts / ms / 1e6, 1), "frac": round(byts / ms / 1e6 / peak, 4),
+           "macs_per_dst_px": 20.0,
+           "bounds": both_bounds(byts, px, 16.0 * 2 / 3 + 8.0 / 3, 8.0 * 2 / 3 + 4.0 / 3, ms, sm_mhz, peak),
+           "target": "north_star: >= 0.70 of the HBM roofline for 4K -> 1080p batches",
+           "parity": {"bit_exact": bool(ok), "golden": [want_y, want_c, want_c], "frames_checked": 2}}
+    del src, dst
+    return out
+
+
+def run_cfg5(torch, iqo, dist, rank, world, local, dev):
+    """BASELINE configs[4] at full size, destination row bands sharded over the ranks: every rank fills
+    its band + halo rows of the 32768 x 32768 LCG image in pinned host memory, then -- timed -- uploads them,
+    resizes the band (iqo_cuda_resize_band, global row indices) and downloads the result.  No device-to-device
+    traffic; the gather below exists only so that rank 0 can hash the whole image.  With fewer than 8 ranks every
+    rank does 8 / world bands one after the other."""
+    import numpy as np
+    from libiqo_b200 import sharding, vectors
+    kind, deg, px, sw, sh, dw, dh = CFG5
+    want = vectors.golden_hash(kind, deg, px, sw, sh, dw, dh)
+    y0, rows = sharding.band_shard(dh, world, rank)
+    nb = max(1, 8 // world)
+    stream = torch.cuda.current_stream().cuda_stream
+    out_dev = torch.empty((rows, dw), dtype=torch.uint8, device=dev)
+    out_host = torch.empty((rows, dw), dtype=torch.uint8, pin_memory=True)
+    with iqo.LanczosResizer(deg, sw, sh, dw, dh, device=local) as r:
+        bands = []
+        for b in range(nb):
+            b0, brows = sharding.frame_shard(rows, nb, b)
+            if brows:
+                s0, sn = r.band_src_rows(y0 + b0, brows)
+                bands.append((b0, brows, s0, sn))
+        lo = min(b[2] for b in bands)
+        hi = max(b[2] + b[3] for b in bands)
+        host = torch.empty((hi - lo, sw), dtype=torch.uint8, pin_memory=True)   # this rank's rows only
+        vectors.lcg_fill(host.numpy(), seed=1, offset=lo * sw)
+        dsrc = [torch.empty((sn, sw), dtype=torch.uint8, device=dev) for (_, _, _, sn) in bands]
+        uploaded = sum(sn * sw for (_, _, _, sn) in bands)
+
+        def one_pass(timed_kernels):
+            evs = []
+            for i, (b0, brows, s0, sn) in enumerate(bands):
+                dsrc[i].copy_(host[s0 - lo:s0 - lo + sn], non_blocking=True)            # band + halo upload
+                if timed_kernels:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                r.resize_band(y0 + b0, brows, s0, sn, sw, dsrc[i], dw, out_dev[b0:b0 + brows], stream)
+                if timed_kernels:
+                    e1.record()
+                    evs.append((e0, e1))
+                out_host[b0:b0 + brows].copy_(out_dev[b0:b0 + brows], non_blocking=True)  # result download
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in evs)
+
+        one_pass(False)   # warm-up (clocks, first-touch of the pinned pages)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ms_kernel = one_pass(True)
+        ms_e2e = (time.perf_counter() - t0) * 1e3
+        kernel = r.last_kernel()
+    t = torch.tensor([ms_kernel, ms_e2e, float(uploaded)], dtype=torch.float64, device=dev)
+    tsum = t.clone()
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tsum)
+        sizes = [sharding.band_shard(dh, world, q)[1] for q in range(world)]
+        parts = [torch.empty((n, dw), dtype=torch.uint8, device=dev) for n in sizes] if rank == 0 else None
+        dist.gather(out_dev, parts, dst=0)
+    else:
+        parts = [out_dev]
+    if rank != 0:
+        return None
+    h = vectors._FNV_BASIS
+    for p in parts:
+        h = vectors.fnv1a64(p.cpu().numpy(), h)
+    got = "%016x" % h
+    # rank 0's own band must also have come back through the D2H copy intact
+    d2h_ok = bool(torch.equal(out_host, out_dev.cpu()))
+    return {"workload": "cfg5 32768x32768 -> 12000x12000 Lanczos4, row bands + host-side halo", "n_gpus": world,
+            "bands_per_gpu": nb, "kernel": kernel, "ms_kernel": round(float(t[0]), 3), "ms_e2e": round(float(t[1]), 3),
+            "timing": "max over ranks; ms_kernel = sum of the rank's band launches (CUDA events), ms_e2e = wall clock of "
+                      "upload (pinned host -> device) + kernels + download of the rank's bands",
+            "gpix_s_kernel": round(dw * dh / float(t[0]) / 1e6, 1), "gpix_s_e2e": round(dw * dh / float(t[1]) / 1e6, 1),
+            "uploaded_bytes": int(tsum[2]), "uploaded_bytes_max_rank": int(t[2]), "source_bytes": sw * sh,
+            "downloaded_bytes": dw * dh, "fnv1a64": got, "golden": want, "hash_ok": got == want and d2h_ok}
+
+
+def run_e2e_single(iqo, local):
+    """The drop-in call itself: iqo::*Resizer::resize() == iqo_cuda_resize on ONE pageable host image (H2D, kernel,
+    D2H and a stream synchronise inside every call), median of 50 calls after 10 warm-up calls."""
+    import numpy as np
+    from libiqo_b200 import vectors
+    out = []
+    for name in ("cfg1_lanczos3_1080p_to_720p", "cfg2a_area_2160p_to_1080p", "cfg2b_linear_720p_to_2160p",
+                 "cfg4_lanczos3_1080p_to_540p"):
+        kind, deg, px, sw, sh, dw, dh, _ = WORKLOADS[name]
+        src = vectors.lcg_image(sh, sw, seed=1)
+        dst = np.zeros((dh, dw), dtype=np.uint8)
+        with iqo.make_resizer(kind, deg, sw, sh, dw, dh, px, device=local) as r:
+            for _ in range(10):
+                r.resize(sw, src, dw, dst)
+            ts = []
+            for _ in range(50):
+                t = time.perf_counter()
+                r.resize(sw, src, dw, dst)
+                ts.append(time.perf_counter() - t)
+            kernel = r.last_kernel()
+        want = vectors.golden_hash(kind, deg, px, sw, sh, dw, dh)
+        med = sorted(ts)[len(ts) // 2]
+        out.append({"workload": name, "us_per_call": round(med * 1e6, 1), "mpix_s": round(dw * dh / med / 1e6, 1),
+                    "kernel": kernel, "h2d_bytes": sw * sh, "d2h_bytes": dw * dh,
+                    "bit_exact": ("%016x" % vectors.fnv1a64(dst)) == want})
+    return {"api": "iqo_cuda_resize (what iqo::LanczosResizer::resize forwards to), pageable numpy buffers, one image per call",
+            "calls": out}
+
+
+def run_multi_device(torch, iqo, ndev):
+    """The in-process multi-device drivers (one host thread + stream per device) on all `ndev` devices: cfg5's ratio
+    as row bands against the committed golden hash, and a frame batch against single-device results."""
+    import numpy as np
+    from libiqo_b200 import vectors
+    devices = list(range(ndev))
+    sw, sh, dw, dh = 4096, 1024, 1500, 375
+    src = vectors.lcg_image(sh, sw, seed=4)
+    out = np.zeros((dh, dw), dtype=np.uint8)
+    t0 = time.perf_counter()
+    iqo.resize_bands_multi(0, 4, sw, sh, dw, dh, 1, sw, src, dw, out, devices)
+    t_b = time.perf_counter() - t0
+    bands_ok = ("%016x" % vectors.fnv1a64(out)) == vectors.golden_hash(0, 4, 1, sw, sh, dw, dh, seed=4)
+    n, sw, sh, dw, dh = 8 * ndev, 1920, 1080, 960, 540
+    frames = np.stack([vectors.lcg_image(sh, sw, seed=1)] * n)
+    outs = np.zeros((n, dh, dw), dtype=np.uint8)
+    t0 = time.perf_counter()
+    iqo.resize_batch_multi(0, 3, sw, sh, dw, dh, 1, n, sw, sw * sh, frames, dw, dw * dh, outs, devices)
+    t_f = time.perf_counter() - t0
+    batch_ok = ("%016x" % vectors.fnv1a64(outs[0])) == "bc3ae031361c0774" and bool((outs == outs[0]).all())
+    return {"devices": devices, "bands_multi_ok": bool(bands_ok), "bands_multi_ms": round(t_b * 1e3, 2),
+            "batch_multi_ok": bool(batch_ok), "batch_multi_ms": round(t_f * 1e3, 2),
+            "api": "iqo_cuda_resize_bands_multi / iqo_cuda_resize_batch_multi called from rank 0 (first call: includes plan + context setup)"}
+
+
 # ----------------------------------------------------------------------------- CUDA arm
 
 def run_cuda(args):
@@ -304,8 +611,9 @@ def _run_cuda(args, json_fd):
         torch.cuda.synchronize()
 
     sampler = ClockSampler(visible_physical_index(local)) if rank == 0 else None
+    warmup = max(args.warmup, 3)
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(warmup):
         step()
     barrier()
     launches0 = iqo.launch_count()
@@ -333,6 +641,10 @@ def _run_cuda(args, json_fd):
     total_px = float(nframes_all.item()) * dw * dh
     value = total_px / (ms_step * 1e-3) / 1e6
     kernel_name = r.last_kernel()
+    sm_mhz_headline = None
+    if sampler and sampler.samples:
+        s_ = sorted(sampler.samples)
+        sm_mhz_headline = s_[len(s_) // 2]
 
     # ---- parity of the timed configuration (outside the timed region): the planted frames of the batch the
     # timed launches wrote, against the committed hash of the reference's output (no oracle on this arm)
@@ -369,23 +681,76 @@ def _run_cuda(args, json_fd):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
         e2e_ok = bool(torch.equal(hd.to(dev), dst[:ef]))
+        h2d, d2h = ef * sw * sh, ef * dw * dh
         e2e = {"value": round(float(ef) * dw * dh * world * esteps / dt / 1e6, 1), "unit": UNIT,
-               "h2d_bytes_per_step": ef * sw * sh, "d2h_bytes_per_step": ef * dw * dh,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                "frames_per_step": ef, "steps": esteps, "ms_per_step": round(dt / esteps * 1e3, 3),
-               "api": "iqo_cuda_resize_batch_host (pinned host buffers, double-buffered H2D/kernel/D2H)",
+               "h2d_gbs_per_gpu": round(h2d * esteps / dt / 1e9, 2), "d2h_gbs_per_gpu": round(d2h * esteps / dt / 1e9, 2),
+               "api": "iqo_cuda_resize_batch_host (pinned host buffers, pipelined H2D / kernel / D2H)",
                "matches_device_run": e2e_ok}
+        # the same call on pageable (ordinary malloc) buffers: what a drop-in caller that knows nothing about CUDA passes
+        if rank == 0:
+            try:
+                pf = min(256, ef)
+                ps = np.empty((pf, sh, sw), dtype=np.uint8)
+                ps[:] = hs[:pf].numpy()
+                pd = np.zeros((pf, dh, dw), dtype=np.uint8)
+                r.resize_batch_host(pf, sw, sw * sh, ps, dw, dw * dh, pd)
+                t0 = time.perf_counter()
+                r.resize_batch_host(pf, sw, sw * sh, ps, dw, dw * dh, pd)
+                dtp = time.perf_counter() - t0
+                e2e["pageable"] = {"value": round(pf * dw * dh / dtp / 1e6, 1), "unit": UNIT, "frames": pf,
+                                   "matches_device_run": bool(np.array_equal(pd, dst[:pf].cpu().numpy()))}
+                del ps, pd
+            except Exception as e:
+                e2e["pageable"] = {"error": repr(e)}
+        del hs, hd
+
+    # ---- extra legs (outside the headline timed regions)
+    peak, peak_src = hbm_peak()
+    extras = {}
+    del src
+    torch.cuda.empty_cache()
+    if not args.no_extras:
+        if rank == 0:
+            wl = []
+            for name in EXTRA_WORKLOADS:
+                try:
+                    wl.append(run_extra_workload(torch, iqo, name, dev, local, peak, sm_mhz_headline))
+                except Exception as e:
+                    wl.append({"workload": name, "error": repr(e)})
+                torch.cuda.empty_cache()
+            try:
+                wl.insert(2, run_cfg3(torch, iqo, dev, peak, sm_mhz_headline))
+            except Exception as e:
+                wl.append({"workload": "cfg3_yuv420", "error": repr(e)})
+            torch.cuda.empty_cache()
+            extras["workloads"] = wl
+        barrier()
+        try:
+            extras["cfg5"] = run_cfg5(torch, iqo, dist, rank, world, local, dev)
+        except Exception as e:
+            extras["cfg5"] = {"error": repr(e)}
+        barrier()
+        if rank == 0:
+            try:
+                extras["e2e_single"] = run_e2e_single(iqo, local)
+            except Exception as e:
+                extras["e2e_single"] = {"error": repr(e)}
+            ndev = torch.cuda.device_count()
+            if world > 1 and ndev >= 2:
+                try:
+                    extras["multi_device"] = run_multi_device(torch, iqo, min(ndev, world))
+                except Exception as e:
+                    extras["multi_device"] = {"error": repr(e)}
+        barrier()
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
-    # ---- roofline of the dominant (only) kernel
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    # ---- roofline of the dominant (only) kernel of the headline step
     launches_per_step = max(1, launches // args.steps)
     alg_bytes = float(frames) * (sw * sh + dw * dh) / launches_per_step
     launch_ms = ms_step / launches_per_step
@@ -403,36 +768,40 @@ def _run_cuda(args, json_fd):
                 "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": round(launch_ms, 4),
                 "macs_per_dst_px": None}
     try:
-        # compute side: all taps counted, zeros included; the scalar-IMAD peak is the measured
-        # 64 lanes/clk/SM (profiles/r1_microbench_pipe_rates.txt) at the sampled SM clock.  dp4a/dp2a do 4/2 MACs
-        # per lane-instruction and mirrored taps are pre-added, so the achieved MAC rate may exceed that peak.
-        ny = iqo.plan_query(kind, deg, sw, sh, dw, dh, px, 1)["numCoefs"] if sh != dh else 1
-        nx = iqo.plan_query(kind, deg, sw, sh, dw, dh, px, 0)["numCoefs"] if sw != dw else 1
-        macs = (ny * sw * dh + nx * dw * dh) / float(dw * dh)
-        roofline["macs_per_dst_px"] = round(macs, 2)
-        roofline["achieved_tmac_s"] = round(value * 1e6 * macs / 1e12, 2)
-        roofline["imad_peak_tmac_s"] = round(148 * 64 * 1.965e9 / 1e12, 2)
+        mv, mh = macs_per_dst_px(iqo, kind, deg, px, sw, sh, dw, dh)
+        roofline["macs_per_dst_px"] = round(mv + mh, 2)
+        roofline["achieved_tmac_s"] = round(value / world * 1e6 * (mv + mh) / 1e12, 2)
+        b = both_bounds(alg_bytes * launches_per_step, float(frames) * dw * dh, mv, mh, ms_step, sm_mhz_headline, peak)
+        roofline["bounds"] = b
+        roofline["bound"] = b["bound"]
     except Exception:
         pass
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
-        res = time_cpu(work, seconds=args.cpu_seconds)
+        res = time_cpu(work, steps=args.steps, warmup=warmup)   # the reference arm's protocol
         cpu = {k: res[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        cpu["us_per_single_image_call"] = res["us_per_call"]
+        try:
+            # per-call time of the other single-image configs on the same host cores (beside e2e_single)
+            per_call = {}
+            for name in ("cfg1_lanczos3_1080p_to_720p", "cfg2a_area_2160p_to_1080p", "cfg2b_linear_720p_to_2160p"):
+                per_call[name] = time_cpu(WORKLOADS[name], steps=3, warmup=1, seconds=3.0, max_frames=16)["us_per_call"]
+            cpu["us_per_call"] = per_call
+        except Exception as e:
+            cpu["us_per_call"] = {"error": repr(e)}
 
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4),
+        "steps": args.steps, "warmup": warmup, "ms_per_step": round(ms_step, 4),
         "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "int32", "data": "synthetic",
-        "config": {"workload": args.workload, "frames_per_gpu": frames, "src": [sw, sh], "dst": [dw, dh],
-                   "kernel": kernel_name, "sharding": "independent frames per GPU, no collective",
-                   "cache": "inputs %.1f GB per GPU exceed the 126 MB L2 (no flush needed)"
-                            % (frames * sw * sh / 1e9),
-                   "timing": "CUDA events on the launch stream, max over ranks"},
+        "config": workload_config(args.workload, frames),
+        "detail": {"device": "B200", "kernel": kernel_name, "timing": "CUDA events on the launch stream, max over ranks"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": sampler.summary() if sampler else None, "parity": parity,
     }
+    line.update(extras)
     os.write(json_fd, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()

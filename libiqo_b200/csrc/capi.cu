@@ -104,6 +104,10 @@ EncodeTiledFn encodeTiled()
     return fn;
 }
 
+#ifndef IQO_STREAM_TMA_DEFAULT
+#define IQO_STREAM_TMA_DEFAULT 1
+#endif
+
 size_t alignUp(size_t v, size_t a)
 {
     return (v + a - 1) / a * a;
@@ -409,11 +413,27 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
             h.skipHi0 = hp.skipHi0;
             memcpy(h.cwXo, hp.cwXo, sizeof h.cwXo);
             r->lastKernel = hp.symmetric ? "half_sym_stream" : "half_stream";
+            // source FIFO fed by TMA (one box per turn) unless switched off or the descriptor cannot be built
+            static const int envStreamTma = [] { const char *e = getenv("IQO_CUDA_STREAM_TMA"); return e ? atoi(e) : IQO_STREAM_TMA_DEFAULT; }();
             for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
+                const size_t nf = std::min<size_t>(65535, nFrames - f0);
                 h.src = src + f0 * srcFrameStride;
                 h.dst = dst + f0 * dstFrameStride;
-                h.nFrames = int(std::min<size_t>(65535, nFrames - f0));
-                CUDA_TRY(launchHalfStream(h, stream));
+                h.nFrames = int(nf);
+                CUtensorMap smap;
+                bool tma = envStreamTma != 0 && r->useTma && encodeTiled() != 0;
+                if (tma) {
+                    // 16-bit view (a box dimension holds at most 256 elements): (x / 2, y, frame), box 136 x 4 NG x 1
+                    const cuuint64_t dims[3] = {cuuint64_t(h.SW / 2), cuuint64_t(h.SH), cuuint64_t(nf)};
+                    const cuuint64_t strides[2] = {cuuint64_t(srcSt), cuuint64_t(nf > 1 ? srcFrameStride : srcSt * size_t(h.SH))};
+                    const cuuint32_t box[3] = {136, cuuint32_t(halfStreamBoxRows(h.NG)), 1};
+                    const cuuint32_t estr[3] = {1, 1, 1};
+                    CUresult cr = encodeTiled()(&smap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint8_t *>(h.src), dims, strides,
+                                                box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    if (cr != CUDA_SUCCESS) tma = false;
+                }
+                CUDA_TRY(launchHalfStream(h, tma ? &smap : 0, stream));
             }
             return IQO_CUDA_OK;
         }

@@ -815,16 +815,46 @@ __host__ __device__ constexpr int streamWarpBytes(int NG)
     return 2 * NG * kStreamRowBytes + IQO_STREAM_FIFO_TURNS * NG * kStreamSlotBytes + kStreamSideRows * kStreamSideWords * 4;
 }
 
+// TMA-fed variant: the source FIFO is two boxes of one turn each (4 NG rows x 272 bytes, one
+// cp.async.bulk.tensor per turn issued by lane 0, completion on an mbarrier per box) instead of
+// 4 cp.async per lane and group.  The tensor map views the frames as 16-bit pairs (a box dimension
+// holds at most 256 elements): (x / 2, y, frame), box 136 x 4 NG x 1; rows and columns outside the
+// image arrive as zeros, which only ever meet zero coefficients.
+struct HalfStreamTmaArgs {
+    alignas(64) CUtensorMap tmap;
+    HalfArgs h;
+};
+template <bool TMA>
+struct StreamParam {
+    typedef HalfArgs type;
+    static __device__ __forceinline__ const HalfArgs &args(const HalfArgs &p) { return p; }
+};
+template <>
+struct StreamParam<true> {
+    typedef HalfStreamTmaArgs type;
+    static __device__ __forceinline__ const HalfArgs &args(const HalfStreamTmaArgs &p) { return p.h; }
+};
+__host__ __device__ constexpr int streamTmaBoxBytes(int NG)
+{
+    return (4 * NG * kStreamSrcRowBytes + 127) / 128 * 128;  // TMA destinations are 128-byte aligned
+}
+__host__ __device__ constexpr int streamTmaWarpBytes(int NG)
+{
+    return 2 * streamTmaBoxBytes(NG) + 2 * NG * kStreamRowBytes + kStreamSideRows * kStreamSideWords * 4 + 16;
+}
+
 // The loop runs in *turns* of NG row pairs (one revolution of the register ring), so that ring
 // positions, FIFO slots and W rows are compile-time constants and the per-pair bookkeeping is
 // paid once per turn: NG vertical passes, one __syncwarp, then the horizontal pass of the 2 NG rows.
-template <int NG, int NXH, bool SYM, bool SKIP0, int Z>
-__global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__ HalfArgs a)
+template <int NG, int NXH, bool SYM, bool SKIP0, int Z, bool TMA>
+__global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__ typename StreamParam<TMA>::type prm)
 {
-    extern __shared__ __align__(16) uint8_t streamSmem[];
+    extern __shared__ __align__(128) uint8_t streamSmem[];
+    const HalfArgs &a = StreamParam<TMA>::args(prm);
     constexpr int kBase = 5 - NXH / 2;  // pair word of taps 0, 1 of pixel 0
     constexpr int kFifo = IQO_STREAM_FIFO_TURNS * NG;      // groups in a lane's FIFO
     constexpr int kWBuf = 2 * NG * kStreamRowBytes;        // W rows of one turn
+    constexpr int kBox = streamTmaBoxBytes(NG);            // TMA: one box = the NG source groups of a turn
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tx0 = (blockIdx.x * kStreamWarps + warp) * kHalfTileW;
     if (tx0 >= a.DW) return;
@@ -836,10 +866,12 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
     uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
     const int xs0 = 2 * tx0 - 8;  // first source column of lane 0 (multiple of 8); W element i is column xs0 + i - 1
     const int txEnd = min(tx0 + kHalfTileW, a.DW);
-    uint8_t *warpSmem = streamSmem + warp * streamWarpBytes(NG);
-    const uint32_t wBase = smemAddr(warpSmem);
-    const uint32_t fifoBase = wBase + kWBuf;
-    uint32_t *side = reinterpret_cast<uint32_t *>(warpSmem + kWBuf + kFifo * kStreamSlotBytes);
+    // shared bytes of a warp: [W rows | FIFO | side] (cp.async) or [box 0 | box 1 | W rows | side | 2 mbarriers] (TMA)
+    uint8_t *warpSmem = streamSmem + warp * (TMA ? streamTmaWarpBytes(NG) : streamWarpBytes(NG));
+    const uint32_t fifoBase = smemAddr(warpSmem) + (TMA ? 0 : kWBuf);
+    const uint32_t wBase = smemAddr(warpSmem) + (TMA ? 2 * kBox : 0);
+    uint32_t *side = reinterpret_cast<uint32_t *>(warpSmem + (TMA ? 2 * kBox + kWBuf : kWBuf + kFifo * kStreamSlotBytes));
+    const uint32_t mbarBase = smemAddr(side) + kStreamSideRows * kStreamSideWords * 4;  // TMA only
 
     // source role: lanes 0..16 copy the 16-byte aligned chunks [xs0 - 8 + 16 lane, +16) of a source row (L1 bypassed);
     // chunks outside the image are zero-filled without a read, one that straddles the right edge reads 8 bytes
@@ -874,9 +906,10 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
     int sideRows = 0;
 
     // turns starting at pairs [kIntB, kIntE] (whole turn inside) touch no border row and request only rows inside the image
+    // (TMA: rows outside the image arrive as zeros, only the border rows matter)
     const int gAhead = a.qmin + NG - 1 + kFifo - 1;  // the step of pair k requests group k + gAhead
-    const int kIntB = max((a.mbY + 1) >> 1, -gAhead);
-    const int kIntE = min(min(a.meY >> 1, ((a.SH - a.delta) >> 2) - gAhead), k1);
+    const int kIntB = TMA ? (a.mbY + 1) >> 1 : max((a.mbY + 1) >> 1, -gAhead);
+    const int kIntE = TMA ? min(a.meY >> 1, k1) : min(min(a.meY >> 1, ((a.SH - a.delta) >> 2) - gAhead), k1);
 
     int g = k0 + a.qmin;  // next source group to request
     const uint8_t *gp = base + (long long)(4 * g + a.delta) * pitch;
@@ -906,10 +939,34 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
         gp += 4 * pitch;
         ++g;
     };
+    // TMA: box j of the band holds the source groups NG j - 1 ... NG j + NG - 2 (group 0 = k0 + qmin), i.e. box 0 the
+    // groups of the initial register ring and box t + 1 the groups turn t consumes; it lives in slot j & 1 and completes
+    // phase (j >> 1) & 1 of that slot's mbarrier.
+    const int boxX = tx0 - 8;                                      // u16 elements: byte column xs0 - 8
+    const int boxY0 = 4 * (k0 + a.qmin - 1) + a.delta;             // first row of box 0
+    auto issueBox = [&](const int j) {
+        if (lane == 0) {
+            const uint32_t bar = mbarBase + 8 * (j & 1);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "n"(4 * NG * kStreamSrcRowBytes) : "memory");
+            asm volatile(
+                "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                ::"r"(fifoBase + (j & 1) * kBox), "l"(reinterpret_cast<unsigned long long>(&prm)), "r"(boxX),
+                  "r"(boxY0 + 4 * NG * j), "r"((int)blockIdx.z), "r"(bar)
+                : "memory");
+        }
+    };
+    auto waitBox = [&](const int j) {
+        asm volatile(
+            "{\n\t.reg .pred q;\n\tIQO_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t@!q bra IQO_WAIT;\n\t}"
+            ::"r"(mbarBase + 8 * (j & 1)), "r"((j >> 1) & 1)
+            : "memory");
+    };
     // oldest requested group (slot `ra`) -> transposed columns: .x/.y/.z/.w = four vertical bytes of column 0..3 (A) and 4..7 (B)
     auto consume = [&](const uint32_t slot, uint4 &ca, uint4 &cb) {
-        asm volatile("cp.async.wait_group %0;" ::"n"(kFifo - 2) : "memory");
-        __syncwarp();  // the chunks were copied by other lanes; everybody has also read the slot refilled next
+        if (!TMA) {
+            asm volatile("cp.async.wait_group %0;" ::"n"(kFifo - 2) : "memory");
+            __syncwarp();  // the chunks were copied by other lanes; everybody has also read the slot refilled next
+        }
         const uint32_t ra = slot + 8 + 8 * lane;
         const uint2 r0 = ldsV2<0>(ra), r1 = ldsV2<kStreamSrcRowBytes>(ra), r2 = ldsV2<2 * kStreamSrcRowBytes>(ra),
                     r3 = ldsV2<3 * kStreamSrcRowBytes>(ra);
@@ -930,12 +987,28 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
     // n + kFifo - 1 goes out right after group n is read and lands in the slot read one step earlier.
     // Before the first turn: groups 0 .. NG-2 are in the register ring, groups up to NG + kFifo - 3 requested.
     uint4 winA[NG], winB[NG];
+    int boxJ = 1;  // TMA: box of the running turn
+    if (TMA) {
+        if (lane == 0) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarBase));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarBase + 8));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        issueBox(0);
+        issueBox(1);
+        waitBox(0);
 #pragma unroll
-    for (int j = 0; j < kFifo - 1; ++j) issue(BoolTag<true>(), fifoBase + j * kStreamSlotBytes);
+        for (int j = 0; j < NG - 1; ++j) consume(fifoBase + (j + 1) * kStreamSlotBytes, winA[j], winB[j]);
+        __syncwarp();  // box 0 has been read by every lane: its slot may be refilled
+    } else {
 #pragma unroll
-    for (int j = 0; j < NG - 1; ++j) {
-        consume(fifoBase + j * kStreamSlotBytes, winA[j], winB[j]);
-        issue(BoolTag<true>(), fifoBase + ((j + kFifo - 1) % kFifo) * kStreamSlotBytes);
+        for (int j = 0; j < kFifo - 1; ++j) issue(BoolTag<true>(), fifoBase + j * kStreamSlotBytes);
+#pragma unroll
+        for (int j = 0; j < NG - 1; ++j) {
+            consume(fifoBase + j * kStreamSlotBytes, winA[j], winB[j]);
+            issue(BoolTag<true>(), fifoBase + ((j + kFifo - 1) % kFifo) * kStreamSlotBytes);
+        }
     }
 
     // border columns of the parked rows; `yEnd` is the row after the last parked one
@@ -964,8 +1037,12 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
         const uint32_t ra = s == 0 ? fifoCur + (NG - 1) * kStreamSlotBytes : fifoOth + (s - 1) * kStreamSlotBytes;
         const uint32_t sa = s == 0 ? fifoCur + (NG - 2) * kStreamSlotBytes
                           : s == 1 ? fifoCur + (NG - 1) * kStreamSlotBytes : fifoOth + (s - 2) * kStreamSlotBytes;
-        consume(ra, winA[(s + NG - 1) % NG], winB[(s + NG - 1) % NG]);
-        issue(edgeTag, sa);
+        if (TMA) {
+            consume(fifoBase + (boxJ & 1) * kBox + s * kStreamSlotBytes, winA[(s + NG - 1) % NG], winB[(s + NG - 1) % NG]);
+        } else {
+            consume(ra, winA[(s + NG - 1) % NG], winB[(s + NG - 1) % NG]);
+            issue(edgeTag, sa);
+        }
 #pragma unroll
         for (int par = 0; par < 2; ++par) {
             uint32_t c0 = a.cwY[par][0], c1 = NG > 1 ? a.cwY[par][1] : 0u, c2 = NG > 2 ? a.cwY[par][2] : 0u;
@@ -1029,6 +1106,10 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
     };
 
     for (int k = k0; k < k1; k += NG) {
+        if (TMA) {
+            if (k + NG < k1) issueBox(boxJ + 1);  // next turn's groups, into the slot the previous turn has finished with
+            waitBox(boxJ);
+        }
         if (k >= kIntB && k + NG <= kIntE) {
             vertical(BoolTag<false>(), std::integral_constant<int, 0>(), k);
             if (NG > 1) vertical(BoolTag<false>(), std::integral_constant<int, 1 % NG>(), k + 1);
@@ -1041,7 +1122,21 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
         __syncwarp();
         // horizontal pass of the turn's row pairs that belong to the band: lane = (row of the pair, 8-pixel group)
         const int np = min(NG, k1 - k);
-        if (hmode != 0) {
+        if (hmode == 1 && k + NG <= k1 && 2 * (k + NG) <= a.DH) {
+            // whole turn inside the band and the image, 8-byte stores: no per-row checks
+#pragma unroll
+            for (int i = 0; i < NG; ++i) {
+                uint32_t n[16];
+                const uint32_t wl = wld + i * 2 * kStreamRowBytes;
+                const uint4 q0 = ldsV4<0>(wl), q1 = ldsV4<16>(wl), q2 = ldsV4<32>(wl), q3 = ldsV4<48>(wl);
+                n[0] = q0.x, n[1] = q0.y, n[2] = q0.z, n[3] = q0.w;
+                n[4] = q1.x, n[5] = q1.y, n[6] = q1.z, n[7] = q1.w;
+                n[8] = q2.x, n[9] = q2.y, n[10] = q2.z, n[11] = q2.w;
+                n[12] = q3.x, n[13] = q3.y, n[14] = q3.z, n[15] = q3.w;
+                const uint2 o = halfGroupPixelsOdd<NXH, SYM, SKIP0>(a, n);
+                *reinterpret_cast<uint2 *>(outp + i * ostep) = o;
+            }
+        } else if (hmode != 0) {
             uint32_t wl = wld;
             uint8_t *op = outp;
 #pragma unroll
@@ -1065,7 +1160,9 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
         }
         outp += NG * ostep;
         __syncwarp();  // the W rows are free again
-        if (IQO_STREAM_FIFO_TURNS > 1) {
+        if (TMA) {
+            ++boxJ;
+        } else if (IQO_STREAM_FIFO_TURNS > 1) {
             const uint32_t t = fifoCur;
             fifoCur = fifoOth;
             fifoOth = t;
@@ -1076,24 +1173,38 @@ __global__ void IQO_STREAM_BOUNDS resizeHalfStreamKernel(const __grid_constant__
             if (sideRows + 2 * NG > kStreamSideRows || k + NG >= k1) flush(2 * (k + np));
         }
     }
-    asm volatile("cp.async.wait_all;" ::: "memory");
+    if (!TMA) asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 template <int NG, int NXH, bool SYM, bool SKIP0, int Z>
-cudaError_t launchHalfStreamT(const HalfArgs &a, cudaStream_t stream)
+cudaError_t launchHalfStreamT(const HalfArgs &a, const CUtensorMap *tmap, cudaStream_t stream)
 {
     const int strips = (a.DW + kHalfTileW - 1) / kHalfTileW;
     const int pairs = (a.DH + 1) / 2;
     dim3 grid((strips + kStreamWarps - 1) / kStreamWarps, (pairs + a.bandPairs - 1) / a.bandPairs, a.nFrames);
-    constexpr int smem = kStreamWarps * streamWarpBytes(NG);
-    static PerDeviceOnce attrSet;  // per instantiation; a benign race sets it twice at worst
     const int dev = currentDevice();
-    if (!attrSet.done(dev)) {
-        cudaError_t e = cudaFuncSetAttribute(resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-        if (e != cudaSuccess) return e;
-        attrSet.set(dev);
+    if (tmap) {
+        constexpr int smem = kStreamWarps * streamTmaWarpBytes(NG);
+        static PerDeviceOnce attrSet;  // per instantiation; a benign race sets it twice at worst
+        if (!attrSet.done(dev)) {
+            cudaError_t e = cudaFuncSetAttribute(resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            attrSet.set(dev);
+        }
+        HalfStreamTmaArgs p;
+        p.tmap = *tmap;
+        p.h = a;
+        resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z, true><<<grid, 32 * kStreamWarps, smem, stream>>>(p);
+    } else {
+        constexpr int smem = kStreamWarps * streamWarpBytes(NG);
+        static PerDeviceOnce attrSet;
+        if (!attrSet.done(dev)) {
+            cudaError_t e = cudaFuncSetAttribute(resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            if (e != cudaSuccess) return e;
+            attrSet.set(dev);
+        }
+        resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z, false><<<grid, 32 * kStreamWarps, smem, stream>>>(a);
     }
-    resizeHalfStreamKernel<NG, NXH, SYM, SKIP0, Z><<<grid, 32 * kStreamWarps, smem, stream>>>(a);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -2146,13 +2257,18 @@ bool halfStreamHasKernel(int NG, int NXH)
     return (NG == 2 || NG == 3) && (NXH == 2 || NXH == 4 || NXH == 6);
 }
 
-cudaError_t launchHalfStream(const HalfArgs &a, cudaStream_t stream)
+int halfStreamBoxRows(int NG)
+{
+    return 4 * NG;
+}
+
+cudaError_t launchHalfStream(const HalfArgs &a, const CUtensorMap *tmap, cudaStream_t stream)
 {
 #define IQO_STREAM_CASE(G, NH, ZM)                                                              \
     if (a.NG == G && a.NXH == NH && a.zmask == ZM)                                              \
-        return !a.symmetric ? launchHalfStreamT<G, NH, false, false, ZM>(a, stream)             \
-               : a.skipHi0  ? launchHalfStreamT<G, NH, true, true, ZM>(a, stream)               \
-                            : launchHalfStreamT<G, NH, true, false, ZM>(a, stream);
+        return !a.symmetric ? launchHalfStreamT<G, NH, false, false, ZM>(a, tmap, stream)       \
+               : a.skipHi0  ? launchHalfStreamT<G, NH, true, true, ZM>(a, tmap, stream)         \
+                            : launchHalfStreamT<G, NH, true, false, ZM>(a, tmap, stream);
     IQO_STREAM_CASE(3, 6, 0)
     IQO_STREAM_CASE(3, 4, 0)
     IQO_STREAM_CASE(3, 2, 0)

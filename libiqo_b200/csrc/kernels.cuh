@@ -83,7 +83,10 @@ cudaError_t launchHalf(const HalfArgs &a, const CUtensorMap *tmap, int boxRows, 
 int halfSourceRowsMax();
 // Streaming variant: a warp per (120-pixel column strip, band of a.bandPairs row pairs, frame).
 // Needs 16-byte aligned source rows and SW % 8 == 0; at most 65535 frames and bands per launch.
-cudaError_t launchHalfStream(const HalfArgs &a, cudaStream_t stream);
+// tmap != NULL: the source FIFO is fed by TMA through a 3-D tensor map over a 16-bit view of the frames
+// (x / 2, y, frame) with box 136 x halfStreamBoxRows(NG) x 1; NULL: by cp.async chunks.
+cudaError_t launchHalfStream(const HalfArgs &a, const CUtensorMap *tmap, cudaStream_t stream);
+int halfStreamBoxRows(int NG);
 bool halfStreamHasKernel(int NG, int NXH);
 
 // Arguments of the general packed kernel (see plan.hpp PackedPlan).

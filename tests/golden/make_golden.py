@@ -75,6 +75,13 @@ LARGE = [
     (AREA, 0, 1, 1000, 1000, 333, 777, 8, 3, 6, None),
     (LINEAR, 0, 1, 960, 540, 1920, 1080, 0, 0, 7, None),
     (LINEAR, 0, 1, 640, 480, 1600, 1000, 0, 1, 8, None),
+    (LANCZOS, 4, 1, 8192, 8192, 3000, 3000, 0, 0, 1, None),  # bench.py's cfg5s workload (cfg5's ratio, batch-sized)
+]
+
+# BASELINE config 5 at full size (1 GiB source): hash only, kept out of LARGE so that the per-case tests do
+# not iterate over it (tests/test_oracle.py and tests/test_gpu_bands.py have dedicated full-size tests)
+HUGE = [
+    (LANCZOS, 4, 1, 32768, 32768, 12000, 12000, 0, 0, 1, "0ec3dba9ab1194ca"),
 ]
 
 
@@ -104,11 +111,20 @@ def main():
             assert h == expect, (c, h)
         large_meta.append(list(c[:10]) + [h])
         print(c[:10], h)
+    huge_meta = []
+    for c in HUGE:
+        kind, deg, px, sw, sh, dw, dh, spad, dpad, seed, expect = c
+        rc, dst = ref_resize(kind, case_src(c), dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+        assert rc == 0
+        h = "%016x" % fnv1a(dst, dw)
+        assert h == expect, (c, h)
+        huge_meta.append(list(c[:10]) + [h])
+        print(c[:10], h)
     with open(os.path.join(HERE, "cases.json"), "w") as f:
         json.dump({"generator": "tests/golden/make_golden.py (reference Generic via oracle/_ref)",
                    "fields": ["kind", "degree", "pxScale", "srcW", "srcH", "dstW", "dstH",
                               "srcStridePad", "dstStridePad", "seed", "(large only) fnv1a64 of dst"],
-                   "small": small_meta, "large": large_meta}, f, indent=1)
+                   "small": small_meta, "large": large_meta, "huge": huge_meta}, f, indent=1)
 
 
 if __name__ == "__main__":

@@ -74,7 +74,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true", help="skip workloads / cfg5 / e2e_single / multi_device")
-    ap.add_argument("--path", default="auto", choices=["auto", "generic", "no_tma", "no_stream", "stream"])
+    ap.add_argument("--path", default="auto", choices=["auto", "generic", "no_tma", "no_stream", "stream", "mma", "no_mma"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: every GPU gets the workload's frame count; strong: that count is sharded over the GPUs")
     return ap.parse_args()
@@ -599,7 +599,7 @@ def _run_cuda(args, json_fd):
     dst = torch.zeros((frames, dh, dw), dtype=torch.uint8, device=dev)
     r = iqo.make_resizer(kind, deg, sw, sh, dw, dh, px, device=local)
     r.set_path({"generic": iqo.PATH_GENERIC, "no_tma": iqo.PATH_NO_TMA, "no_stream": iqo.PATH_NO_STREAM,
-                "stream": iqo.PATH_STREAM}.get(args.path, iqo.PATH_AUTO))
+                "stream": iqo.PATH_STREAM, "mma": iqo.PATH_MMA, "no_mma": iqo.PATH_NO_MMA}.get(args.path, iqo.PATH_AUTO))
     stream = torch.cuda.current_stream().cuda_stream
 
     def step():

@@ -62,9 +62,12 @@ enum {
                                   when the source pitch or base is not 8/16-byte aligned)          */
     IQO_CUDA_PATH_NO_STREAM = 3, /* like AUTO, but without the warp-streaming kernels: 2:1 Lanczos uses
                                   the tiled (TMA) kernel, other Lanczos ratios the general packed one */
-    IQO_CUDA_PATH_STREAM = 4    /* like AUTO, but the warp-streaming kernels also take launches that are
+    IQO_CUDA_PATH_STREAM = 4,   /* like AUTO, but the warp-streaming kernels also take launches that are
                                   too small to fill the GPU with one warp per strip (AUTO gives those
                                   to the tiled / packed kernels, which start faster)                */
+    IQO_CUDA_PATH_MMA = 5,      /* Lanczos: the tensor-path kernel (both passes as integer mma.sync matrix
+                                  products) takes every launch it is eligible for, small ones too     */
+    IQO_CUDA_PATH_NO_MMA = 6    /* like AUTO, but never the tensor-path kernel                        */
 };
 
 /* Replaces: I{Lanczos,Area,Linear}ResizerImpl::init (reference src/IQOLanczosResizerImpl.hpp:17-22,

@@ -18,10 +18,10 @@ import ctypes as C
 import os
 
 __all__ = ["LanczosResizer", "AreaResizer", "LinearResizer", "Yuv420Resizer", "IqoCudaError", "lib", "build",
-           "LANCZOS", "AREA", "LINEAR", "PATH_AUTO", "PATH_GENERIC", "PATH_NO_TMA", "PATH_NO_STREAM", "PATH_STREAM", "exported_symbols"]
+           "LANCZOS", "AREA", "LINEAR", "PATH_AUTO", "PATH_GENERIC", "PATH_NO_TMA", "PATH_NO_STREAM", "PATH_STREAM", "PATH_MMA", "PATH_NO_MMA", "exported_symbols"]
 
 LANCZOS, AREA, LINEAR = 0, 1, 2
-PATH_AUTO, PATH_GENERIC, PATH_NO_TMA, PATH_NO_STREAM, PATH_STREAM = 0, 1, 2, 3, 4
+PATH_AUTO, PATH_GENERIC, PATH_NO_TMA, PATH_NO_STREAM, PATH_STREAM, PATH_MMA, PATH_NO_MMA = 0, 1, 2, 3, 4, 5, 6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libiqo_cuda.so")

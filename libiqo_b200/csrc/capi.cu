@@ -104,6 +104,15 @@ EncodeTiledFn encodeTiled()
     return fn;
 }
 
+#ifndef IQO_MMA_WARPS_DEFAULT
+#define IQO_MMA_WARPS_DEFAULT 4
+#endif
+#ifndef IQO_MMA_AUTO_DEFAULT
+#define IQO_MMA_AUTO_DEFAULT 1
+#endif
+#ifndef IQO_MMA_WCOLS_DEFAULT
+#define IQO_MMA_WCOLS_DEFAULT 272
+#endif
 #ifndef IQO_STREAM_TMA_DEFAULT
 #define IQO_STREAM_TMA_DEFAULT 1
 #endif
@@ -125,6 +134,7 @@ struct SharedPlan {
     SmallPlan small;
     RatioPlan ratio;
     LStreamPlan lstream;
+    MmaPlan mma;
     PackedPlan packed;
     GenericGeom geom;
     PackedGeom pgeom;
@@ -140,8 +150,11 @@ struct SharedPlan {
     int32_t *gRowRec;     // general Lanczos streaming path
     int32_t *sRowsY;      // small-kernel path
     uint32_t *sMagicY;
+    // tensor-path kernel tables
+    int32_t *mVBlock, *mVRow, *mStripXs, *mHTile, *mHCol;
+    uint32_t *mVFrag, *mHFrag;
     SharedPlan()
-        : device(0), dBorderY(0), dMagicY(0), dSBorderY(0), dBorderX(0), dBorderXo(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), rRowRec(0), gRowRec(0), sRowsY(0), sMagicY(0)
+        : device(0), dBorderY(0), dMagicY(0), dSBorderY(0), dBorderX(0), dBorderXo(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), rRowRec(0), gRowRec(0), sRowsY(0), sMagicY(0), mVBlock(0), mVRow(0), mStripXs(0), mHTile(0), mHCol(0), mVFrag(0), mHFrag(0)
     {
     }
     ~SharedPlan();
@@ -174,7 +187,7 @@ struct iqo_cuda_resizer {
     cudaStream_t *stream;
     uint8_t **dSrc, **dDst;
     int device;
-    bool useTma, useStream, forceStream;
+    bool useTma, useStream, forceStream, useMma, forceMma;
     int path;
     const char *lastKernel;
     size_t srcPitch, dstPitch;  // device pitches of the staging frames
@@ -183,7 +196,7 @@ struct iqo_cuda_resizer {
     iqo_cuda_resizer(const std::shared_ptr<SharedPlan> &s, Workspace *w)
         : sp(s), ws(w), plan(s->plan), half(s->half), tx(s->tx), ty(s->ty), geom(s->geom), dBorderY(s->dBorderY),
           dMagicY(s->dMagicY), dBorderX(s->dBorderX), stream(w->stream), dSrc(w->dSrc), dDst(w->dDst), device(s->device),
-          useTma(true), useStream(true), forceStream(false), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
+          useTma(true), useStream(true), forceStream(false), useMma(true), forceMma(false), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
     {
     }
 };
@@ -233,6 +246,13 @@ SharedPlan::~SharedPlan()
     cudaFree(sMagicY);
     cudaFree(pMagicY);
     cudaFree(pCwX);
+    cudaFree(mVBlock);
+    cudaFree(mVRow);
+    cudaFree(mStripXs);
+    cudaFree(mHTile);
+    cudaFree(mHCol);
+    cudaFree(mVFrag);
+    cudaFree(mHFrag);
     cudaGetLastError();
 }
 
@@ -271,6 +291,17 @@ bool isDevicePointer(const void *p)
     return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
 }
 
+// AUTO gives a launch to the tensor-path kernel when it has enough warps (strip x band) to fill the device
+bool mmaWorthIt(const iqo_cuda_resizer *r, size_t nFrames, size_t dstRows)
+{
+    static const int envAuto = [] { const char *e = getenv("IQO_CUDA_MMA_AUTO"); return e ? atoi(e) : IQO_MMA_AUTO_DEFAULT; }();
+    if (!envAuto) return false;
+    const MmaPlan &mp = r->sp->mma;
+    if (!mp.eligible || mp.stripTiles <= 0) return false;
+    const long long strips = ((r->plan.x.D + 7) / 8 + mp.stripTiles - 1) / mp.stripTiles;
+    return strips * (long long)((dstRows + 31) / 32) * (long long)nFrames >= 4ll * r->sp->sms;
+}
+
 int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, size_t srcRow0, size_t srcRows,
            size_t srcSt, size_t srcFrameStride, const uint8_t *src,
            size_t dstSt, size_t dstFrameStride, uint8_t *dst, cudaStream_t stream)
@@ -293,6 +324,82 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
     a.lanczos = r->plan.kind == kLanczos;
     a.workSigned = r->plan.workSigned;
     const bool whole = dstRow0 == 0 && dstRows == size_t(r->plan.y.D) && srcRow0 == 0;
+    // Lanczos, both passes on the integer tensor path (any ratio, row bands included)
+    auto tryMma = [&]() -> int {
+        if (!(r->useMma && r->sp->mma.eligible && ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 && (nFrames == 1 || srcFrameStride % 16 == 0))) return 0;
+        {
+        const SharedPlan &sp = *r->sp;
+        const MmaPlan &mp = sp.mma;
+        MmaArgs q;
+        q.dstPitch = (long long)dstSt;
+        q.dstFrameStride = (long long)dstFrameStride;
+        q.DW = int(r->plan.x.D);
+        q.srcRow0 = int(srcRow0);
+        q.dstRow0 = int(dstRow0);
+        q.dstRows = int(dstRows);
+        q.stripTiles = mp.stripTiles;
+        q.wcols = mp.wcols;
+        q.vKMax = mp.vKMax;
+        q.hKMax = mp.hKMax;
+        q.nChunks = mp.nChunks;
+        static const int envMmaWarps = [] { const char *e = getenv("IQO_CUDA_MMA_WARPS"); return e ? atoi(e) : IQO_MMA_WARPS_DEFAULT; }();
+        q.warps = (envMmaWarps == 1 || envMmaWarps == 2 || envMmaWarps == 4) ? envMmaWarps : IQO_MMA_WARPS_DEFAULT;
+        q.workBias = mp.workBias;
+        q.mbY = int(r->plan.y.mainBegin);
+        q.meY = int(r->plan.y.mainEnd);
+        q.mbX = int(r->plan.x.mainBegin);
+        q.meX = int(r->plan.x.mainEnd);
+        q.dstVec = ((uintptr_t)dst % 16) == 0 && dstSt % 16 == 0 && dstFrameStride % 16 == 0;
+        q.vBlock = reinterpret_cast<const int2 *>(sp.mVBlock);
+        q.vFrag = reinterpret_cast<const uint4 *>(sp.mVFrag);
+        q.vRow = reinterpret_cast<const int2 *>(sp.mVRow);
+        q.stripXs = sp.mStripXs;
+        q.hTile = reinterpret_cast<const int2 *>(sp.mHTile);
+        q.hFrag = reinterpret_cast<const uint4 *>(sp.mHFrag);
+        q.hCol = reinterpret_cast<const int2 *>(sp.mHCol);
+        // bands of whole 16-row blocks: enough warps to fill the device several times over
+        const long long strips = ((q.DW + 7) / 8 + q.stripTiles - 1) / q.stripTiles;
+        const long long blocks = (long long)((dstRow0 + dstRows + 15) / 16 - dstRow0 / 16);
+        int bandBlocks = 16;
+        static const int envBand = [] { const char *e = getenv("IQO_CUDA_MMA_BAND_BLOCKS"); return e ? atoi(e) : 0; }();
+        if (envBand > 0) bandBlocks = envBand;
+        else
+            while (bandBlocks > 4 && strips * ((blocks + bandBlocks - 1) / bandBlocks) * (long long)nFrames < 4ll * sp.sms * 4) bandBlocks /= 2;
+        q.bandBlocks = bandBlocks;
+        const size_t smem = mmaSmemBytes(q.wcols, q.stripTiles, q.nChunks, q.hKMax);
+        if (smem <= 200 * 1024 && (blocks + bandBlocks - 1) / bandBlocks <= 65535) {
+            bool ok = true;
+            for (size_t f0 = 0; f0 < nFrames && ok; f0 += 65535) {
+                const size_t nf = std::min<size_t>(65535, nFrames - f0);
+                q.nFrames = int(nf);
+                q.dst = dst + f0 * dstFrameStride;
+                const uint8_t *fsrc = src + f0 * srcFrameStride;
+                CUtensorMap tmap;
+                // 16-bit view of the source rows present in the buffer: (x / 2, y, frame), box (wcols / 2) x 8 x 1
+                const cuuint64_t dims[3] = {cuuint64_t(r->plan.x.S / 2), cuuint64_t(srcRows), cuuint64_t(nf)};
+                const cuuint64_t strides[2] = {cuuint64_t(srcSt), cuuint64_t(nf > 1 ? srcFrameStride : srcSt * srcRows)};
+                const cuuint32_t box[3] = {cuuint32_t(q.wcols / 2), cuuint32_t(kMmaChunkRows), 1};
+                const cuuint32_t estr[3] = {1, 1, 1};
+                CUresult cr = encodeTiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint8_t *>(fsrc), dims, strides,
+                                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (cr != CUDA_SUCCESS) {
+                    ok = false;   // e.g. a stride the descriptor cannot express: other kernels take the launch
+                    if (f0 != 0) return fail(IQO_CUDA_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(cr));
+                    break;
+                }
+                r->lastKernel = "lanczos_mma";
+                CUDA_TRY(launchMma(q, tmap, stream));
+            }
+            if (ok) return 1;
+        }
+        }
+        return 0;
+    };
+    if (r->forceMma) {
+        const int rc = tryMma();
+        if (rc != 0) return rc < 0 ? rc : IQO_CUDA_OK;
+    }
     // 2:1 Lanczos with at most four non-zero taps per axis (YUV420 chroma planes): streaming kernel
     if (r->path == IQO_CUDA_PATH_AUTO && r->sp->small.eligible && whole && ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 &&
         srcFrameStride % 16 == 0 && ((uintptr_t)dst % 8) == 0 && dstSt % 8 == 0 && dstFrameStride % 8 == 0) {
@@ -552,7 +659,13 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
             return IQO_CUDA_OK;
         }
     }
-    // Lanczos at any other ratio, row bands included: general streaming kernel
+    // Lanczos at any other ratio, row bands included: the tensor-path kernel when the launch is big enough
+    // (measured on B200, cfg5's ratio: 0.72 ms against 1.13 ms for the general streaming kernel below)
+    if (!r->forceMma && mmaWorthIt(r, nFrames, dstRows)) {
+        const int rc = tryMma();
+        if (rc != 0) return rc < 0 ? rc : IQO_CUDA_OK;
+    }
+    // ... else the general streaming kernel
     // (cross-over against the packed kernel, warm back-to-back launches of cfg5's row bands, tools/gigapixel.py --bands:
     //  42 warps per SM at the shortest band 0.154 vs 0.280 ms, 11 per SM 48 vs 61 us, 5.4 per SM 35 vs 31 us)
     if (r->useStream && sp.lstream.eligible && ((uintptr_t)src % 8) == 0 && srcSt % 8 == 0 && srcFrameStride % 8 == 0 &&
@@ -781,6 +894,16 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
             sp->lstream.eligible = false;
         }
     }
+    static const int envMmaWcols = [] { const char *e = getenv("IQO_CUDA_MMA_WCOLS"); return e ? atoi(e) : 0; }();
+    buildMmaPlan(sp->plan, sp->mma, envMmaWcols > 0 ? envMmaWcols : IQO_MMA_WCOLS_DEFAULT);
+    if (sp->mma.eligible) {
+        const MmaPlan &q = sp->mma;
+        if (encodeTiled() == 0 || !uploadVec(sp->mVBlock, q.vBlock) || !uploadVec(sp->mVRow, q.vRow) || !uploadVec(sp->mStripXs, q.stripXs) ||
+            !uploadVec(sp->mHTile, q.hTile) || !uploadVec(sp->mHCol, q.hCol) || !uploadVec(sp->mVFrag, q.vFrag) || !uploadVec(sp->mHFrag, q.hFrag)) {
+            cudaGetLastError();
+            sp->mma.eligible = false;
+        }
+    }
     out = sp;
     return IQO_CUDA_OK;
 }
@@ -995,10 +1118,12 @@ int iqo_cuda_sync(iqo_cuda_resizer *r)
 
 int iqo_cuda_set_path(iqo_cuda_resizer *r, int path)
 {
-    if (!r || path < 0 || path > IQO_CUDA_PATH_STREAM) return fail(IQO_CUDA_E_ARG, "bad path");
+    if (!r || path < 0 || path > IQO_CUDA_PATH_NO_MMA) return fail(IQO_CUDA_E_ARG, "bad path");
     r->useTma = (path != IQO_CUDA_PATH_NO_TMA);
-    r->useStream = (path == IQO_CUDA_PATH_AUTO || path == IQO_CUDA_PATH_STREAM);
+    r->useStream = (path == IQO_CUDA_PATH_AUTO || path == IQO_CUDA_PATH_STREAM || path == IQO_CUDA_PATH_NO_MMA);
     r->forceStream = (path == IQO_CUDA_PATH_STREAM);
+    r->useMma = (path == IQO_CUDA_PATH_AUTO || path == IQO_CUDA_PATH_MMA);
+    r->forceMma = (path == IQO_CUDA_PATH_MMA);
     r->path = (path == IQO_CUDA_PATH_GENERIC) ? IQO_CUDA_PATH_GENERIC : IQO_CUDA_PATH_AUTO;
     return IQO_CUDA_OK;
 }

@@ -202,6 +202,7 @@ __device__ __forceinline__ int swzWord(int word)
     return ((chunk ^ ((chunk >> 3) & 1)) << 2) | (word & 3);
 }
 
+constexpr int kMmaMaxKStepsDev = 3;  // plan.hpp kMmaMaxKSteps
 constexpr int kHalfTileW = 120;     // destination columns per tile
 constexpr int kHalfRowWords = 128;  // W row: 256 u16 = 128 words
 constexpr int kHalfMaxRows = 64;    // destination rows per tile (<=)
@@ -2172,7 +2173,395 @@ cudaError_t launchLStreamT(const LStreamArgs &a, cudaStream_t stream)
     return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tensor-path Lanczos kernel (plan.hpp MmaPlan): any ratio, phase count and row band.  Both passes are banded
+// integer matrix products on the legacy integer tensor path (mma.sync.m16n8k32, SASS IMMA.16832: measured on
+// B200 at 2048 MAC/clk/SM against 256 for dp4a, tools/mma_probe.cu), exact like every integer sum.
+//   A warp (one per CTA) owns a strip of destination columns and walks down 16-row destination blocks.
+//   source      raw source rows travel global -> shared by TMA in chunks of 16 rows (circular FIFO of a.nChunks chunks,
+//               an mbarrier per chunk); the chunks the next block needs are requested right after the vertical pass of
+//               the running block, so their latency hides behind its horizontal pass.
+//   vertical    per 16 source columns: ldmatrix.m16n16.trans.b8 turns 32 source rows x 16 columns straight into the
+//               B fragments (four vertically adjacent bytes per register -- no PRMT transposes, no lane-private ring);
+//               the A fragments are the block's coefficient bytes from the planner (1 - 3 k-steps of 32 source rows);
+//               results + bias are packed to 16-bit pairs and written with stmatrix into the block's W tile.
+//   horizontal  per 8 destination columns: ldmatrix of W (16 rows x 32 columns per k-step), PRMT splits the low and
+//               high bytes (the k order inside a fragment is {2t, 2t+1, 8+2t, 9+2t}; the planner permutes the
+//               coefficient fragments the same way), four mma per k-step (W low/high byte x coefficient low/high
+//               plane), recombination, rounding shift or border division, saturation.
+//   output      the block's 16 x stripW result tile is staged in shared memory and leaves as 16-byte row pieces.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void mmaS8U8(int (&d)[4], const uint4 &a, uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+// k = 16 form: the B operand is a single register (ldmatrix.m16n16.trans.b8 hands out the two 16-row halves of a
+// 32-row k range in registers that are not adjacent, which the k = 32 form would need)
+__device__ __forceinline__ void mmaS8U8k16(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t b)
+{
+    asm("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(b));
+}
+// first product of a chain: the accumulator input is (cLo, cLo, cHi, cHi) -- no register copies to initialise d
+__device__ __forceinline__ void mmaS8U8k16Init(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t b, int cLo, int cHi)
+{
+    asm("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%8,%8};"
+                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a0), "r"(a1), "r"(b), "r"(cLo), "r"(cHi));
+}
+__device__ __forceinline__ void mmaU8U8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void mmaU8S8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
+{
+    asm("mma.sync.aligned.m16n8k32.row.col.s32.u8.s8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct MmaKernelArgs {
+    alignas(64) CUtensorMap tmap;
+    MmaArgs a;
+};
+
+__host__ __device__ constexpr int mmaWStride(int wcols) { return 2 * wcols + 16; }          // bytes; (stride / 16) is odd
+__host__ __device__ constexpr int mmaOutStride(int stripTiles) { return (8 * stripTiles + 15) / 16 * 16 + 16 + ((((8 * stripTiles + 15) / 16) & 1) ? 16 : 0); }   // multiple of 16, odd number of 16-byte units: the 8 rows of an epilogue store fall on different banks
+// shared bytes of a warp: [FIFO chunks | W tile | output tile | strip tables: B fragments, W offsets, {init, divisor} | mbarriers]
+__host__ __device__ constexpr int mmaTableBytes(int stripTiles, int hks) { return stripTiles * (hks * 512 + 8 + 64); }
+constexpr int kMmaChunk = 8;   // plan.hpp kMmaChunkRows
+
+#ifndef IQO_MMA_MINB
+#define IQO_MMA_MINB 8
+#endif
+// VKS / HKS: k-steps of the vertical / horizontal products.  Blocks and tiles that need fewer carry zero coefficient
+// fragments for the rest (the planner's tables are zero padded), so the loops have no data-dependent structure.
+// The warps of a CTA (a.warps = 1, 2 or 4) share one strip: FIFO, W tile, output tile and tables are common, the
+// segments of the vertical pass, the tiles of the horizontal pass and the rows of the store are dealt out round robin;
+// two CTA barriers per block separate the phases.
+template <int VKS, int HKS>
+__global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(const __grid_constant__ MmaKernelArgs prm)
+{
+    extern __shared__ __align__(128) uint8_t mmaSmem[];
+    const MmaArgs &a = prm.a;
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int strip = blockIdx.x;
+    const int T0 = strip * a.stripTiles;                        // first destination tile of the strip
+    const int tx0 = 8 * T0;
+    const int nt = min(a.stripTiles, (a.DW + 7) / 8 - T0);      // tiles of this strip
+    const int tw = min(8 * nt, a.DW - tx0);                     // destination columns of this strip
+    const int xs = __ldg(a.stripXs + strip);                    // source column of W element 0
+    const int rowBytes = a.wcols;                               // FIFO row
+    const int chunkBytes = kMmaChunk * rowBytes;
+    const int chunkMask = a.nChunks - 1;                        // nChunks is a power of two
+    const int wStride = mmaWStride(a.wcols), oStride = mmaOutStride(a.stripTiles);
+    const uint32_t fifoBase = smemAddr(mmaSmem);
+    const uint32_t wBase = fifoBase + a.nChunks * chunkBytes;
+    uint8_t *oTile = mmaSmem + a.nChunks * chunkBytes + 16 * wStride;
+    uint8_t *tabs = oTile + 16 * oStride;
+    uint4 *sFrag = reinterpret_cast<uint4 *>(tabs);                                        // [tile][HKS][lane]
+    int *sOff = reinterpret_cast<int *>(tabs + a.stripTiles * HKS * 512);                  // [tile] byte offset of the tile's k range in a W row
+    int2 *sCol = reinterpret_cast<int2 *>(sOff + 2 * a.stripTiles);                        // [tile * 8] {init, divisor}
+    const uint32_t mbarBase = smemAddr(sCol + 8 * a.stripTiles);
+    uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
+    const int nseg = a.wcols >> 4;
+
+    // blocks of this warp (global block indices)
+    const int blkFirst = (a.dstRow0 >> 4) + blockIdx.y * a.bandBlocks;
+    const int blkEnd = min(blkFirst + a.bandBlocks, (a.dstRow0 + a.dstRows + 15) >> 4);
+    if (blkFirst >= blkEnd) return;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < a.nChunks; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarBase + 8 * i));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    // chunk c (global source rows 8 c ... 8 c + 7) is the (c - cStart)-th of the band: slot j & chunkMask, phase of the slot's (j / nChunks)-th use
+    int2 vb = __ldg(a.vBlock + blkFirst);   // {first source row, rows}
+    const int cStart = vb.x >> 3;           // arithmetic shift: floor
+    const int chunkShift = 31 - __clz(a.nChunks);
+    int cIssued = cStart;                   // next chunk to request
+    int cWaited = cStart;                   // chunks below have been waited for
+    auto issueUpTo = [&](const int cHi) {
+        for (int c = cIssued; c <= cHi; ++c) {
+            const int j = c - cStart;
+            const int slot = j & chunkMask;
+            const uint32_t bar = mbarBase + 8 * slot;
+            if (threadIdx.x == 0) {
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(chunkBytes) : "memory");
+                asm volatile(
+                    "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                    ::"r"(fifoBase + slot * chunkBytes), "l"(reinterpret_cast<unsigned long long>(&prm)), "r"(xs >> 1),
+                      "r"(kMmaChunk * c - a.srcRow0), "r"((int)blockIdx.z), "r"(bar)
+                    : "memory");
+            }
+        }
+        cIssued = max(cIssued, cHi + 1);
+    };
+    auto waitUpTo = [&](const int cHi) {
+        for (int c = cWaited; c <= cHi; ++c) {
+            const int j = c - cStart;
+            asm volatile(
+                "{\n\t.reg .pred q;\n\tIQO_MMA_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t@!q bra IQO_MMA_WAIT;\n\t}"
+                ::"r"(mbarBase + 8 * (j & chunkMask)), "r"((j >> chunkShift) & 1)
+                : "memory");
+        }
+        cWaited = max(cWaited, cHi + 1);
+    };
+    auto rowAddr = [&](const int r) -> uint32_t {   // shared address of global source row r (its chunk must be resident)
+        return fifoBase + (((r >> 3) - cStart) & chunkMask) * chunkBytes + (r & 7) * rowBytes;
+    };
+    issueUpTo((vb.x + vb.y - 1) >> 3);   // the first block's rows: in flight while the tables are staged
+
+    // the strip's horizontal tables -> shared memory (every block of the band uses them)
+    for (int i = threadIdx.x; i < nt * HKS * 32; i += blockDim.x) sFrag[i] = __ldg(a.hFrag + (size_t)T0 * HKS * 32 + i);
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) sOff[i] = 2 * (__ldg(a.hTile + T0 + i).x - xs);
+    for (int i = threadIdx.x; i < 8 * nt; i += blockDim.x) sCol[i] = __ldg(a.hCol + 8 * T0 + i);
+    __syncthreads();
+
+    // lane roles of the matrix loads / stores
+    const int mi = lane >> 3, ri = lane & 7;
+    const uint32_t wSt = wBase + ((mi & 1) * 8 + ri) * wStride + (mi >> 1) * 16;   // stmatrix: M0/M1 rows 0-7/8-15 of columns 0-7, M2/M3 of columns 8-15
+    const uint32_t wLd = wBase + ((mi >> 1) * 8 + ri) * wStride + (mi & 1) * 16;   // ldmatrix: M0/M1 columns 0-7/8-15 of rows 0-7, M2/M3 of rows 8-15
+    const int bias = a.workBias;
+    // output tile -> global: lanes per row = the power of two that covers the row's 16-byte pieces
+    const int nch = (tw + 15) >> 4;
+    int lprShift = 0;
+    while ((1 << lprShift) < nch) ++lprShift;
+    const int stRow = threadIdx.x >> lprShift, stCh = threadIdx.x & ((1 << lprShift) - 1), stRows = (int)blockDim.x >> lprShift;
+
+    uint4 af[VKS];   // A fragments (coefficients) of the running block
+#pragma unroll
+    for (int s = 0; s < VKS; ++s) af[s] = __ldg(a.vFrag + ((size_t)blkFirst * VKS + s) * 32 + lane);
+
+    for (int b = blkFirst; b < blkEnd; ++b) {
+        const int r0 = vb.x, rLast = vb.x + vb.y - 1;
+        waitUpTo(rLast >> 3);
+
+        // ---------------- vertical pass ----------------
+        uint32_t ra[VKS];   // k index 32 s + lane is source row r0 + 32 s + lane; rows past the block's last one meet zero coefficients
+#pragma unroll
+        for (int s = 0; s < VKS; ++s) ra[s] = rowAddr(min(r0 + 32 * s + lane, rLast));
+        const bool borderBlock = (16 * b < a.mbY) || (16 * b + 16 > a.meY);
+        int denoLo = 0, denoHi = 0;
+        uint32_t magicLo = 0, magicHi = 0;
+        if (borderBlock) {
+            const int2 v0 = __ldg(a.vRow + 16 * b + g), v1 = __ldg(a.vRow + 16 * b + g + 8);
+            denoLo = v0.x, magicLo = (uint32_t)v0.y, denoHi = v1.x, magicHi = (uint32_t)v1.y;
+        }
+        const int initLo = denoLo ? 0 : bias, initHi = denoHi ? 0 : bias;
+        // the B fragments of a segment (16 columns x 32 VKS source rows) are fetched one segment ahead of their mma
+        auto loadSeg = [&](uint32_t (&bf)[VKS][4], const int seg) {
+#pragma unroll
+            for (int s = 0; s < VKS; ++s)
+                asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(bf[s][0]), "=r"(bf[s][1]), "=r"(bf[s][2]), "=r"(bf[s][3]) : "r"(ra[s] + 16 * seg));
+        };
+        auto computeSeg = [&](const uint32_t (&bf)[VKS][4], const int seg) {
+            int dA[4], dB[4];
+#pragma unroll
+            for (int s = 0; s < VKS; ++s) {
+                if (s == 0) {
+                    mmaS8U8k16Init(dA, af[s].x, af[s].y, bf[s][0], initLo, initHi);   // columns 0..7 of the segment, source rows 0 ... 15
+                    mmaS8U8k16Init(dB, af[s].x, af[s].y, bf[s][1], initLo, initHi);   // columns 8..15
+                } else {
+                    mmaS8U8k16(dA, af[s].x, af[s].y, bf[s][0]);
+                    mmaS8U8k16(dB, af[s].x, af[s].y, bf[s][1]);
+                }
+                mmaS8U8k16(dA, af[s].z, af[s].w, bf[s][2]);   // source rows 32 s + 16 ... + 31
+                mmaS8U8k16(dB, af[s].z, af[s].w, bf[s][3]);
+            }
+            if (borderBlock && (denoLo | denoHi)) {
+                // resizeYborder: int16 numerator * 64 / denominator, C (truncating) division (see halfVerticalStrip)
+                auto bdiv = [&](int x, int deno, uint32_t magic) -> int {
+                    if (!deno) return x;
+                    const int n = (int)(short)x * 64;
+                    const uint32_t mm = (uint32_t)abs(n);
+                    const int q = magic ? (int)__umulhi(mm, magic) : (int)mm;
+                    return (int)(short)(n < 0 ? -q : q) + bias;
+                };
+                dA[0] = bdiv(dA[0], denoLo, magicLo), dA[1] = bdiv(dA[1], denoLo, magicLo);
+                dB[0] = bdiv(dB[0], denoLo, magicLo), dB[1] = bdiv(dB[1], denoLo, magicLo);
+                dA[2] = bdiv(dA[2], denoHi, magicHi), dA[3] = bdiv(dA[3], denoHi, magicHi);
+                dB[2] = bdiv(dB[2], denoHi, magicHi), dB[3] = bdiv(dB[3], denoHi, magicHi);
+            }
+            const uint32_t w0 = prmt((uint32_t)dA[0], (uint32_t)dA[1], 0x5410), w1 = prmt((uint32_t)dA[2], (uint32_t)dA[3], 0x5410);
+            const uint32_t w2 = prmt((uint32_t)dB[0], (uint32_t)dB[1], 0x5410), w3 = prmt((uint32_t)dB[2], (uint32_t)dB[3], 0x5410);
+            asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(wSt + 32 * seg), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+        };
+        if (warp < nseg) {
+            // this warp's segments: warp, warp + nw, ...
+            uint32_t bf0[VKS][4], bf1[VKS][4];
+            loadSeg(bf0, warp);
+            int seg = warp;
+            for (; seg + nw < nseg; seg += 2 * nw) {
+                loadSeg(bf1, seg + nw);
+                computeSeg(bf0, seg);
+                if (seg + 2 * nw < nseg) loadSeg(bf0, seg + 2 * nw);
+                computeSeg(bf1, seg + nw);
+            }
+            if (seg < nseg) computeSeg(bf0, seg);
+        }
+        __syncthreads();   // W is complete; every warp has finished reading the source rows of this block
+        if (b + 1 < blkEnd) {
+            // the next block's rows and coefficient fragments arrive during the horizontal pass
+            vb = __ldg(a.vBlock + b + 1);
+            issueUpTo((vb.x + vb.y - 1) >> 3);
+#pragma unroll
+            for (int s = 0; s < VKS; ++s) af[s] = __ldg(a.vFrag + ((size_t)(b + 1) * VKS + s) * 32 + lane);
+        }
+
+        // ---------------- horizontal pass: tiles in pairs, the operands of a step fetched one step ahead ----------------
+        {
+            struct Step {
+                uint32_t r[8];
+                uint4 bf;
+            };
+            auto loadStep = [&](Step &st, const int ti, const int s) {
+                const uint32_t wl = wLd + sOff[ti] + 64 * s;
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(st.r[0]), "=r"(st.r[1]), "=r"(st.r[2]), "=r"(st.r[3]) : "r"(wl));
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(st.r[4]), "=r"(st.r[5]), "=r"(st.r[6]), "=r"(st.r[7]) : "r"(wl + 32));
+                st.bf = sFrag[(ti * HKS + s) * 32 + lane];
+            };
+            int ll[4], lh[4], hl[4], hh[4];
+            auto computeStep = [&](const Step &st, const bool first) {
+                if (first) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) ll[e] = lh[e] = hl[e] = hh[e] = 0;
+                }
+                uint32_t alo[4], ahi[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    alo[i] = prmt(st.r[2 * i], st.r[2 * i + 1], 0x6420);
+                    ahi[i] = prmt(st.r[2 * i], st.r[2 * i + 1], 0x7531);
+                }
+                mmaU8U8(ll, alo, st.bf.x, st.bf.y);
+                mmaU8S8(hh, ahi, st.bf.z, st.bf.w);
+                mmaU8S8(lh, alo, st.bf.z, st.bf.w);
+                mmaU8U8(hl, ahi, st.bf.x, st.bf.y);
+            };
+            auto finishTile = [&](const int ti) {
+                // thread (g, t): rows g, g + 8; columns 8 (T0 + ti) + 2 t, + 1
+                const int4 hc = *reinterpret_cast<const int4 *>(sCol + 8 * ti + 2 * t);   // {init, divisor} of the two columns
+                int v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int init = (e & 1) ? hc.z : hc.x;
+                    v[e] = ll[e] + ((lh[e] + hl[e]) << 8) + (hh[e] << 16) + init;
+                }
+                if ((hc.y | hc.w) == 0) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = (int)(short)(v[e] >> 20);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int dv = (e & 1) ? hc.w : hc.y;
+                        v[e] = (int)(short)(dv != 0 ? v[e] / dv : v[e] >> 20);   // resizeXborder: truncating division by deno * 64
+                    }
+                }
+                const uint32_t p01 = packSatU8(v[1], v[0], 0u), p23 = packSatU8(v[3], v[2], 0u);
+                *reinterpret_cast<uint16_t *>(oTile + g * oStride + 8 * ti + 2 * t) = (uint16_t)p01;
+                *reinterpret_cast<uint16_t *>(oTile + (g + 8) * oStride + 8 * ti + 2 * t) = (uint16_t)p23;
+            };
+            // steps are numbered i = ti * HKS + s; a pair of tiles is 2 HKS steps, so the two operand buffers alternate
+            // at compile-time positions inside the unrolled pair
+            // this warp's tiles: warp, warp + nw, ...
+            Step st[2];
+            if (warp < nt) loadStep(st[0], warp, 0);
+            for (int tp = warp; tp < nt; tp += 2 * nw) {
+#pragma unroll
+                for (int u = 0; u < 2 * HKS; ++u) {
+                    const int ti = tp + (u / HKS) * nw, s = u % HKS;
+                    const int nti = tp + ((u + 1) / HKS) * nw, ns = (u + 1) % HKS;
+                    if (ti < nt) {
+                        if (nti < nt) loadStep(st[(u + 1) & 1], nti, ns);
+                        computeStep(st[u & 1], s == 0);
+                        if (s == HKS - 1) finishTile(ti);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---------------- store the 16 x tw tile ----------------
+        {
+            const int yb = 16 * b;
+            const int yLo = max(a.dstRow0, yb), yHi = min(a.dstRow0 + a.dstRows, yb + 16);   // rows of the block inside the launch
+            if (a.dstVec) {
+                if (stCh < nch) {
+                    for (int r = stRow; r < 16; r += stRows) {
+                        const int y = yb + r;
+                        if (y < yLo || y >= yHi) continue;
+                        const uint8_t *sp = oTile + r * oStride + 16 * stCh;
+                        uint8_t *dp = dst + (long long)(y - a.dstRow0) * a.dstPitch + tx0 + 16 * stCh;
+                        if (16 * stCh + 16 <= tw) {
+                            *reinterpret_cast<uint4 *>(dp) = *reinterpret_cast<const uint4 *>(sp);
+                        } else {
+                            for (int i = 0; i < tw - 16 * stCh; ++i) dp[i] = sp[i];
+                        }
+                    }
+                }
+            } else {
+                for (int r = warp; r < 16; r += nw) {
+                    const int y = yb + r;
+                    if (y < yLo || y >= yHi) continue;
+                    for (int x = lane; x < tw; x += 32) dst[(long long)(y - a.dstRow0) * a.dstPitch + tx0 + x] = oTile[r * oStride + x];
+                }
+            }
+        }
+        // (the next block's first barrier orders these reads of the output tile before its horizontal pass writes it;
+        //  W was last read before the barrier above, so the next vertical pass may overwrite it)
+    }
+}
+
 }  // namespace
+
+size_t mmaSmemBytes(int wcols, int stripTiles, int nChunks, int hKMax)
+{
+    return size_t(nChunks) * kMmaChunk * wcols + 16 * size_t(mmaWStride(wcols)) + 16 * size_t(mmaOutStride(stripTiles)) +
+           size_t(mmaTableBytes(stripTiles, hKMax)) + 8 * size_t(nChunks) + 16;
+}
+
+template <int VKS, int HKS>
+cudaError_t launchMmaT(const MmaKernelArgs &p, dim3 grid, size_t smem, cudaStream_t stream)
+{
+    static PerDeviceOnce attrSet;
+    const int dev = currentDevice();
+    if (!attrSet.done(dev)) {
+        cudaError_t e = cudaFuncSetAttribute(resizeLanczosMmaKernel<VKS, HKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attrSet.set(dev);
+    }
+    resizeLanczosMmaKernel<VKS, HKS><<<grid, 32 * p.a.warps, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launchMma(const MmaArgs &a, const CUtensorMap &tmap, cudaStream_t stream)
+{
+    const int tiles = (a.DW + 7) / 8;
+    const int strips = (tiles + a.stripTiles - 1) / a.stripTiles;
+    const int blocks = ((a.dstRow0 + a.dstRows + 15) >> 4) - (a.dstRow0 >> 4);
+    const int bands = (blocks + a.bandBlocks - 1) / a.bandBlocks;
+    if (bands > 65535 || a.nFrames > 65535) return cudaErrorInvalidConfiguration;
+    const size_t smem = mmaSmemBytes(a.wcols, a.stripTiles, a.nChunks, a.hKMax);
+    MmaKernelArgs p;
+    p.tmap = tmap;
+    p.a = a;
+    dim3 grid(strips, bands, a.nFrames);
+    g_launches.fetch_add(1);
+#define IQO_MMA_CASE(V, H) \
+    if (a.vKMax == V && a.hKMax == H) return launchMmaT<V, H>(p, grid, smem, stream);
+    IQO_MMA_CASE(1, 1) IQO_MMA_CASE(1, 2) IQO_MMA_CASE(1, 3)
+    IQO_MMA_CASE(2, 1) IQO_MMA_CASE(2, 2) IQO_MMA_CASE(2, 3)
+    IQO_MMA_CASE(3, 1) IQO_MMA_CASE(3, 2) IQO_MMA_CASE(3, 3)
+#undef IQO_MMA_CASE
+    return cudaErrorInvalidValue;
+}
 
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D)
 {

@@ -192,6 +192,34 @@ struct LStreamArgs {
 bool lstreamHasKernel(int NP);
 cudaError_t launchLStream(const LStreamArgs &a, cudaStream_t stream);
 
+// Arguments of the tensor-path Lanczos kernel (plan.hpp MmaPlan).  The source is read through a 3-D tensor map over a
+// 16-bit view of the frames (x / 2, y, frame) with box (wcols / 2) x 16 x 1.
+struct MmaArgs {
+    uint8_t *dst;                  // addresses global destination row dstRow0
+    long long dstPitch, dstFrameStride;
+    int DW;
+    int srcRow0;                   // global source row of the tensor map's row 0 (row-band mode; else 0)
+    int dstRow0, dstRows;          // destination rows of this launch (global indices)
+    int bandBlocks;                // 16-row blocks per warp
+    int stripTiles, wcols;
+    int vKMax, hKMax;
+    int nChunks;                   // 8-row chunks of the source FIFO
+    int warps;                     // warps per CTA (1, 2 or 4): they share the strip's FIFO / W / tables
+    int workBias;
+    int mbY, meY, mbX, meX;
+    int dstVec;                    // destination rows can take 16-byte stores
+    const int2 *vBlock;
+    const uint4 *vFrag;
+    const int2 *vRow;
+    const int32_t *stripXs;
+    const int2 *hTile;
+    const uint4 *hFrag;
+    const int2 *hCol;
+    int nFrames;
+};
+size_t mmaSmemBytes(int wcols, int stripTiles, int nChunks, int hKMax);
+cudaError_t launchMma(const MmaArgs &a, const CUtensorMap &tmap, cudaStream_t stream);
+
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D);
 cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_t stream);
 cudaError_t initKernels();  // sets function attributes once per device

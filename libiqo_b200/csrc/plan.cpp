@@ -973,3 +973,204 @@ void buildLStreamPlan(const Plan &p, const PackedPlan &q, LStreamPlan &g)
 }
 
 }  // namespace iqo_b200
+
+// ---------------------------------------------------------------------------------------------
+// Plan of the tensor-path Lanczos kernel (both passes as banded integer matrix products)
+// ---------------------------------------------------------------------------------------------
+namespace iqo_b200 {
+
+namespace {
+
+int64_t floorTo(int64_t v, int64_t m)
+{
+    int64_t q = v / m;
+    if (v % m != 0 && v < 0) --q;
+    return q * m;
+}
+
+}  // namespace
+
+void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
+{
+    m.eligible = false;
+    m.why.clear();
+    m.workBias = 0;
+    m.vKMax = m.hKMax = 1;
+    m.nChunks = 2;
+    m.stripTiles = 0;
+    m.wcols = wcols;
+    const AxisPlan &X = p.x, &Y = p.y;
+    if (p.kind != kLanczos) { m.why = "not Lanczos"; return; }
+    if (!X.identity && X.mainBegin >= X.mainEnd) { m.why = "no main columns (source narrower than the kernel)"; return; }
+    if (Y.coefMin < -128 || Y.coefMax > 127) { m.why = "vertical coefficients do not fit int8"; return; }
+    if (X.coefMin < -32768 || X.coefMax > 32767) { m.why = "horizontal coefficients do not fit two byte planes"; return; }
+    if (X.S % 2 != 0) { m.why = "odd source width (the tensor map views the rows as 16-bit pairs)"; return; }
+    if (wcols % 16 != 0 || wcols < 64 || wcols > 512) { m.why = "bad strip width"; return; }
+    const int NX = X.N, NY = Y.N;
+
+    // ---- intermediate range (as buildPackedPlan): no 16-bit wrap, border rows rescaled by 64 / deno ----
+    long long wmin = 0, wmax = 0;
+    for (int r = 0; r < Y.numRows; ++r) {
+        long long pos = 0, neg = 0;
+        for (int i = 0; i < NY; ++i) {
+            const int c = Y.coef[size_t(r) * NY + i];
+            (c > 0 ? pos : neg) += c;
+        }
+        long long lo = 255 * neg, hi = 255 * pos;
+        if (lo < -32768 || hi > 32767) { m.why = "vertical sum may wrap int16"; return; }
+        const int den = Y.deno[size_t(r)];
+        if (den != 0) {
+            if (den < 0 || den > 255) { m.why = "border denominator out of range"; return; }
+            lo = lo * 64 / den - 1;
+            hi = hi * 64 / den + 1;
+        }
+        wmin = std::min(wmin, lo);
+        wmax = std::max(wmax, hi);
+    }
+    m.workBias = int(-wmin);
+    if (wmax + m.workBias > 65535) { m.why = "intermediate range wider than 16 bits"; return; }
+
+    // ---- vertical blocks ----
+    const int64_t blocks = (Y.D + 15) / 16;
+    m.vBlock.assign(size_t(blocks) * 2, 0);
+    m.vRow.assign(size_t(blocks) * 32, 0);
+    std::vector<int64_t> lo(size_t(blocks), 0);
+    m.vKMax = 1;
+    for (int64_t b = 0; b < blocks; ++b) {
+        int64_t rlo = 1ll << 40, rhi = -(1ll << 40);
+        for (int64_t y = 16 * b; y < std::min<int64_t>(Y.D, 16 * b + 16); ++y) {
+            const int32_t *c = &Y.coef[size_t(Y.row[size_t(y)]) * NY];
+            const int64_t f = Y.first[size_t(y)];
+            for (int i = 0; i < NY; ++i)
+                if (c[i] != 0) {
+                    if (f + i < 0 || f + i >= Y.S) { m.why = "vertical tap outside the image with non-zero weight"; return; }
+                    rlo = std::min(rlo, f + i);
+                    rhi = std::max(rhi, f + i);
+                }
+            const int den = Y.deno[size_t(Y.row[size_t(y)])];
+            m.vRow[size_t(y) * 2] = den;
+            m.vRow[size_t(y) * 2 + 1] = den > 1 ? int32_t(uint32_t((1ull << 32) / uint64_t(den) + 1)) : 0;
+        }
+        if (rhi < rlo) { m.why = "all-zero vertical block"; return; }
+        lo[size_t(b)] = rlo;
+        m.vBlock[size_t(b) * 2 + 1] = int32_t(rhi);
+    }
+    // the kernel's source FIFO only moves forward: first rows must not decrease from block to block
+    for (int64_t b = blocks - 2; b >= 0; --b) lo[size_t(b)] = std::min(lo[size_t(b)], lo[size_t(b) + 1]);
+    int chunksNeeded = 1;
+    for (int64_t b = 0; b < blocks; ++b) {
+        const int64_t rlo = lo[size_t(b)], rhi = m.vBlock[size_t(b) * 2 + 1];
+        const int ks = int((rhi - rlo + 32) / 32);
+        if (ks > kMmaMaxKSteps) { m.why = "vertical kernel spans more than three 32-row k-steps per 16 destination rows"; return; }
+        m.vKMax = std::max(m.vKMax, ks);
+        m.vBlock[size_t(b) * 2] = int32_t(rlo);
+        m.vBlock[size_t(b) * 2 + 1] = int32_t(rhi - rlo + 1);   // source rows the block reads; k beyond them meets zero coefficients
+        chunksNeeded = std::max(chunksNeeded, int(floorTo(rhi, kMmaChunkRows) / kMmaChunkRows - floorTo(rlo, kMmaChunkRows) / kMmaChunkRows + 1));
+    }
+    m.nChunks = 2;
+    while (m.nChunks < chunksNeeded) m.nChunks *= 2;
+    m.vFrag.assign(size_t(blocks) * m.vKMax * 128, 0);
+    for (int64_t b = 0; b < blocks; ++b) {
+        const int ks = (m.vBlock[size_t(b) * 2 + 1] + 31) / 32;
+        // A[row][k]: coefficient of destination row 16 b + row for source row lo + k
+        auto coefAt = [&](int row, int64_t k) -> uint32_t {
+            const int64_t y = 16 * b + row;
+            if (y >= Y.D) return 0u;
+            const int64_t i = lo[size_t(b)] + k - Y.first[size_t(y)];
+            if (i < 0 || i >= NY) return 0u;
+            return uint32_t(Y.coef[size_t(Y.row[size_t(y)]) * NY + size_t(i)]) & 0xffu;
+        };
+        for (int s = 0; s < ks; ++s)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t = lane & 3;
+                uint32_t *f = &m.vFrag[((size_t(b) * m.vKMax + s) * 32 + lane) * 4];
+                for (int i = 0; i < 4; ++i) {
+                    f[0] |= coefAt(g, 32 * s + 4 * t + i) << (8 * i);
+                    f[1] |= coefAt(g + 8, 32 * s + 4 * t + i) << (8 * i);
+                    f[2] |= coefAt(g, 32 * s + 16 + 4 * t + i) << (8 * i);
+                    f[3] |= coefAt(g + 8, 32 * s + 16 + 4 * t + i) << (8 * i);
+                }
+            }
+    }
+
+    // ---- horizontal tiles ----
+    const int64_t tiles = (X.D + 7) / 8;
+    m.hTile.assign(size_t(tiles) * 2, 0);
+    m.hCol.assign(size_t(tiles) * 16, 0);
+    std::vector<int64_t> c0(size_t(tiles), 0), cEnd(size_t(tiles), 0);
+    m.hKMax = 1;
+    for (int64_t T = 0; T < tiles; ++T) {
+        int64_t clo = 1ll << 40, chi = -(1ll << 40);
+        for (int64_t d = 8 * T; d < std::min<int64_t>(X.D, 8 * T + 8); ++d) {
+            const int r = X.row[size_t(d)];
+            const int32_t *c = &X.coef[size_t(r) * NX];
+            const int64_t f = X.first[size_t(d)];
+            long long sum = 0;
+            for (int i = 0; i < NX; ++i) {
+                sum += c[i];
+                if (c[i] != 0) {
+                    if (f + i < 0 || f + i >= X.S) { m.why = "horizontal tap outside the image with non-zero weight"; return; }
+                    clo = std::min(clo, f + i);
+                    chi = std::max(chi, f + i);
+                }
+            }
+            m.hCol[size_t(d) * 2] = int32_t((1ll << (p.shift - 1)) - (long long)m.workBias * sum);
+            m.hCol[size_t(d) * 2 + 1] = X.deno[size_t(r)] * 64;
+        }
+        if (chi < clo) { m.why = "all-zero horizontal tile"; return; }
+        clo = floorTo(clo, 8);
+        const int ks = int((chi - clo + 32) / 32);
+        if (ks > kMmaMaxKSteps) { m.why = "horizontal kernel spans more than three 32-column k-steps per 8 destination columns"; return; }
+        m.hKMax = std::max(m.hKMax, ks);
+        c0[size_t(T)] = clo;
+        cEnd[size_t(T)] = clo + 32 * ks;
+        m.hTile[size_t(T) * 2] = int32_t(clo);
+        m.hTile[size_t(T) * 2 + 1] = ks;
+    }
+    // strips: the largest even tile count whose source window [xs, xs + wcols) holds every tile's k range
+    int st = int(std::min<int64_t>(32, (tiles + 1) & ~1ll));
+    for (; st >= 2; st -= 2) {
+        bool ok = true;
+        for (int64_t T0 = 0; T0 < tiles && ok; T0 += st) {
+            const int64_t xs = floorTo(c0[size_t(T0)], 16);
+            for (int64_t T = T0; T < std::min<int64_t>(tiles, T0 + st) && ok; ++T)
+                if (c0[size_t(T)] < xs || cEnd[size_t(T)] - xs > wcols) ok = false;
+        }
+        if (ok) break;
+    }
+    if (st < 2) { m.why = "horizontal kernel wider than a warp strip"; return; }
+    m.stripTiles = st;
+    m.wcols = wcols;
+    const int64_t strips = (tiles + st - 1) / st;
+    m.stripXs.assign(size_t(strips), 0);
+    for (int64_t s = 0; s < strips; ++s) m.stripXs[size_t(s)] = int32_t(floorTo(c0[size_t(s * st)], 16));
+    m.hFrag.assign(size_t(tiles) * m.hKMax * 128, 0);
+    for (int64_t T = 0; T < tiles; ++T) {
+        const int ks = m.hTile[size_t(T) * 2 + 1];
+        // B[k][n]: coefficient of destination column 8 T + n for the source column the kernel's A fragment holds at k:
+        // k = 16 h + 4 t + i  <->  column c0 + 32 s + 16 h + {2 t, 2 t + 1, 8 + 2 t, 9 + 2 t}[i]
+        auto coefAt = [&](int n, int64_t col) -> int {
+            const int64_t d = 8 * T + n;
+            if (d >= X.D) return 0;
+            const int64_t i = col - X.first[size_t(d)];
+            if (i < 0 || i >= NX) return 0;
+            return X.coef[size_t(X.row[size_t(d)]) * NX + size_t(i)];
+        };
+        for (int s = 0; s < ks; ++s)
+            for (int lane = 0; lane < 32; ++lane) {
+                const int g = lane >> 2, t = lane & 3;
+                uint32_t *f = &m.hFrag[((size_t(T) * m.hKMax + s) * 32 + lane) * 4];
+                for (int h = 0; h < 2; ++h)
+                    for (int i = 0; i < 4; ++i) {
+                        const int off = (i & 1) + 2 * t + ((i >> 1) ? 8 : 0);
+                        uint32_t l, hi;
+                        splitPlanes(coefAt(g, c0[size_t(T)] + 32 * s + 16 * h + off), l, hi);
+                        f[h] |= l << (8 * i);
+                        f[2 + h] |= hi << (8 * i);
+                    }
+            }
+    }
+    m.eligible = true;
+}
+
+}  // namespace iqo_b200

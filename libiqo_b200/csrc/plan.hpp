@@ -209,3 +209,40 @@ struct LStreamPlan {
 void buildLStreamPlan(const Plan &plan, const PackedPlan &packed, LStreamPlan &g);
 
 }  // namespace iqo_b200
+
+namespace iqo_b200 {
+
+// Lanczos at any ratio with both passes on the integer tensor path (kernels.cu: resizeLanczosMmaKernel).
+// Both passes are banded integer matrix products evaluated with mma.sync.m16n8k32 (s32 accumulators):
+//   vertical    W[16 dst rows x 8 columns] = A (coefficients, s8, 16 x 32 k) * B (source bytes, u8, 32 source rows x 8 columns),
+//               k = consecutive source rows starting at the block's first row, 1 - 3 k-steps per 16-row block;
+//   horizontal  out[16 rows x 8 dst columns] = A (bytes of W, u8, 16 x 32 k) * B (coefficient byte planes, 32 source columns x 8),
+//               four products per k-step (low / high byte of W times low / high byte plane of the 14-bit coefficients).
+// The planner lays the coefficient operands out in the register order of the mma fragments, one 16-byte (vertical) or
+// 8-byte (horizontal) piece per lane, so that the kernel loads them with one coalesced vector load.
+struct MmaPlan {
+    bool eligible;
+    std::string why;
+    int workBias;                   // added to the intermediate: non-negative 16-bit values
+    // vertical: 16-row destination blocks (global block index = dst row / 16)
+    int vKMax;                      // most k-steps of a block (<= kMmaMaxKSteps)
+    int nChunks;                    // 8-row chunks of the kernel's source FIFO (power of two; holds any block's rows)
+    std::vector<int32_t> vBlock;    // [blocks][2]: first source row of the block's k range (may be negative), rows read from it
+    std::vector<uint32_t> vFrag;    // [blocks][vKMax][32 lanes][4]: A fragments (s8 coefficient bytes)
+    std::vector<int32_t> vRow;      // [blocks * 16][2]: Lanczos border denominator (0: ordinary row), multiply-high constant
+    // horizontal: 8-column destination tiles, strips of stripTiles tiles per warp
+    int hKMax;
+    int stripTiles;                 // tiles per strip (even, so that strips start on 16-byte boundaries of the destination)
+    int wcols;                      // source columns staged per strip (multiple of 16, <= 512)
+    std::vector<int32_t> stripXs;   // [strips]: source column of W element 0 (multiple of 16, may be negative)
+    std::vector<int32_t> hTile;     // [tiles][2]: first source column of the tile's k range (multiple of 8), k-steps
+    std::vector<uint32_t> hFrag;    // [tiles][hKMax][32 lanes][4]: B fragments {low plane b0, b1, high plane b0, b1}
+    std::vector<int32_t> hCol;      // [tiles * 8][2]: accumulator init (rounding - bias * sum), divisor (0: shift by 20)
+};
+const int kMmaMaxKSteps = 3;
+const int kMmaChunkRows = 8;      // source rows per TMA request of the kernel's FIFO
+
+// wcols: staged source columns per strip the kernel was launched for (208 unless tuned)
+void buildMmaPlan(const Plan &plan, MmaPlan &m, int wcols);
+
+}  // namespace iqo_b200

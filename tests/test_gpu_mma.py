@@ -1,0 +1,147 @@
+"""Tensor-path Lanczos kernel (resizeLanczosMmaKernel: both passes as integer mma.sync matrix products, source rows
+fed by TMA) forced with IQO_CUDA_PATH_MMA and compared bit-for-bit with the oracle: the BASELINE shapes, odd sizes,
+padded pitches, row bands, batches and a random sweep.  Replaces the reference's resizeYmain / resizeYborder /
+resizeXmain / resizeXborder loops (src/IQOLanczosResizerImpl_Generic.cpp:464-612)."""
+import random
+
+import numpy as np
+import pytest
+
+import libiqo_b200 as iqo
+from oracle_lib import LANCZOS, fnv1a, lcg_image, oracle_resize
+
+pytestmark = pytest.mark.gpu
+
+
+def mma_resize(src, dw, dh, deg, px=1, sw=None, dst_stride=None):
+    sh, sst = src.shape
+    sw = sw or sst
+    dst_stride = dst_stride or dw
+    dst = np.full((dh, dst_stride), 0xA5, dtype=np.uint8)
+    with iqo.LanczosResizer(deg, sw, sh, dw, dh, px) as r:
+        r.set_path(iqo.PATH_MMA)
+        r.resize(sst, src, dst_stride, dst)
+        kernel = r.last_kernel()
+    return dst, kernel
+
+
+CASES = [
+    # (degree, pxScale, srcW, srcH, dstW, dstH, srcPad, dstPad)
+    (3, 1, 1920, 1080, 960, 540, 0, 0),      # cfg4
+    (3, 1, 1920, 1080, 1280, 720, 0, 0),     # cfg1
+    (2, 1, 3840, 2160, 1920, 1080, 0, 0),    # cfg3 luma
+    (2, 2, 1920, 1080, 960, 540, 0, 0),      # cfg3 chroma
+    (4, 1, 4096, 1024, 1500, 375, 0, 0),     # cfg5's ratio
+    (4, 1, 2048, 2048, 750, 750, 0, 0),
+    (3, 1, 64, 48, 40, 30, 0, 0),
+    (3, 1, 40, 30, 64, 48, 0, 0),            # up-sampling
+    (3, 1, 320, 180, 640, 360, 0, 0),
+    (2, 1, 34, 21, 64, 47, 0, 0),
+    (3, 1, 96, 54, 64, 36, 16, 3),           # padded pitches, unaligned destination stride (byte stores)
+    (3, 1, 488, 250, 244, 125, 8, 0),
+    (3, 1, 1208, 98, 604, 49, 0, 0),
+    (5, 1, 900, 700, 330, 211, 4, 1),
+    (3, 1, 64, 48, 64, 30, 0, 0),            # X pass-through
+    (3, 1, 64, 48, 40, 48, 0, 0),            # Y pass-through
+    (1, 1, 50, 40, 24, 20, 14, 0),
+    (4, 2, 100, 80, 50, 40, 12, 0),
+    (3, 3, 300, 200, 150, 100, 4, 4),
+    (3, 1, 18, 400, 9, 200, 14, 7),          # narrower than one tile
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_mma_kernel_matches_oracle(case):
+    deg, px, sw, sh, dw, dh, spad, dpad = case
+    src = lcg_image(sh, sw + spad, seed=31)
+    rc, want = oracle_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+    assert rc == 0
+    got, kernel = mma_resize(src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+    assert kernel == "lanczos_mma", kernel
+    bad = np.argwhere(got != want)
+    assert bad.size == 0, (len(bad), bad[:8].tolist())
+
+
+def test_mma_extreme_values():
+    sw, sh = 480, 272
+    yy, xx = np.mgrid[0:sh, 0:sw]
+    for name, src in (("white", np.full((sh, sw), 255, np.uint8)), ("black", np.zeros((sh, sw), np.uint8)),
+                      ("checker1", (((yy + xx) & 1) * 255).astype(np.uint8)),
+                      ("checker2", ((((yy >> 1) + (xx >> 1)) & 1) * 255).astype(np.uint8)),
+                      ("vstripes", ((xx & 1) * 255).astype(np.uint8)), ("hstripes", ((yy & 1) * 255).astype(np.uint8))):
+        for deg, px, dw, dh in ((3, 1, 240, 136), (2, 1, 240, 136), (3, 1, 320, 181), (4, 1, 176, 100), (3, 1, 960, 544)):
+            rc, want = oracle_resize(LANCZOS, src, dw, dh, deg, px)
+            assert rc == 0
+            got, kernel = mma_resize(src, dw, dh, deg, px)
+            assert kernel == "lanczos_mma"
+            assert np.array_equal(got, want), (name, deg, px, dw, dh)
+
+
+def test_mma_random_sweep():
+    rng = random.Random(4242)
+    ran = 0
+    for _ in range(150):
+        deg = rng.randint(1, 6)
+        px = rng.choice([1, 1, 2, 3])
+        sw, sh = 2 * rng.randint(4, 300), rng.randint(8, 300)          # even widths (the tensor map views rows as 16-bit pairs)
+        dw, dh = rng.randint(4, 500), rng.randint(4, 400)
+        if rng.random() < 0.1:
+            dw = sw
+        if rng.random() < 0.1:
+            dh = sh
+        spad = rng.choice([0, 16, 32]) + (-sw) % 16                     # staged pitch is 16-byte aligned anyway; vary the host stride
+        dpad = rng.randint(0, 5)
+        src = lcg_image(sh, sw + spad, seed=rng.randint(1, 1 << 30))
+        rc, want = oracle_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+        if rc != 0:
+            continue
+        got, kernel = mma_resize(src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+        assert np.array_equal(got, want), (deg, px, sw, sh, dw, dh, kernel)
+        ran += kernel == "lanczos_mma"
+    assert ran >= 80, ran
+
+
+def test_mma_bands_batches_and_device_pitches():
+    torch = pytest.importorskip("torch")
+    # row bands with srcRow0 != 0 at cfg5's ratio
+    sw, sh, dw, dh = 4096, 1024, 1500, 375
+    src = lcg_image(sh, sw, seed=4)
+    out = np.zeros((dh, dw), dtype=np.uint8)
+    with iqo.LanczosResizer(4, sw, sh, dw, dh) as r:
+        r.set_path(iqo.PATH_MMA)
+        for y0, n in [(0, 5), (5, 123), (128, 200), (328, 47)]:
+            s0, sn = r.band_src_rows(y0, n)
+            dsrc = torch.from_numpy(src[s0:s0 + sn].copy()).cuda()
+            ddst = torch.full((n, dw + 16), 0xA5, dtype=torch.uint8, device="cuda")
+            r.resize_band(y0, n, s0, sn, sw, dsrc, dw + 16, ddst, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert r.last_kernel() == "lanczos_mma"
+            got = ddst.cpu().numpy()
+            assert (got[:, dw:] == 0xA5).all()
+            out[y0:y0 + n] = got[:, :dw]
+    assert "%016x" % fnv1a(out) == "eb104bb1ff7eb33f"
+    # device-resident batch, frame stride with slack, three ratios
+    for deg, sw, sh, dw, dh in ((3, 960, 540, 480, 270), (3, 960, 540, 640, 360), (4, 1024, 512, 375, 188)):
+        n = 5
+        pitch = sw + 32
+        host = np.stack([lcg_image(sh, pitch, seed=70 + f) for f in range(n)])
+        host[3] = 255
+        want = np.stack([oracle_resize(LANCZOS, host[f], dw, dh, deg, sw=sw)[1] for f in range(n)])
+        dsrc = torch.from_numpy(host).cuda()
+        ddst = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
+        with iqo.LanczosResizer(deg, sw, sh, dw, dh) as r:
+            r.set_path(iqo.PATH_MMA)
+            r.resize_batch(n, pitch, pitch * sh, dsrc, dw, dw * dh, ddst, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert r.last_kernel() == "lanczos_mma"
+        assert np.array_equal(ddst.cpu().numpy(), want), (deg, sw, sh, dw, dh)
+    # a pitch that is not 16-byte aligned is declined (TMA needs it): another kernel takes the launch
+    host = lcg_image(270, 488, seed=3)
+    dsrc = torch.from_numpy(host).cuda()
+    ddst = torch.zeros((135, 240), dtype=torch.uint8, device="cuda")
+    with iqo.LanczosResizer(3, 480, 270, 240, 135) as r:
+        r.set_path(iqo.PATH_MMA)
+        r.resize_batch(1, 488, 488 * 270, dsrc, 240, 240 * 135, ddst, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert r.last_kernel() != "lanczos_mma"
+    assert np.array_equal(ddst.cpu().numpy(), oracle_resize(LANCZOS, host, 240, 135, 3, sw=480)[1])

@@ -1,0 +1,21 @@
+set -x
+cd "$GRAFT_REPO_ROOT"; mkdir -p gpurun_out
+summ() { python - "$1" <<'P'
+import json,sys
+try:
+    d=json.loads(open(sys.argv[1]).read())
+except Exception as e:
+    print("no json", e); sys.exit(0)
+print("HEAD", d['detail']['kernel'], d['ms_per_step'], d['roofline']['frac'], 'parity', d['parity']['bit_exact'], 'e2e', d['e2e'] and d['e2e']['value'])
+for w in d.get('workloads', []):
+    print("  WL %-38s %-16s ms %-8s frac %-7s parity %s" % (w.get('workload'), w.get('kernel','')[:16], w.get('ms'), w.get('frac'), (w.get('parity') or {}).get('bit_exact'), ), w.get('error',''))
+c=d.get('cfg5') or {}
+print("  cfg5", c.get('kernel'), c.get('ms_kernel'), c.get('ms_e2e'), c.get('hash_ok'), c.get('error'))
+P
+}
+for wc in 208 144 272; do
+  IQO_CUDA_MMA_AUTO=1 IQO_CUDA_MMA_WCOLS=$wc timeout 600 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/r2_bench_mma_w$wc.json 2> gpurun_out/r2_bench_mma_w$wc.err; echo "rc=$? wcols=$wc"; summ gpurun_out/r2_bench_mma_w$wc.json
+done
+for bb in 4 8 32; do
+  IQO_CUDA_MMA_AUTO=1 IQO_CUDA_MMA_BAND_BLOCKS=$bb timeout 600 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/r2_bench_mma_bb$bb.json 2> gpurun_out/r2_bench_mma_bb$bb.err; echo "rc=$? bandBlocks=$bb"; summ gpurun_out/r2_bench_mma_bb$bb.json
+done

@@ -2204,11 +2204,17 @@ __device__ __forceinline__ void mmaS8U8k16(int (&d)[4], uint32_t a0, uint32_t a1
     asm("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
                  : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(b));
 }
-// first product of a chain: the accumulator input is (cLo, cLo, cHi, cHi) -- no register copies to initialise d
-__device__ __forceinline__ void mmaS8U8k16Init(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t b, int cLo, int cHi)
+// first product of a chain: zero accumulator input (RZ: no register copies to initialise d)
+__device__ __forceinline__ void mmaS8U8k16Zero(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t b)
 {
-    asm("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%8,%8};"
-                 : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a0), "r"(a1), "r"(b), "r"(cLo), "r"(cHi));
+    asm("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
+        : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a0), "r"(a1), "r"(b), "r"(0));
+}
+__device__ __forceinline__ uint32_t addU16x2(uint32_t a, uint32_t b)
+{
+    uint32_t d;
+    asm("add.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
 }
 __device__ __forceinline__ void mmaU8U8(int (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1)
 {
@@ -2246,7 +2252,7 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     extern __shared__ __align__(128) uint8_t mmaSmem[];
     const MmaArgs &a = prm.a;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), nw = blockDim.x >> 5;   // (the shuffle tells the compiler it is warp-uniform)
     const int strip = blockIdx.x;
     const int T0 = strip * a.stripTiles;                        // first destination tile of the strip
     const int tx0 = 8 * T0;
@@ -2274,42 +2280,47 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     if (blkFirst >= blkEnd) return;
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < a.nChunks; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarBase + 8 * i));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarBase));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarBase + 8));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
-    // chunk c (global source rows 8 c ... 8 c + 7) is the (c - cStart)-th of the band: slot j & chunkMask, phase of the slot's (j / nChunks)-th use
+    // chunk c (global source rows 8 c ... 8 c + 7) lives in FIFO slot (c - cStart) & chunkMask.  The chunks requested for
+    // one block form a group that completes one phase of an mbarrier: group i uses barrier i & 1, phase (i >> 1) & 1.
     int2 vb = __ldg(a.vBlock + blkFirst);   // {first source row, rows}
     const int cStart = vb.x >> 3;           // arithmetic shift: floor
-    const int chunkShift = 31 - __clz(a.nChunks);
     int cIssued = cStart;                   // next chunk to request
-    int cWaited = cStart;                   // chunks below have been waited for
+    int grpIssued = 0, grpWaited = 0;       // groups requested / waited for
     auto issueUpTo = [&](const int cHi) {
-        for (int c = cIssued; c <= cHi; ++c) {
-            const int j = c - cStart;
-            const int slot = j & chunkMask;
-            const uint32_t bar = mbarBase + 8 * slot;
-            if (threadIdx.x == 0) {
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(chunkBytes) : "memory");
-                asm volatile(
-                    "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                    ::"r"(fifoBase + slot * chunkBytes), "l"(reinterpret_cast<unsigned long long>(&prm)), "r"(xs >> 1),
-                      "r"(kMmaChunk * c - a.srcRow0), "r"((int)blockIdx.z), "r"(bar)
-                    : "memory");
+        if (warp == 0) {
+            const uint32_t bar = mbarBase + 8 * (grpIssued & 1);
+            const int nNew = max(cHi + 1 - cIssued, 0);
+            if (lane == 0) {
+                if (nNew > 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nNew * chunkBytes) : "memory");
+                else
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");   // nothing new: the phase completes at once
+            }
+            for (int c = cIssued; c <= cHi; ++c) {
+                const int slot = (c - cStart) & chunkMask;
+                if (lane == 0)
+                    asm volatile(
+                        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                        ::"r"(fifoBase + slot * chunkBytes), "l"(reinterpret_cast<unsigned long long>(&prm)), "r"(xs >> 1),
+                          "r"(kMmaChunk * c - a.srcRow0), "r"((int)blockIdx.z), "r"(bar)
+                        : "memory");
             }
         }
         cIssued = max(cIssued, cHi + 1);
+        ++grpIssued;
     };
-    auto waitUpTo = [&](const int cHi) {
-        for (int c = cWaited; c <= cHi; ++c) {
-            const int j = c - cStart;
-            asm volatile(
-                "{\n\t.reg .pred q;\n\tIQO_MMA_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t@!q bra IQO_MMA_WAIT;\n\t}"
-                ::"r"(mbarBase + 8 * (j & chunkMask)), "r"((j >> chunkShift) & 1)
-                : "memory");
-        }
-        cWaited = max(cWaited, cHi + 1);
+    auto waitGroup = [&]() {
+        asm volatile(
+            "{\n\t.reg .pred q;\n\tIQO_MMA_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t@!q bra IQO_MMA_WAIT;\n\t}"
+            ::"r"(mbarBase + 8 * (grpWaited & 1)), "r"((grpWaited >> 1) & 1)
+            : "memory");
+        ++grpWaited;
     };
     auto rowAddr = [&](const int r) -> uint32_t {   // shared address of global source row r (its chunk must be resident)
         return fifoBase + (((r >> 3) - cStart) & chunkMask) * chunkBytes + (r & 7) * rowBytes;
@@ -2339,7 +2350,7 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
 
     for (int b = blkFirst; b < blkEnd; ++b) {
         const int r0 = vb.x, rLast = vb.x + vb.y - 1;
-        waitUpTo(rLast >> 3);
+        waitGroup();   // the rows of this block have landed
 
         // ---------------- vertical pass ----------------
         uint32_t ra[VKS];   // k index 32 s + lane is source row r0 + 32 s + lane; rows past the block's last one meet zero coefficients
@@ -2352,7 +2363,10 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
             const int2 v0 = __ldg(a.vRow + 16 * b + g), v1 = __ldg(a.vRow + 16 * b + g + 8);
             denoLo = v0.x, magicLo = (uint32_t)v0.y, denoHi = v1.x, magicHi = (uint32_t)v1.y;
         }
-        const int initLo = denoLo ? 0 : bias, initHi = denoHi ? 0 : bias;
+        // ordinary rows get the bias as a packed 16-bit add on the pair words (every biased value is a non-negative u16);
+        // border rows add it inside their division
+        const uint32_t biasPair = (uint32_t)bias | ((uint32_t)bias << 16);
+        const uint32_t biasLo = denoLo ? 0u : biasPair, biasHi = denoHi ? 0u : biasPair;
         // the B fragments of a segment (16 columns x 32 VKS source rows) are fetched one segment ahead of their mma
         auto loadSeg = [&](uint32_t (&bf)[VKS][4], const int seg) {
 #pragma unroll
@@ -2365,8 +2379,8 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
 #pragma unroll
             for (int s = 0; s < VKS; ++s) {
                 if (s == 0) {
-                    mmaS8U8k16Init(dA, af[s].x, af[s].y, bf[s][0], initLo, initHi);   // columns 0..7 of the segment, source rows 0 ... 15
-                    mmaS8U8k16Init(dB, af[s].x, af[s].y, bf[s][1], initLo, initHi);   // columns 8..15
+                    mmaS8U8k16Zero(dA, af[s].x, af[s].y, bf[s][0]);   // columns 0..7 of the segment, source rows 0 ... 15
+                    mmaS8U8k16Zero(dB, af[s].x, af[s].y, bf[s][1]);   // columns 8..15
                 } else {
                     mmaS8U8k16(dA, af[s].x, af[s].y, bf[s][0]);
                     mmaS8U8k16(dB, af[s].x, af[s].y, bf[s][1]);
@@ -2388,8 +2402,8 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
                 dA[2] = bdiv(dA[2], denoHi, magicHi), dA[3] = bdiv(dA[3], denoHi, magicHi);
                 dB[2] = bdiv(dB[2], denoHi, magicHi), dB[3] = bdiv(dB[3], denoHi, magicHi);
             }
-            const uint32_t w0 = prmt((uint32_t)dA[0], (uint32_t)dA[1], 0x5410), w1 = prmt((uint32_t)dA[2], (uint32_t)dA[3], 0x5410);
-            const uint32_t w2 = prmt((uint32_t)dB[0], (uint32_t)dB[1], 0x5410), w3 = prmt((uint32_t)dB[2], (uint32_t)dB[3], 0x5410);
+            const uint32_t w0 = addU16x2(prmt((uint32_t)dA[0], (uint32_t)dA[1], 0x5410), biasLo), w1 = addU16x2(prmt((uint32_t)dA[2], (uint32_t)dA[3], 0x5410), biasHi);
+            const uint32_t w2 = addU16x2(prmt((uint32_t)dB[0], (uint32_t)dB[1], 0x5410), biasLo), w3 = addU16x2(prmt((uint32_t)dB[2], (uint32_t)dB[3], 0x5410), biasHi);
             asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(wSt + 32 * seg), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
         };
         if (warp < nseg) {
@@ -2428,11 +2442,11 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
                              : "=r"(st.r[4]), "=r"(st.r[5]), "=r"(st.r[6]), "=r"(st.r[7]) : "r"(wl + 32));
                 st.bf = sFrag[(ti * HKS + s) * 32 + lane];
             };
-            int ll[4], lh[4], hl[4], hh[4];
+            int ll[4], mid[4], hh[4];
             auto computeStep = [&](const Step &st, const bool first) {
                 if (first) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) ll[e] = lh[e] = hl[e] = hh[e] = 0;
+                    for (int e = 0; e < 4; ++e) ll[e] = mid[e] = hh[e] = 0;
                 }
                 uint32_t alo[4], ahi[4];
 #pragma unroll
@@ -2440,10 +2454,10 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
                     alo[i] = prmt(st.r[2 * i], st.r[2 * i + 1], 0x6420);
                     ahi[i] = prmt(st.r[2 * i], st.r[2 * i + 1], 0x7531);
                 }
+                mmaU8S8(mid, alo, st.bf.z, st.bf.w);
                 mmaU8U8(ll, alo, st.bf.x, st.bf.y);
                 mmaU8S8(hh, ahi, st.bf.z, st.bf.w);
-                mmaU8S8(lh, alo, st.bf.z, st.bf.w);
-                mmaU8U8(hl, ahi, st.bf.x, st.bf.y);
+                mmaU8U8(mid, ahi, st.bf.x, st.bf.y);
             };
             auto finishTile = [&](const int ti) {
                 // thread (g, t): rows g, g + 8; columns 8 (T0 + ti) + 2 t, + 1
@@ -2452,7 +2466,7 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int init = (e & 1) ? hc.z : hc.x;
-                    v[e] = ll[e] + ((lh[e] + hl[e]) << 8) + (hh[e] << 16) + init;
+                    v[e] = ll[e] + (mid[e] << 8) + (hh[e] << 16) + init;
                 }
                 if ((hc.y | hc.w) == 0) {
 #pragma unroll

@@ -14,6 +14,6 @@ c=d.get('cfg5') or {}
 print("  cfg5", c.get('kernel'), c.get('ms_kernel'), c.get('ms_e2e'), c.get('hash_ok'), c.get('error'))
 P
 }
-for wc in 144 208 272; do for w in 1 2 4; do
+for wc in 208 272; do for w in 2 4; do
   IQO_CUDA_MMA_AUTO=1 IQO_CUDA_MMA_WCOLS=$wc IQO_CUDA_MMA_WARPS=$w timeout 600 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/r2_bench_mma_w${wc}_nw$w.json 2> gpurun_out/r2_bench_mma_w${wc}_nw$w.err; echo "rc=$? wcols=$wc warps=$w"; summ gpurun_out/r2_bench_mma_w${wc}_nw$w.json
 done; done

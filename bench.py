@@ -688,6 +688,31 @@ def _run_cuda(args, json_fd):
                "h2d_gbs_per_gpu": round(h2d * esteps / dt / 1e9, 2), "d2h_gbs_per_gpu": round(d2h * esteps / dt / 1e9, 2),
                "api": "iqo_cuda_resize_batch_host (pinned host buffers, pipelined H2D / kernel / D2H)",
                "matches_device_run": e2e_ok}
+        # the host link's own ceiling, measured the same way on all ranks at once: plain pinned copies of the same bytes,
+        # H2D and D2H on two streams (no kernel) -- e2e divided by this is the efficiency of the pipeline itself
+        try:
+            dtmp = torch.empty_like(src[:ef])
+            sA, sB = torch.cuda.Stream(), torch.cuda.Stream()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(esteps):
+                with torch.cuda.stream(sA):
+                    dtmp.copy_(hs, non_blocking=True)
+                with torch.cuda.stream(sB):
+                    hd.copy_(dst[:ef], non_blocking=True)
+            torch.cuda.synchronize()
+            dtc = time.perf_counter() - t0
+            t = torch.tensor([dtc], dtype=torch.float64, device=dev)
+            if dist is not None:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtc = float(t.item())
+            e2e["copy_only"] = {"h2d_gbs_per_gpu": round(h2d * esteps / dtc / 1e9, 2), "d2h_gbs_per_gpu": round(d2h * esteps / dtc / 1e9, 2),
+                                "equivalent_value": round(float(ef) * dw * dh * world * esteps / dtc / 1e6, 1),
+                                "note": "pinned H2D + D2H of one step's bytes on two streams, no kernel, all ranks at once: the ceiling of the host link"}
+            e2e["pipeline_efficiency"] = round(e2e["value"] / e2e["copy_only"]["equivalent_value"], 3)
+            del dtmp
+        except Exception as e:
+            e2e["copy_only"] = {"error": repr(e)}
         # the same call on pageable (ordinary malloc) buffers: what a drop-in caller that knows nothing about CUDA passes
         if rank == 0:
             try:

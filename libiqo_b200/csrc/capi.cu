@@ -166,11 +166,17 @@ struct Workspace {
     cudaStream_t stream[2];
     uint8_t *dSrc[2], *dDst[2];
     size_t srcCap, dstCap;  // bytes per slot
-    Workspace() : device(0), srcCap(0), dstCap(0)
+    // pinned host staging for callers that pass pageable memory (two slots, like the device staging)
+    uint8_t *hSrc[2], *hDst[2];
+    size_t hSrcCap, hDstCap;
+    cudaEvent_t slotDone[2];
+    Workspace() : device(0), srcCap(0), dstCap(0), hSrcCap(0), hDstCap(0)
     {
         for (int i = 0; i < 2; ++i) {
             stream[i] = 0;
             dSrc[i] = dDst[i] = 0;
+            hSrc[i] = hDst[i] = 0;
+            slotDone[i] = 0;
         }
     }
 };
@@ -796,6 +802,82 @@ int ensureStaging(iqo_cuda_resizer *r, size_t frames)
     return IQO_CUDA_OK;
 }
 
+// true when p is ordinary pageable host memory (not pinned / registered, not device)
+bool isPageable(const void *p)
+{
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+// rows x widthBytes from src to dst (different pitches allowed), split over a few host threads: one thread moves
+// ~10 GB/s, the PCIe link wants five times that
+void parallelCopy2D(uint8_t *dst, size_t dstPitch, const uint8_t *src, size_t srcPitch, size_t widthBytes, size_t rows)
+{
+    static const int envThreads = [] { const char *e = getenv("IQO_CUDA_COPY_THREADS"); return e ? atoi(e) : 0; }();
+    const size_t total = widthBytes * rows;
+    int nt = envThreads > 0 ? envThreads : int(std::min<size_t>(8, std::max<unsigned>(1u, std::thread::hardware_concurrency() / 2)));
+    if (total < (size_t(4) << 20)) nt = 1;
+    auto part = [=](size_t r0, size_t r1) {
+        if (dstPitch == widthBytes && srcPitch == widthBytes) {
+            memcpy(dst + r0 * widthBytes, src + r0 * widthBytes, (r1 - r0) * widthBytes);
+        } else {
+            for (size_t r = r0; r < r1; ++r) memcpy(dst + r * dstPitch, src + r * srcPitch, widthBytes);
+        }
+    };
+    if (nt <= 1) {
+        part(0, rows);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = (rows + nt - 1) / nt;
+    for (int i = 1; i < nt; ++i) {
+        const size_t r0 = std::min(rows, per * i), r1 = std::min(rows, r0 + per);
+        if (r1 > r0) th.push_back(std::thread(part, r0, r1));
+    }
+    part(0, std::min(rows, per));
+    for (size_t i = 0; i < th.size(); ++i) th[i].join();
+}
+
+// pinned host staging of the handle's workspace: `sBytes` / `dBytes` per slot (0: not needed)
+int ensureHostStaging(iqo_cuda_resizer *r, size_t sBytes, size_t dBytes)
+{
+    Workspace *w = r->ws;
+    for (int i = 0; i < 2; ++i)
+        if (!w->slotDone[i] && cudaEventCreateWithFlags(&w->slotDone[i], cudaEventDisableTiming) != cudaSuccess)
+            return fail(IQO_CUDA_E_CUDA, "event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (w->hSrcCap < sBytes) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFreeHost(w->hSrc[i]);
+            w->hSrc[i] = 0;
+        }
+        w->hSrcCap = 0;
+        for (int i = 0; i < 2; ++i)
+            if (cudaHostAlloc(reinterpret_cast<void **>(&w->hSrc[i]), sBytes, cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(IQO_CUDA_E_NOMEM, "cannot allocate %zu bytes of pinned host staging", sBytes);
+            }
+        w->hSrcCap = sBytes;
+    }
+    if (w->hDstCap < dBytes) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFreeHost(w->hDst[i]);
+            w->hDst[i] = 0;
+        }
+        w->hDstCap = 0;
+        for (int i = 0; i < 2; ++i)
+            if (cudaHostAlloc(reinterpret_cast<void **>(&w->hDst[i]), dBytes, cudaHostAllocPortable) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(IQO_CUDA_E_NOMEM, "cannot allocate %zu bytes of pinned host staging", dBytes);
+            }
+        w->hDstCap = dBytes;
+    }
+    return IQO_CUDA_OK;
+}
+
 // ---- plan cache and workspace pool (process wide, never destroyed: no static-destruction
 // order problems with the CUDA runtime) ----
 struct PlanKey {
@@ -937,8 +1019,11 @@ void destroyWorkspace(Workspace *w)
 {
     for (int i = 0; i < 2; ++i) {
         if (w->stream[i]) cudaStreamDestroy(w->stream[i]);
+        if (w->slotDone[i]) cudaEventDestroy(w->slotDone[i]);
         cudaFree(w->dSrc[i]);
         cudaFree(w->dDst[i]);
+        cudaFreeHost(w->hSrc[i]);
+        cudaFreeHost(w->hDst[i]);
     }
     cudaGetLastError();
     delete w;
@@ -1081,7 +1166,7 @@ void iqo_cuda_destroy(iqo_cuda_resizer *r)
     {
         std::lock_guard<std::mutex> lock(g.mu);
         // huge staging buffers are not worth keeping around
-        if (g.freeWs.size() < kMaxPooledWorkspaces && w->srcCap + w->dstCap <= (size_t(256) << 20)) {
+        if (g.freeWs.size() < kMaxPooledWorkspaces && w->srcCap + w->dstCap + w->hSrcCap + w->hDstCap <= (size_t(512) << 20)) {
             g.freeWs.push_back(w);
             pooled = true;
         }
@@ -1279,6 +1364,78 @@ int iqo_cuda_resize_batch_host(iqo_cuda_resizer *r, size_t nFrames,
     // frames whose rows follow each other at the row stride can be moved by one 2-D copy per chunk
     const bool srcRegular = (srcFrameStride == srcSt * SH);
     const bool dstRegular = (dstFrameStride == dstSt * DH);
+
+    // Pageable caller memory: the driver would stage such copies itself, synchronously and at ~10 GB/s.  Instead the
+    // frames go through the handle's pinned staging slots: a few host threads fill / drain them while the copies and
+    // the kernel of the other slot are in flight.
+    const bool srcPg = isPageable(src), dstPg = isPageable(dst);
+    if ((srcPg || dstPg) && nFrames * frameBytes >= (size_t(8) << 20)) {
+        const size_t hsPitch = r->srcPitch, hdPitch = r->dstPitch;   // the pinned slots use the device layout: one flat copy each way
+        rc = ensureHostStaging(r, srcPg ? chunk * sFrame : 0, dstPg ? chunk * dFrame : 0);
+        if (rc) return rc;
+        Workspace *w = r->ws;
+        struct Pending {
+            size_t first, n;
+            bool live;
+        } pend[2] = {{0, 0, false}, {0, 0, false}};
+        auto retire = [&](int sl) -> int {   // wait for the slot's download, then hand the frames to the caller's buffer
+            if (!pend[sl].live) return IQO_CUDA_OK;
+            CUDA_TRY(cudaEventSynchronize(w->slotDone[sl]));
+            if (dstPg) {
+                if (dstRegular && dstSt == hdPitch && DW == hdPitch)
+                    parallelCopy2D(dst + pend[sl].first * dstFrameStride, dstSt, w->hDst[sl], hdPitch, DW, DH * pend[sl].n);
+                else
+                    for (size_t f = 0; f < pend[sl].n; ++f)
+                        parallelCopy2D(dst + (pend[sl].first + f) * dstFrameStride, dstSt, w->hDst[sl] + f * dFrame, hdPitch, DW, DH);
+            }
+            pend[sl].live = false;
+            return IQO_CUDA_OK;
+        };
+        size_t donePg = 0;
+        int sl = 0;
+        while (donePg < nFrames) {
+            const size_t n = std::min(chunk, nFrames - donePg);
+            cudaStream_t st = r->stream[sl];
+            rc = retire(sl);   // the slot's previous round is complete: its staging may be refilled
+            if (rc) return rc;
+            const uint8_t *hs = src + donePg * srcFrameStride;
+            if (srcPg) {
+                if (srcRegular && srcSt == hsPitch && SW == hsPitch)   // rows without padding: one flat copy
+                    parallelCopy2D(w->hSrc[sl], hsPitch, hs, srcSt, hsPitch, SH * n);
+                else
+                    for (size_t f = 0; f < n; ++f) parallelCopy2D(w->hSrc[sl] + f * sFrame, hsPitch, hs + f * srcFrameStride, srcSt, SW, SH);
+                CUDA_TRY(cudaMemcpyAsync(r->dSrc[sl], w->hSrc[sl], n * sFrame, cudaMemcpyHostToDevice, st));
+            } else if (srcRegular) {
+                CUDA_TRY(cudaMemcpy2DAsync(r->dSrc[sl], r->srcPitch, hs, srcSt, SW, SH * n, cudaMemcpyHostToDevice, st));
+            } else {
+                for (size_t f = 0; f < n; ++f)
+                    CUDA_TRY(cudaMemcpy2DAsync(r->dSrc[sl] + f * sFrame, r->srcPitch, hs + f * srcFrameStride, srcSt, SW, SH, cudaMemcpyHostToDevice, st));
+            }
+            rc = launch(r, n, 0, DH, 0, SH, r->srcPitch, sFrame, r->dSrc[sl], r->dstPitch, dFrame, r->dDst[sl], st);
+            if (rc) return rc;
+            uint8_t *hd = dst + donePg * dstFrameStride;
+            if (dstPg) {
+                CUDA_TRY(cudaMemcpyAsync(w->hDst[sl], r->dDst[sl], n * dFrame, cudaMemcpyDeviceToHost, st));
+            } else if (dstRegular) {
+                CUDA_TRY(cudaMemcpy2DAsync(hd, dstSt, r->dDst[sl], r->dstPitch, DW, DH * n, cudaMemcpyDeviceToHost, st));
+            } else {
+                for (size_t f = 0; f < n; ++f)
+                    CUDA_TRY(cudaMemcpy2DAsync(hd + f * dstFrameStride, dstSt, r->dDst[sl] + f * dFrame, r->dstPitch, DW, DH, cudaMemcpyDeviceToHost, st));
+            }
+            CUDA_TRY(cudaEventRecord(w->slotDone[sl], st));
+            pend[sl].first = donePg;
+            pend[sl].n = n;
+            pend[sl].live = true;
+            donePg += n;
+            sl ^= 1;
+        }
+        rc = retire(sl);
+        if (rc == IQO_CUDA_OK) rc = retire(sl ^ 1);
+        if (rc) return rc;
+        CUDA_TRY(cudaStreamSynchronize(r->stream[0]));
+        CUDA_TRY(cudaStreamSynchronize(r->stream[1]));
+        return IQO_CUDA_OK;
+    }
 
     size_t done = 0;
     int slot = 0;

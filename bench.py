@@ -46,11 +46,14 @@ WORKLOADS = {
     "cfg2b_linear_720p_to_2160p": (2, 0, 1, 1280, 720, 3840, 2160, 768),
     # cfg5's ratio (1024:375, Lanczos4, 22 taps, 375 phases) on a size that fits a batch
     "cfg5s_lanczos4_8192_to_3000": (0, 4, 1, 8192, 8192, 3000, 3000, 16),
+    # Area / Linear at ratios without a dedicated streaming kernel: the tensor-path kernel
+    "area_1080p_to_720p": (1, 0, 1, 1920, 1080, 1280, 720, 1024),
+    "linear_720p_to_1080p": (2, 0, 1, 1280, 720, 1920, 1080, 1024),
 }
 DEFAULT_WORKLOAD = "cfg4_lanczos3_1080p_to_540p"
 # the other BASELINE configs, reported in `workloads` (cfg3 is added as whole YUV420 frames)
 EXTRA_WORKLOADS = ["cfg1_lanczos3_1080p_to_720p", "cfg2a_area_2160p_to_1080p", "cfg2b_linear_720p_to_2160p",
-                   "cfg5s_lanczos4_8192_to_3000"]
+                   "cfg5s_lanczos4_8192_to_3000", "area_1080p_to_720p", "linear_720p_to_1080p"]
 CFG3 = (0, 2, 3840, 2160, 1920, 1080, 256)   # kind, degree, srcW, srcH, dstW, dstH, frames
 CFG5 = (0, 4, 1, 32768, 32768, 12000, 12000)
 METRIC = "dst_mpix_per_s_lanczos3_u8_resize"

@@ -151,10 +151,10 @@ struct SharedPlan {
     int32_t *sRowsY;      // small-kernel path
     uint32_t *sMagicY;
     // tensor-path kernel tables
-    int32_t *mVBlock, *mVRow, *mStripXs, *mHTile, *mHCol;
+    int32_t *mVBlock, *mVRow, *mVRowMap, *mStripXs, *mHTile, *mHCol;
     uint32_t *mVFrag, *mHFrag;
     SharedPlan()
-        : device(0), dBorderY(0), dMagicY(0), dSBorderY(0), dBorderX(0), dBorderXo(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), rRowRec(0), gRowRec(0), sRowsY(0), sMagicY(0), mVBlock(0), mVRow(0), mStripXs(0), mHTile(0), mHCol(0), mVFrag(0), mHFrag(0)
+        : device(0), dBorderY(0), dMagicY(0), dSBorderY(0), dBorderX(0), dBorderXo(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), rRowRec(0), gRowRec(0), sRowsY(0), sMagicY(0), mVBlock(0), mVRow(0), mVRowMap(0), mStripXs(0), mHTile(0), mHCol(0), mVFrag(0), mHFrag(0)
     {
     }
     ~SharedPlan();
@@ -254,6 +254,7 @@ SharedPlan::~SharedPlan()
     cudaFree(pCwX);
     cudaFree(mVBlock);
     cudaFree(mVRow);
+    cudaFree(mVRowMap);
     cudaFree(mStripXs);
     cudaFree(mHTile);
     cudaFree(mHCol);
@@ -359,6 +360,8 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         q.vBlock = reinterpret_cast<const int2 *>(sp.mVBlock);
         q.vFrag = reinterpret_cast<const uint4 *>(sp.mVFrag);
         q.vRow = reinterpret_cast<const int2 *>(sp.mVRow);
+        q.vRowMap = sp.mVRowMap;
+        q.isSigned = mp.isSigned ? 1 : 0;
         q.stripXs = sp.mStripXs;
         q.hTile = reinterpret_cast<const int2 *>(sp.mHTile);
         q.hFrag = reinterpret_cast<const uint4 *>(sp.mHFrag);
@@ -394,7 +397,7 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
                     if (f0 != 0) return fail(IQO_CUDA_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(cr));
                     break;
                 }
-                r->lastKernel = "lanczos_mma";
+                r->lastKernel = r->plan.kind == kLanczos ? "lanczos_mma" : r->plan.kind == kArea ? "area_mma" : "linear_mma";
                 CUDA_TRY(launchMma(q, tmap, stream));
             }
             if (ok) return 1;
@@ -980,7 +983,7 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
     buildMmaPlan(sp->plan, sp->mma, envMmaWcols > 0 ? envMmaWcols : IQO_MMA_WCOLS_DEFAULT);
     if (sp->mma.eligible) {
         const MmaPlan &q = sp->mma;
-        if (encodeTiled() == 0 || !uploadVec(sp->mVBlock, q.vBlock) || !uploadVec(sp->mVRow, q.vRow) || !uploadVec(sp->mStripXs, q.stripXs) ||
+        if (encodeTiled() == 0 || !uploadVec(sp->mVBlock, q.vBlock) || !uploadVec(sp->mVRow, q.vRow) || !uploadVec(sp->mVRowMap, q.vRowMap) || !uploadVec(sp->mStripXs, q.stripXs) ||
             !uploadVec(sp->mHTile, q.hTile) || !uploadVec(sp->mHCol, q.hCol) || !uploadVec(sp->mVFrag, q.vFrag) || !uploadVec(sp->mHFrag, q.hFrag)) {
             cudaGetLastError();
             sp->mma.eligible = false;

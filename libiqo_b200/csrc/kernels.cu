@@ -2210,6 +2210,26 @@ __device__ __forceinline__ void mmaS8U8k16Zero(int (&d)[4], uint32_t a0, uint32_
     asm("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
         : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a0), "r"(a1), "r"(b), "r"(0));
 }
+template <bool SIGNED>
+__device__ __forceinline__ void mmaCoefU8k16(int (&d)[4], uint32_t a0, uint32_t a1, uint32_t b, const bool zero)
+{
+    // A = coefficient bytes (s8 for Lanczos, u8 for Area / Linear), B = source bytes (u8)
+    if (SIGNED) {
+        if (zero)
+            asm("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
+                : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a0), "r"(a1), "r"(b), "r"(0));
+        else
+            asm("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(b));
+    } else {
+        if (zero)
+            asm("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%7,%7,%7,%7};"
+                : "=r"(d[0]), "=r"(d[1]), "=r"(d[2]), "=r"(d[3]) : "r"(a0), "r"(a1), "r"(b), "r"(0));
+        else
+            asm("mma.sync.aligned.m16n8k16.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(b));
+    }
+}
 __device__ __forceinline__ uint32_t addU16x2(uint32_t a, uint32_t b)
 {
     uint32_t d;
@@ -2246,7 +2266,7 @@ constexpr int kMmaChunk = 8;   // plan.hpp kMmaChunkRows
 // The warps of a CTA (a.warps = 1, 2 or 4) share one strip: FIFO, W tile, output tile and tables are common, the
 // segments of the vertical pass, the tiles of the horizontal pass and the rows of the store are dealt out round robin;
 // two CTA barriers per block separate the phases.
-template <int VKS, int HKS>
+template <int VKS, int HKS, bool SIGNED>
 __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(const __grid_constant__ MmaKernelArgs prm)
 {
     extern __shared__ __align__(128) uint8_t mmaSmem[];
@@ -2349,14 +2369,13 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     for (int s = 0; s < VKS; ++s) af[s] = __ldg(a.vFrag + ((size_t)blkFirst * VKS + s) * 32 + lane);
 
     for (int b = blkFirst; b < blkEnd; ++b) {
-        const int r0 = vb.x, rLast = vb.x + vb.y - 1;
         waitGroup();   // the rows of this block have landed
 
         // ---------------- vertical pass ----------------
-        uint32_t ra[VKS];   // k index 32 s + lane is source row r0 + 32 s + lane; rows past the block's last one meet zero coefficients
+        uint32_t ra[VKS];   // k slot 32 s + lane reads the source row the planner's map names (unused slots: any resident row, zero coefficients)
 #pragma unroll
-        for (int s = 0; s < VKS; ++s) ra[s] = rowAddr(min(r0 + 32 * s + lane, rLast));
-        const bool borderBlock = (16 * b < a.mbY) || (16 * b + 16 > a.meY);
+        for (int s = 0; s < VKS; ++s) ra[s] = rowAddr(__ldg(a.vRowMap + ((size_t)b * VKS + s) * 32 + lane));
+        const bool borderBlock = SIGNED && ((16 * b < a.mbY) || (16 * b + 16 > a.meY));
         int denoLo = 0, denoHi = 0;
         uint32_t magicLo = 0, magicHi = 0;
         if (borderBlock) {
@@ -2378,15 +2397,10 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
             int dA[4], dB[4];
 #pragma unroll
             for (int s = 0; s < VKS; ++s) {
-                if (s == 0) {
-                    mmaS8U8k16Zero(dA, af[s].x, af[s].y, bf[s][0]);   // columns 0..7 of the segment, source rows 0 ... 15
-                    mmaS8U8k16Zero(dB, af[s].x, af[s].y, bf[s][1]);   // columns 8..15
-                } else {
-                    mmaS8U8k16(dA, af[s].x, af[s].y, bf[s][0]);
-                    mmaS8U8k16(dB, af[s].x, af[s].y, bf[s][1]);
-                }
-                mmaS8U8k16(dA, af[s].z, af[s].w, bf[s][2]);   // source rows 32 s + 16 ... + 31
-                mmaS8U8k16(dB, af[s].z, af[s].w, bf[s][3]);
+                mmaCoefU8k16<SIGNED>(dA, af[s].x, af[s].y, bf[s][0], s == 0);   // columns 0..7 of the segment, k slots 32 s ... + 15
+                mmaCoefU8k16<SIGNED>(dB, af[s].x, af[s].y, bf[s][1], s == 0);   // columns 8..15
+                mmaCoefU8k16<SIGNED>(dA, af[s].z, af[s].w, bf[s][2], false);    // k slots 32 s + 16 ... + 31
+                mmaCoefU8k16<SIGNED>(dB, af[s].z, af[s].w, bf[s][3], false);
             }
             if (borderBlock && (denoLo | denoHi)) {
                 // resizeYborder: int16 numerator * 64 / denominator, C (truncating) division (see halfVerticalStrip)
@@ -2454,9 +2468,10 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
                     alo[i] = prmt(st.r[2 * i], st.r[2 * i + 1], 0x6420);
                     ahi[i] = prmt(st.r[2 * i], st.r[2 * i + 1], 0x7531);
                 }
-                mmaU8S8(mid, alo, st.bf.z, st.bf.w);
+                // coefficient high plane: signed for Lanczos, 0 .. 128 for Area / Linear
+                if (SIGNED) mmaU8S8(mid, alo, st.bf.z, st.bf.w); else mmaU8U8(mid, alo, st.bf.z, st.bf.w);
                 mmaU8U8(ll, alo, st.bf.x, st.bf.y);
-                mmaU8S8(hh, ahi, st.bf.z, st.bf.w);
+                if (SIGNED) mmaU8S8(hh, ahi, st.bf.z, st.bf.w); else mmaU8U8(hh, ahi, st.bf.z, st.bf.w);
                 mmaU8U8(mid, ahi, st.bf.x, st.bf.y);
             };
             auto finishTile = [&](const int ti) {
@@ -2468,7 +2483,10 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
                     const int init = (e & 1) ? hc.z : hc.x;
                     v[e] = ll[e] + (mid[e] << 8) + (hh[e] << 16) + init;
                 }
-                if ((hc.y | hc.w) == 0) {
+                if (!SIGNED) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) v[e] = (int)(short)(v[e] >> 23);   // Area / Linear: 8 + 15 fixed-point bits
+                } else if ((hc.y | hc.w) == 0) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) v[e] = (int)(short)(v[e] >> 20);
                 } else {
@@ -2541,17 +2559,17 @@ size_t mmaSmemBytes(int wcols, int stripTiles, int nChunks, int hKMax)
            size_t(mmaTableBytes(stripTiles, hKMax)) + 8 * size_t(nChunks) + 16;
 }
 
-template <int VKS, int HKS>
+template <int VKS, int HKS, bool SIGNED>
 cudaError_t launchMmaT(const MmaKernelArgs &p, dim3 grid, size_t smem, cudaStream_t stream)
 {
     static PerDeviceOnce attrSet;
     const int dev = currentDevice();
     if (!attrSet.done(dev)) {
-        cudaError_t e = cudaFuncSetAttribute(resizeLanczosMmaKernel<VKS, HKS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(resizeLanczosMmaKernel<VKS, HKS, SIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attrSet.set(dev);
     }
-    resizeLanczosMmaKernel<VKS, HKS><<<grid, 32 * p.a.warps, smem, stream>>>(p);
+    resizeLanczosMmaKernel<VKS, HKS, SIGNED><<<grid, 32 * p.a.warps, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -2569,7 +2587,7 @@ cudaError_t launchMma(const MmaArgs &a, const CUtensorMap &tmap, cudaStream_t st
     dim3 grid(strips, bands, a.nFrames);
     g_launches.fetch_add(1);
 #define IQO_MMA_CASE(V, H) \
-    if (a.vKMax == V && a.hKMax == H) return launchMmaT<V, H>(p, grid, smem, stream);
+    if (a.vKMax == V && a.hKMax == H) return a.isSigned ? launchMmaT<V, H, true>(p, grid, smem, stream) : launchMmaT<V, H, false>(p, grid, smem, stream);
     IQO_MMA_CASE(1, 1) IQO_MMA_CASE(1, 2) IQO_MMA_CASE(1, 3)
     IQO_MMA_CASE(2, 1) IQO_MMA_CASE(2, 2) IQO_MMA_CASE(2, 3)
     IQO_MMA_CASE(3, 1) IQO_MMA_CASE(3, 2) IQO_MMA_CASE(3, 3)

@@ -211,6 +211,8 @@ struct MmaArgs {
     const int2 *vBlock;
     const uint4 *vFrag;
     const int2 *vRow;
+    const int32_t *vRowMap;        // [blocks][vKMax * 32]: source row of every k slot
+    int isSigned;                  // Lanczos (signed coefficients, 20-bit shift, border divisions) or Area / Linear
     const int32_t *stripXs;
     const int2 *hTile;
     const uint4 *hFrag;

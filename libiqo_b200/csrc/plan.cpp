@@ -1000,10 +1000,15 @@ void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
     m.stripTiles = 0;
     m.wcols = wcols;
     const AxisPlan &X = p.x, &Y = p.y;
-    if (p.kind != kLanczos) { m.why = "not Lanczos"; return; }
-    if (!X.identity && X.mainBegin >= X.mainEnd) { m.why = "no main columns (source narrower than the kernel)"; return; }
-    if (Y.coefMin < -128 || Y.coefMax > 127) { m.why = "vertical coefficients do not fit int8"; return; }
-    if (X.coefMin < -32768 || X.coefMax > 32767) { m.why = "horizontal coefficients do not fit two byte planes"; return; }
+    m.isSigned = p.workSigned;
+    if (p.kind == kLanczos) {
+        if (!X.identity && X.mainBegin >= X.mainEnd) { m.why = "no main columns (source narrower than the kernel)"; return; }
+        if (Y.coefMin < -128 || Y.coefMax > 127) { m.why = "vertical coefficients do not fit int8"; return; }
+        if (X.coefMin < -32768 || X.coefMax > 32767) { m.why = "horizontal coefficients do not fit two byte planes"; return; }
+    } else {
+        if (Y.coefMin < 0 || Y.coefMax > 256) { m.why = "vertical weights outside 0..256"; return; }
+        if (X.coefMin < 0 || X.coefMax > 32768) { m.why = "horizontal weights outside 0..32768"; return; }
+    }
     if (X.S % 2 != 0) { m.why = "odd source width (the tensor map views the rows as 16-bit pairs)"; return; }
     if (wcols % 16 != 0 || wcols < 64 || wcols > 512) { m.why = "bad strip width"; return; }
     const int NX = X.N, NY = Y.N;
@@ -1017,7 +1022,7 @@ void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
             (c > 0 ? pos : neg) += c;
         }
         long long lo = 255 * neg, hi = 255 * pos;
-        if (lo < -32768 || hi > 32767) { m.why = "vertical sum may wrap int16"; return; }
+        if (m.isSigned ? (lo < -32768 || hi > 32767) : (hi > 65535)) { m.why = "vertical sum may wrap 16 bits"; return; }
         const int den = Y.deno[size_t(r)];
         if (den != 0) {
             if (den < 0 || den > 255) { m.why = "border denominator out of range"; return; }
@@ -1057,10 +1062,22 @@ void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
     }
     // the kernel's source FIFO only moves forward: first rows must not decrease from block to block
     for (int64_t b = blocks - 2; b >= 0; --b) lo[size_t(b)] = std::min(lo[size_t(b)], lo[size_t(b) + 1]);
+    // Area / Linear: rows that carry a weight of 256 somewhere in the block need a second k slot (255 + 1)
+    std::vector<std::vector<int64_t> > dup(static_cast<size_t>(blocks));
+    if (!m.isSigned)
+        for (int64_t b = 0; b < blocks; ++b)
+            for (int64_t y = 16 * b; y < std::min<int64_t>(Y.D, 16 * b + 16); ++y) {
+                const int32_t *c = &Y.coef[size_t(Y.row[size_t(y)]) * NY];
+                for (int i = 0; i < NY; ++i)
+                    if (c[i] == 256) {
+                        const int64_t row = Y.first[size_t(y)] + i;
+                        if (std::find(dup[size_t(b)].begin(), dup[size_t(b)].end(), row) == dup[size_t(b)].end()) dup[size_t(b)].push_back(row);
+                    }
+            }
     int chunksNeeded = 1;
     for (int64_t b = 0; b < blocks; ++b) {
         const int64_t rlo = lo[size_t(b)], rhi = m.vBlock[size_t(b) * 2 + 1];
-        const int ks = int((rhi - rlo + 32) / 32);
+        const int ks = int((rhi - rlo + 1 + int64_t(dup[size_t(b)].size()) + 31) / 32);
         if (ks > kMmaMaxKSteps) { m.why = "vertical kernel spans more than three 32-row k-steps per 16 destination rows"; return; }
         m.vKMax = std::max(m.vKMax, ks);
         m.vBlock[size_t(b) * 2] = int32_t(rlo);
@@ -1070,15 +1087,23 @@ void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
     m.nChunks = 2;
     while (m.nChunks < chunksNeeded) m.nChunks *= 2;
     m.vFrag.assign(size_t(blocks) * m.vKMax * 128, 0);
+    m.vRowMap.assign(size_t(blocks) * m.vKMax * 32, 0);
     for (int64_t b = 0; b < blocks; ++b) {
-        const int ks = (m.vBlock[size_t(b) * 2 + 1] + 31) / 32;
-        // A[row][k]: coefficient of destination row 16 b + row for source row lo + k
+        const int nrows = m.vBlock[size_t(b) * 2 + 1];
+        const int nslots = nrows + int(dup[size_t(b)].size());
+        const int ks = (nslots + 31) / 32;
+        int32_t *rmap = &m.vRowMap[size_t(b) * m.vKMax * 32];
+        for (int k = 0; k < m.vKMax * 32; ++k)
+            rmap[k] = int32_t(k < nrows ? lo[size_t(b)] + k : k < nslots ? dup[size_t(b)][size_t(k - nrows)] : lo[size_t(b)]);
+        // A[row][k]: coefficient of destination row 16 b + row for the source row of slot k
         auto coefAt = [&](int row, int64_t k) -> uint32_t {
             const int64_t y = 16 * b + row;
-            if (y >= Y.D) return 0u;
-            const int64_t i = lo[size_t(b)] + k - Y.first[size_t(y)];
+            if (y >= Y.D || k >= nslots) return 0u;
+            const int64_t i = int64_t(rmap[k]) - Y.first[size_t(y)];
             if (i < 0 || i >= NY) return 0u;
-            return uint32_t(Y.coef[size_t(Y.row[size_t(y)]) * NY + size_t(i)]) & 0xffu;
+            const int c = Y.coef[size_t(Y.row[size_t(y)]) * NY + size_t(i)];
+            if (c == 256) return k < nrows ? 255u : 1u;   // split over the row's own slot and its extra slot
+            return k < nrows ? uint32_t(c) & 0xffu : 0u;
         };
         for (int s = 0; s < ks; ++s)
             for (int lane = 0; lane < 32; ++lane) {
@@ -1164,7 +1189,13 @@ void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
                     for (int i = 0; i < 4; ++i) {
                         const int off = (i & 1) + 2 * t + ((i >> 1) ? 8 : 0);
                         uint32_t l, hi;
-                        splitPlanes(coefAt(g, c0[size_t(T)] + 32 * s + 16 * h + off), l, hi);
+                        const int cv = coefAt(g, c0[size_t(T)] + 32 * s + 16 * h + off);
+                        if (m.isSigned) {
+                            splitPlanes(cv, l, hi);
+                        } else {
+                            l = uint32_t(cv) & 0xffu;
+                            hi = uint32_t(cv) >> 8;   // 0 .. 128
+                        }
                         f[h] |= l << (8 * i);
                         f[2 + h] |= hi << (8 * i);
                     }

@@ -76,6 +76,8 @@ LARGE = [
     (LINEAR, 0, 1, 960, 540, 1920, 1080, 0, 0, 7, None),
     (LINEAR, 0, 1, 640, 480, 1600, 1000, 0, 1, 8, None),
     (LANCZOS, 4, 1, 8192, 8192, 3000, 3000, 0, 0, 1, None),  # bench.py's cfg5s workload (cfg5's ratio, batch-sized)
+    (AREA, 0, 1, 1920, 1080, 1280, 720, 0, 0, 1, None),      # bench.py: Area at a general ratio (3:2)
+    (LINEAR, 0, 1, 1280, 720, 1920, 1080, 0, 0, 1, None),    # bench.py: Linear at a non-integer ratio (1.5x)
 ]
 
 # BASELINE config 5 at full size (1 GiB source): hash only, kept out of LARGE so that the per-case tests do

@@ -145,3 +145,77 @@ def test_mma_bands_batches_and_device_pitches():
         torch.cuda.synchronize()
         assert r.last_kernel() != "lanczos_mma"
     assert np.array_equal(ddst.cpu().numpy(), oracle_resize(LANCZOS, host, 240, 135, 3, sw=480)[1])
+
+
+# ---------------------------------------------------------------------------------------------
+# Area / Linear on the same kernel (unsigned byte planes, 23-bit shift; a weight of 256 is split 255 + 1 over two
+# k slots that read the same source row).  Replaces src/IQOAreaResizerImpl_Generic.cpp:303-368 and
+# src/IQOLinearResizerImpl_Generic.cpp:290-407 for ratios without a dedicated streaming kernel.
+# ---------------------------------------------------------------------------------------------
+from oracle_lib import AREA, LINEAR  # noqa: E402
+
+AL_CASES = [
+    # (kind, srcW, srcH, dstW, dstH, srcPad, dstPad)
+    (AREA, 1920, 1080, 1280, 720, 0, 0),
+    (AREA, 1000, 1000, 333, 777, 8, 3),
+    (AREA, 64, 48, 40, 30, 0, 0),
+    (AREA, 40, 30, 64, 48, 0, 0),            # "up" = nearest-floor (single taps of weight 256 / 32768)
+    (AREA, 64, 48, 64, 30, 0, 0),
+    (AREA, 64, 48, 40, 48, 0, 0),
+    (AREA, 78, 31, 5, 3, 2, 0),
+    (AREA, 3840, 2160, 1920, 1080, 0, 0),    # cfg2a on the general kernel
+    (LINEAR, 960, 540, 1920, 1080, 0, 0),
+    (LINEAR, 640, 480, 1600, 1000, 0, 1),
+    (LINEAR, 1280, 720, 3840, 2160, 0, 0),   # cfg2b on the general kernel
+    (LINEAR, 40, 30, 100, 75, 0, 0),
+    (LINEAR, 32, 18, 32, 54, 0, 0),
+    (LINEAR, 32, 18, 96, 18, 0, 0),
+    (LINEAR, 2, 2, 5, 6, 14, 0),
+    (LINEAR, 200, 150, 500, 420, 8, 4),
+]
+
+
+@pytest.mark.parametrize("case", AL_CASES)
+def test_mma_kernel_area_linear(case):
+    kind, sw, sh, dw, dh, spad, dpad = case
+    src = lcg_image(sh, sw + spad, seed=37)
+    rc, want = oracle_resize(kind, src, dw, dh, sw=sw, dst_stride=dw + dpad)
+    assert rc == 0
+    dst = np.full((dh, dw + dpad), 0xA5, dtype=np.uint8)
+    with iqo.make_resizer(kind, 0, sw, sh, dw, dh) as r:
+        r.set_path(iqo.PATH_MMA)
+        r.resize(sw + spad, src, dw + dpad, dst)
+        kernel = r.last_kernel()
+    assert kernel == ("area_mma" if kind == AREA else "linear_mma"), kernel
+    bad = np.argwhere(dst != want)
+    assert bad.size == 0, (len(bad), bad[:8].tolist())
+    for v in (0, 255):
+        flat = np.full((sh, sw), v, np.uint8)
+        out = np.zeros((dh, dw), dtype=np.uint8)
+        with iqo.make_resizer(kind, 0, sw, sh, dw, dh) as r:
+            r.set_path(iqo.PATH_MMA)
+            r.resize(sw, flat, dw, out)
+        assert (out == v).all()
+
+
+def test_mma_area_linear_random_sweep():
+    rng = random.Random(777)
+    ran = 0
+    for _ in range(120):
+        kind = rng.choice([AREA, LINEAR])
+        sw, sh = 2 * rng.randint(2, 200), rng.randint(4, 200)
+        if kind == LINEAR:
+            dw, dh = rng.randint(sw, 3 * sw), rng.randint(sh, 3 * sh)
+        else:
+            dw, dh = rng.randint(1, sw + 8), rng.randint(1, sh + 8)
+        src = lcg_image(sh, sw + (-sw) % 16, seed=rng.randint(1, 1 << 30))
+        dpad = rng.randint(0, 5)
+        rc, want = oracle_resize(kind, src, dw, dh, sw=sw, dst_stride=dw + dpad)
+        assert rc == 0
+        dst = np.full((dh, dw + dpad), 0xA5, dtype=np.uint8)
+        with iqo.make_resizer(kind, 0, sw, sh, dw, dh) as r:
+            r.set_path(iqo.PATH_MMA)
+            r.resize(src.shape[1], src, dw + dpad, dst)
+            ran += r.last_kernel().endswith("_mma")
+        assert np.array_equal(dst, want), (kind, sw, sh, dw, dh)
+    assert ran >= 100, ran

@@ -349,6 +349,9 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         q.vKMax = mp.vKMax;
         q.hKMax = mp.hKMax;
         q.nChunks = mp.nChunks;
+        static const int envMmaPow2 = [] { const char *e = getenv("IQO_CUDA_MMA_POW2"); return e ? atoi(e) : 0; }();
+        if (envMmaPow2)   // tuning knob: round the FIFO up to a power of two chunks (more look-ahead room, fewer CTAs per SM)
+            while (q.nChunks & (q.nChunks - 1)) ++q.nChunks;
         static const int envMmaWarps = [] { const char *e = getenv("IQO_CUDA_MMA_WARPS"); return e ? atoi(e) : IQO_MMA_WARPS_DEFAULT; }();
         q.warps = (envMmaWarps == 1 || envMmaWarps == 2 || envMmaWarps == 4) ? envMmaWarps : IQO_MMA_WARPS_DEFAULT;
         q.workBias = mp.workBias;
@@ -356,7 +359,8 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         q.meY = int(r->plan.y.mainEnd);
         q.mbX = int(r->plan.x.mainBegin);
         q.meX = int(r->plan.x.mainEnd);
-        q.dstVec = ((uintptr_t)dst % 16) == 0 && dstSt % 16 == 0 && dstFrameStride % 16 == 0;
+        q.dstVec = (((uintptr_t)dst % 16) == 0 && dstSt % 16 == 0 && dstFrameStride % 16 == 0) ? 2
+                   : (((uintptr_t)dst % 8) == 0 && dstSt % 8 == 0 && dstFrameStride % 8 == 0) ? 1 : 0;
         q.vBlock = reinterpret_cast<const int2 *>(sp.mVBlock);
         q.vFrag = reinterpret_cast<const uint4 *>(sp.mVFrag);
         q.vRow = reinterpret_cast<const int2 *>(sp.mVRow);

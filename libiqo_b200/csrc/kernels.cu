@@ -2281,7 +2281,8 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     const int xs = __ldg(a.stripXs + strip);                    // source column of W element 0
     const int rowBytes = a.wcols;                               // FIFO row
     const int chunkBytes = kMmaChunk * rowBytes;
-    const int chunkMask = a.nChunks - 1;                        // nChunks is a power of two
+    const uint32_t chunkRcp = (uint32_t)(0x100000000ull / (uint32_t)a.nChunks) + 1u;   // j mod nChunks by multiply-high (j < 2^27)
+    auto chunkSlot = [&](const int j) -> int { return j - (int)__umulhi((uint32_t)j, chunkRcp) * a.nChunks; };
     const int wStride = mmaWStride(a.wcols), oStride = mmaOutStride(a.stripTiles);
     const uint32_t fifoBase = smemAddr(mmaSmem);
     const uint32_t wBase = fifoBase + a.nChunks * chunkBytes;
@@ -2306,7 +2307,7 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     }
     __syncthreads();
 
-    // chunk c (global source rows 8 c ... 8 c + 7) lives in FIFO slot (c - cStart) & chunkMask.  The chunks requested for
+    // chunk c (global source rows 8 c ... 8 c + 7) lives in FIFO slot (c - cStart) mod nChunks.  The chunks requested for
     // one block form a group that completes one phase of an mbarrier: group i uses barrier i & 1, phase (i >> 1) & 1.
     int2 vb = __ldg(a.vBlock + blkFirst);   // {first source row, rows}
     const int cStart = vb.x >> 3;           // arithmetic shift: floor
@@ -2323,7 +2324,7 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");   // nothing new: the phase completes at once
             }
             for (int c = cIssued; c <= cHi; ++c) {
-                const int slot = (c - cStart) & chunkMask;
+                const int slot = chunkSlot(c - cStart);
                 if (lane == 0)
                     asm volatile(
                         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -2343,7 +2344,7 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
         ++grpWaited;
     };
     auto rowAddr = [&](const int r) -> uint32_t {   // shared address of global source row r (its chunk must be resident)
-        return fifoBase + (((r >> 3) - cStart) & chunkMask) * chunkBytes + (r & 7) * rowBytes;
+        return fifoBase + chunkSlot((r >> 3) - cStart) * chunkBytes + (r & 7) * rowBytes;
     };
     issueUpTo((vb.x + vb.y - 1) >> 3);   // the first block's rows: in flight while the tables are staged
 
@@ -2358,15 +2359,21 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     const uint32_t wSt = wBase + ((mi & 1) * 8 + ri) * wStride + (mi >> 1) * 16;   // stmatrix: M0/M1 rows 0-7/8-15 of columns 0-7, M2/M3 of columns 8-15
     const uint32_t wLd = wBase + ((mi >> 1) * 8 + ri) * wStride + (mi & 1) * 16;   // ldmatrix: M0/M1 columns 0-7/8-15 of rows 0-7, M2/M3 of rows 8-15
     const int bias = a.workBias;
-    // output tile -> global: lanes per row = the power of two that covers the row's 16-byte pieces
-    const int nch = (tw + 15) >> 4;
+    // output tile -> global in pieces of 16 bytes (a.dstVec == 2), 8 bytes (1: strips start on multiples of 8 pixels) or
+    // single bytes (0); threads per row = the power of two that covers the row's pieces
+    const int pieceShift = a.dstVec == 2 ? 4 : a.dstVec == 1 ? 3 : 0;
+    const int nch = (tw + (1 << pieceShift) - 1) >> pieceShift;
     int lprShift = 0;
-    while ((1 << lprShift) < nch) ++lprShift;
+    while ((1 << lprShift) < nch && (1 << lprShift) < (int)blockDim.x) ++lprShift;
     const int stRow = threadIdx.x >> lprShift, stCh = threadIdx.x & ((1 << lprShift) - 1), stRows = (int)blockDim.x >> lprShift;
 
     uint4 af[VKS];   // A fragments (coefficients) of the running block
+    int rmap[VKS];   // source rows of this lane's k slots
 #pragma unroll
-    for (int s = 0; s < VKS; ++s) af[s] = __ldg(a.vFrag + ((size_t)blkFirst * VKS + s) * 32 + lane);
+    for (int s = 0; s < VKS; ++s) {
+        af[s] = __ldg(a.vFrag + ((size_t)blkFirst * VKS + s) * 32 + lane);
+        rmap[s] = __ldg(a.vRowMap + ((size_t)blkFirst * VKS + s) * 32 + lane);
+    }
 
     for (int b = blkFirst; b < blkEnd; ++b) {
         waitGroup();   // the rows of this block have landed
@@ -2374,7 +2381,7 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
         // ---------------- vertical pass ----------------
         uint32_t ra[VKS];   // k slot 32 s + lane reads the source row the planner's map names (unused slots: any resident row, zero coefficients)
 #pragma unroll
-        for (int s = 0; s < VKS; ++s) ra[s] = rowAddr(__ldg(a.vRowMap + ((size_t)b * VKS + s) * 32 + lane));
+        for (int s = 0; s < VKS; ++s) ra[s] = rowAddr(rmap[s]);
         const bool borderBlock = SIGNED && ((16 * b < a.mbY) || (16 * b + 16 > a.meY));
         int denoLo = 0, denoHi = 0;
         uint32_t magicLo = 0, magicHi = 0;
@@ -2439,7 +2446,10 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
             vb = __ldg(a.vBlock + b + 1);
             issueUpTo((vb.x + vb.y - 1) >> 3);
 #pragma unroll
-            for (int s = 0; s < VKS; ++s) af[s] = __ldg(a.vFrag + ((size_t)(b + 1) * VKS + s) * 32 + lane);
+            for (int s = 0; s < VKS; ++s) {
+                af[s] = __ldg(a.vFrag + ((size_t)(b + 1) * VKS + s) * 32 + lane);
+                rmap[s] = __ldg(a.vRowMap + ((size_t)(b + 1) * VKS + s) * 32 + lane);
+            }
         }
 
         // ---------------- horizontal pass: tiles in pairs, the operands of a step fetched one step ahead ----------------
@@ -2524,25 +2534,21 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
         {
             const int yb = 16 * b;
             const int yLo = max(a.dstRow0, yb), yHi = min(a.dstRow0 + a.dstRows, yb + 16);   // rows of the block inside the launch
-            if (a.dstVec) {
-                if (stCh < nch) {
-                    for (int r = stRow; r < 16; r += stRows) {
-                        const int y = yb + r;
-                        if (y < yLo || y >= yHi) continue;
-                        const uint8_t *sp = oTile + r * oStride + 16 * stCh;
-                        uint8_t *dp = dst + (long long)(y - a.dstRow0) * a.dstPitch + tx0 + 16 * stCh;
-                        if (16 * stCh + 16 <= tw) {
-                            *reinterpret_cast<uint4 *>(dp) = *reinterpret_cast<const uint4 *>(sp);
-                        } else {
-                            for (int i = 0; i < tw - 16 * stCh; ++i) dp[i] = sp[i];
-                        }
+            uint8_t *drow = dst + (long long)(yb + stRow - a.dstRow0) * a.dstPitch + tx0;
+            const long long dstep = (long long)stRows * a.dstPitch;
+            for (int r = stRow; r < 16; r += stRows, drow += dstep) {
+                const int y = yb + r;
+                if (y < yLo || y >= yHi) continue;
+                const uint8_t *srow = oTile + r * oStride;
+                for (int ch = stCh; ch < nch; ch += 1 << lprShift) {   // one trip unless a row has more pieces than the CTA has threads
+                    const int x = ch << pieceShift;
+                    if (pieceShift == 4 && x + 16 <= tw) {
+                        *reinterpret_cast<uint4 *>(drow + x) = *reinterpret_cast<const uint4 *>(srow + x);
+                    } else if (pieceShift == 3 && x + 8 <= tw) {
+                        *reinterpret_cast<uint2 *>(drow + x) = *reinterpret_cast<const uint2 *>(srow + x);
+                    } else {
+                        for (int i = x; i < min(x + (1 << pieceShift), tw); ++i) drow[i] = srow[i];
                     }
-                }
-            } else {
-                for (int r = warp; r < 16; r += nw) {
-                    const int y = yb + r;
-                    if (y < yLo || y >= yHi) continue;
-                    for (int x = lane; x < tw; x += 32) dst[(long long)(y - a.dstRow0) * a.dstPitch + tx0 + x] = oTile[r * oStride + x];
                 }
             }
         }

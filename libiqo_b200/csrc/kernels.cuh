@@ -207,7 +207,7 @@ struct MmaArgs {
     int warps;                     // warps per CTA (1, 2 or 4): they share the strip's FIFO / W / tables
     int workBias;
     int mbY, meY, mbX, meX;
-    int dstVec;                    // destination rows can take 16-byte stores
+    int dstVec;                    // destination rows can take 16-byte (2) / 8-byte (1) stores, else 0
     const int2 *vBlock;
     const uint4 *vFrag;
     const int2 *vRow;

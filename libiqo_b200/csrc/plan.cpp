@@ -1084,8 +1084,7 @@ void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
         m.vBlock[size_t(b) * 2 + 1] = int32_t(rhi - rlo + 1);   // source rows the block reads; k beyond them meets zero coefficients
         chunksNeeded = std::max(chunksNeeded, int(floorTo(rhi, kMmaChunkRows) / kMmaChunkRows - floorTo(rlo, kMmaChunkRows) / kMmaChunkRows + 1));
     }
-    m.nChunks = 2;
-    while (m.nChunks < chunksNeeded) m.nChunks *= 2;
+    m.nChunks = std::max(2, chunksNeeded);
     m.vFrag.assign(size_t(blocks) * m.vKMax * 128, 0);
     m.vRowMap.assign(size_t(blocks) * m.vKMax * 32, 0);
     for (int64_t b = 0; b < blocks; ++b) {

@@ -226,7 +226,7 @@ struct MmaPlan {
     int workBias;                   // added to the intermediate: non-negative 16-bit values
     // vertical: 16-row destination blocks (global block index = dst row / 16)
     int vKMax;                      // most k-steps of a block (<= kMmaMaxKSteps)
-    int nChunks;                    // 8-row chunks of the kernel's source FIFO (power of two; holds any block's rows)
+    int nChunks;                    // 8-row chunks of the kernel's source FIFO (holds any block's rows)
     std::vector<int32_t> vBlock;    // [blocks][2]: first source row of the block's k range (may be negative), rows read from it
     std::vector<uint32_t> vFrag;    // [blocks][vKMax][32 lanes][4]: A fragments (coefficient bytes: s8 Lanczos, u8 Area / Linear)
     std::vector<int32_t> vRowMap;   // [blocks][vKMax * 32]: source row of every k slot.  Slots 0 .. rows-1 are the block's rows in

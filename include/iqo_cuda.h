@@ -194,6 +194,17 @@ IQO_CUDA_API int iqo_cuda_plan_kernel(int kind, unsigned degree,
                                       size_t srcW, size_t srcH, size_t dstW, size_t dstH, size_t pxScale,
                                       char *kernel, size_t kernelCap, char *why, size_t whyCap);
 IQO_CUDA_API int iqo_cuda_set_path(iqo_cuda_resizer *r, int path);
+
+/* Arithmetic of a handle.  FIXED (default) is the parity contract: the reference's Generic fixed-point path, bit-exact.
+ * SIMD_FLOAT is the optional mode of SURVEY 8f-4 for callers who today get the results of the reference's
+ * AVX-512 / AVX2 / SSE4.1 / NEON implementations, which compute in float and do NOT agree with Generic: float
+ * tables normalised by their float sum, FMA accumulation in tap order, round-to-nearest-even, saturation
+ * (reference src/IQOLanczosResizerImpl_AVX512.cpp:47-60,179-185,385-431,547-590) -- with correctly masked border
+ * denominators, where the reference's resizeXborder divides by the sum of ALL coefficients (:507-519).
+ * Lanczos only (IQO_CUDA_E_UNSUPPORTED otherwise); interior pixels agree with the reference's AVX-512 output to
+ * within 1 LSB (tests/test_gpu_float_mode.py states and checks the tolerance). */
+enum { IQO_CUDA_ARITH_FIXED = 0, IQO_CUDA_ARITH_SIMD_FLOAT = 1 };
+IQO_CUDA_API int iqo_cuda_set_arithmetic(iqo_cuda_resizer *r, int arithmetic);
 /* name of the kernel the last launch used, e.g. "generic" */
 IQO_CUDA_API const char *iqo_cuda_last_kernel(const iqo_cuda_resizer *r);
 /* number of kernels this library has launched in this process (all handles) */

@@ -18,9 +18,10 @@ import ctypes as C
 import os
 
 __all__ = ["LanczosResizer", "AreaResizer", "LinearResizer", "Yuv420Resizer", "IqoCudaError", "lib", "build",
-           "LANCZOS", "AREA", "LINEAR", "PATH_AUTO", "PATH_GENERIC", "PATH_NO_TMA", "PATH_NO_STREAM", "PATH_STREAM", "PATH_MMA", "PATH_NO_MMA", "exported_symbols"]
+           "LANCZOS", "AREA", "LINEAR", "PATH_AUTO", "PATH_GENERIC", "PATH_NO_TMA", "PATH_NO_STREAM", "PATH_STREAM", "PATH_MMA", "PATH_NO_MMA", "ARITH_FIXED", "ARITH_SIMD_FLOAT", "exported_symbols"]
 
 LANCZOS, AREA, LINEAR = 0, 1, 2
+ARITH_FIXED, ARITH_SIMD_FLOAT = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_NO_TMA, PATH_NO_STREAM, PATH_STREAM, PATH_MMA, PATH_NO_MMA = 0, 1, 2, 3, 4, 5, 6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -60,6 +61,7 @@ _SIGNATURES = {
                                       _vp, _sz, _vp, _vp, _sz]),
     "iqo_cuda_plan_kernel": (C.c_int, [C.c_int, C.c_uint, _sz, _sz, _sz, _sz, _sz, C.c_char_p, _sz, C.c_char_p, _sz]),
     "iqo_cuda_set_path": (C.c_int, [_vp, C.c_int]),
+    "iqo_cuda_set_arithmetic": (C.c_int, [_vp, C.c_int]),
     "iqo_cuda_last_kernel": (C.c_char_p, [_vp]),
     "iqo_cuda_launch_count": (C.c_ulonglong, []),
     "iqo_cuda_sync": (C.c_int, [_vp]),
@@ -191,6 +193,10 @@ class _Resizer(object):
 
     def set_path(self, path):
         _check(lib().iqo_cuda_set_path(self._h, path))
+
+    def set_arithmetic(self, arithmetic):
+        """ARITH_FIXED (default, the reference's Generic path, bit-exact) or ARITH_SIMD_FLOAT (optional float mode)."""
+        _check(lib().iqo_cuda_set_arithmetic(self._h, arithmetic))
 
     def last_kernel(self):
         return lib().iqo_cuda_last_kernel(self._h).decode()

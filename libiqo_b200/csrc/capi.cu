@@ -104,6 +104,9 @@ EncodeTiledFn encodeTiled()
     return fn;
 }
 
+#ifndef IQO_MMA_EARLY_DEFAULT
+#define IQO_MMA_EARLY_DEFAULT 0
+#endif
 #ifndef IQO_MMA_WARPS_DEFAULT
 #define IQO_MMA_WARPS_DEFAULT 4
 #endif
@@ -135,6 +138,10 @@ struct SharedPlan {
     RatioPlan ratio;
     LStreamPlan lstream;
     MmaPlan mma;
+    FloatPlan flt;        // optional float (SIMD-semantics) mode, built on first use
+    bool fltBuilt;
+    float *fCoefX, *fCoefY, *fDenoX, *fDenoY;
+    std::mutex fltMu;
     PackedPlan packed;
     GenericGeom geom;
     PackedGeom pgeom;
@@ -154,7 +161,7 @@ struct SharedPlan {
     int32_t *mVBlock, *mVRow, *mVRowMap, *mStripXs, *mHTile, *mHCol;
     uint32_t *mVFrag, *mHFrag;
     SharedPlan()
-        : device(0), dBorderY(0), dMagicY(0), dSBorderY(0), dBorderX(0), dBorderXo(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), rRowRec(0), gRowRec(0), sRowsY(0), sMagicY(0), mVBlock(0), mVRow(0), mVRowMap(0), mStripXs(0), mHTile(0), mHCol(0), mVFrag(0), mHFrag(0)
+        : device(0), dBorderY(0), dMagicY(0), dSBorderY(0), dBorderX(0), dBorderXo(0), pFirstY(0), pNtapY(0), pCoefOffY(0), pRecX(0), pMagicY(0), pCwX(0), rRowRec(0), gRowRec(0), sRowsY(0), sMagicY(0), fltBuilt(false), fCoefX(0), fCoefY(0), fDenoX(0), fDenoY(0), mVBlock(0), mVRow(0), mVRowMap(0), mStripXs(0), mHTile(0), mHCol(0), mVFrag(0), mHFrag(0)
     {
     }
     ~SharedPlan();
@@ -194,6 +201,7 @@ struct iqo_cuda_resizer {
     uint8_t **dSrc, **dDst;
     int device;
     bool useTma, useStream, forceStream, useMma, forceMma;
+    int arithmetic;             // IQO_CUDA_ARITH_*
     int path;
     const char *lastKernel;
     size_t srcPitch, dstPitch;  // device pitches of the staging frames
@@ -202,7 +210,7 @@ struct iqo_cuda_resizer {
     iqo_cuda_resizer(const std::shared_ptr<SharedPlan> &s, Workspace *w)
         : sp(s), ws(w), plan(s->plan), half(s->half), tx(s->tx), ty(s->ty), geom(s->geom), dBorderY(s->dBorderY),
           dMagicY(s->dMagicY), dBorderX(s->dBorderX), stream(w->stream), dSrc(w->dSrc), dDst(w->dDst), device(s->device),
-          useTma(true), useStream(true), forceStream(false), useMma(true), forceMma(false), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
+          useTma(true), useStream(true), forceStream(false), useMma(true), forceMma(false), arithmetic(IQO_CUDA_ARITH_FIXED), path(IQO_CUDA_PATH_AUTO), lastKernel("none"), srcPitch(0), dstPitch(0), slotFrames(0)
     {
     }
 };
@@ -255,6 +263,10 @@ SharedPlan::~SharedPlan()
     cudaFree(mVBlock);
     cudaFree(mVRow);
     cudaFree(mVRowMap);
+    cudaFree(fCoefX);
+    cudaFree(fCoefY);
+    cudaFree(fDenoX);
+    cudaFree(fDenoY);
     cudaFree(mStripXs);
     cudaFree(mHTile);
     cudaFree(mHCol);
@@ -331,6 +343,31 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
     a.lanczos = r->plan.kind == kLanczos;
     a.workSigned = r->plan.workSigned;
     const bool whole = dstRow0 == 0 && dstRows == size_t(r->plan.y.D) && srcRow0 == 0;
+    if (r->arithmetic == IQO_CUDA_ARITH_SIMD_FLOAT) {
+        // opt-in float mode: one kernel, outside the parity contract
+        SharedPlan &fp = *r->sp;
+        FloatArgs q;
+        q.x = a.x;
+        q.y = a.y;
+        q.coefX = fp.fCoefX;
+        q.coefY = fp.fCoefY;
+        q.denoX = fp.fDenoX;
+        q.denoY = fp.fDenoY;
+        q.src = src;
+        q.dst = dst;
+        q.srcPitch = a.srcPitch;
+        q.dstPitch = a.dstPitch;
+        q.srcFrameStride = a.srcFrameStride;
+        q.dstFrameStride = a.dstFrameStride;
+        q.nFrames = a.nFrames;
+        q.srcRow0 = a.srcRow0;
+        q.srcRows = a.srcRows;
+        q.dstRow0 = a.dstRow0;
+        q.dstRows = a.dstRows;
+        r->lastKernel = "float_simd_semantics";
+        CUDA_TRY(launchFloat(q, r->geom, stream));
+        return IQO_CUDA_OK;
+    }
     // Lanczos, both passes on the integer tensor path (any ratio, row bands included)
     auto tryMma = [&]() -> int {
         if (!(r->useMma && r->sp->mma.eligible && ((uintptr_t)src % 16) == 0 && srcSt % 16 == 0 && (nFrames == 1 || srcFrameStride % 16 == 0))) return 0;
@@ -349,6 +386,9 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         q.vKMax = mp.vKMax;
         q.hKMax = mp.hKMax;
         q.nChunks = mp.nChunks;
+        static const int envMmaEarly = [] { const char *e = getenv("IQO_CUDA_MMA_EARLY"); return e ? atoi(e) : IQO_MMA_EARLY_DEFAULT; }();
+        q.early = envMmaEarly ? 1 : 0;
+        if (q.early) q.nChunks += mp.maxNewChunks;
         static const int envMmaPow2 = [] { const char *e = getenv("IQO_CUDA_MMA_POW2"); return e ? atoi(e) : 0; }();
         if (envMmaPow2)   // tuning knob: round the FIFO up to a power of two chunks (more look-ahead room, fewer CTAs per SM)
             while (q.nChunks & (q.nChunks - 1)) ++q.nChunks;
@@ -1218,6 +1258,30 @@ int iqo_cuda_set_path(iqo_cuda_resizer *r, int path)
     r->forceMma = (path == IQO_CUDA_PATH_MMA);
     r->path = (path == IQO_CUDA_PATH_GENERIC) ? IQO_CUDA_PATH_GENERIC : IQO_CUDA_PATH_AUTO;
     return IQO_CUDA_OK;
+}
+
+int iqo_cuda_set_arithmetic(iqo_cuda_resizer *r, int arithmetic)
+{
+    IQO_GUARD_BEGIN
+    if (!r || (arithmetic != IQO_CUDA_ARITH_FIXED && arithmetic != IQO_CUDA_ARITH_SIMD_FLOAT)) return fail(IQO_CUDA_E_ARG, "bad arithmetic mode");
+    if (arithmetic == IQO_CUDA_ARITH_SIMD_FLOAT) {
+        SharedPlan &sp = *r->sp;
+        std::lock_guard<std::mutex> lock(sp.fltMu);
+        if (!sp.fltBuilt) {
+            buildFloatPlan(sp.plan, sp.flt);
+            if (!sp.flt.eligible) return fail(IQO_CUDA_E_UNSUPPORTED, "float mode: %s", sp.flt.why.c_str());
+            DeviceGuard guard(r->device);
+            if (!uploadVec(sp.fCoefX, sp.flt.x.coef) || !uploadVec(sp.fCoefY, sp.flt.y.coef) || !uploadVec(sp.fDenoX, sp.flt.x.deno) ||
+                !uploadVec(sp.fDenoY, sp.flt.y.deno)) {
+                cudaGetLastError();
+                return fail(IQO_CUDA_E_NOMEM, "float mode: table upload failed");
+            }
+            sp.fltBuilt = true;
+        }
+    }
+    r->arithmetic = arithmetic;
+    return IQO_CUDA_OK;
+    IQO_GUARD_END
 }
 
 const char *iqo_cuda_last_kernel(const iqo_cuda_resizer *r)

@@ -133,6 +133,67 @@ __global__ void __launch_bounds__(256) resizeGenericKernel(ResizeArgs a, int til
 
 
 // ---------------------------------------------------------------------------------------
+// Float ("SIMD-semantics") mode (plan.hpp FloatPlan): the tile organisation of the generic kernel with
+// the arithmetic of the reference's AVX-512 path -- float FMA accumulation in tap order over normalised float tables
+// (src/IQOLanczosResizerImpl_AVX512.cpp:385-431 vertical, :547-590 horizontal), division by the in-range coefficient
+// sum on border rows and columns, round-to-nearest-even, saturation (:47-60).  Opt-in, outside the parity contract.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) resizeFloatKernel(FloatArgs a, int tileW, int tileH, int workW)
+{
+    extern __shared__ __align__(16) unsigned char smemRawF[];
+    float *work = reinterpret_cast<float *>(smemRawF);
+    const int tx0 = blockIdx.x * tileW;
+    const int ty0 = blockIdx.y * tileH;
+    const int tw = min(tileW, a.x.D - tx0);
+    const int th = min(tileH, a.dstRows - ty0);
+    const uint8_t *__restrict__ src = a.src + (long long)blockIdx.z * a.srcFrameStride;
+    uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
+    const int SW = a.x.S, SH = a.y.S;
+    const int Nx = a.x.N, Ny = a.y.N;
+    const int x0 = clampi(__ldg(a.x.first + tx0), 0, SW - 1);
+    const int x1 = clampi(__ldg(a.x.first + tx0 + tw - 1) + Nx - 1, 0, SW - 1);
+    const int ww = x1 - x0 + 1;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    for (int r = warp; r < th; r += nwarps) {
+        const int y = a.dstRow0 + ty0 + r;
+        const int fy = __ldg(a.y.first + y);
+        const int ry = __ldg(a.y.row + y);
+        const float *__restrict__ cy = a.coefY + (long long)ry * Ny;
+        const float deno = __ldg(a.denoY + ry);
+        for (int c = lane; c < ww; c += 32) {
+            const uint8_t *col = src + x0 + c;
+            float acc = 0.0f;
+            for (int i = 0; i < Ny; ++i) {
+                const int sy = clampi(fy + i, 0, SH - 1) - a.srcRow0;
+                acc = fmaf((float)__ldg(col + (long long)sy * a.srcPitch), __ldg(cy + i), acc);
+            }
+            if (deno != 0.0f) acc = acc / deno;
+            work[r * workW + c] = acc;
+        }
+    }
+    __syncthreads();
+    for (int r = warp; r < th; r += nwarps) {
+        const float *wrow = work + r * workW;
+        uint8_t *out = dst + (long long)(ty0 + r) * a.dstPitch + tx0;
+        for (int dx = lane; dx < tw; dx += 32) {
+            const int x = tx0 + dx;
+            const int fx = __ldg(a.x.first + x);
+            const int rx = __ldg(a.x.row + x);
+            const float *__restrict__ cx = a.coefX + (long long)rx * Nx;
+            float acc = 0.0f;
+            for (int i = 0; i < Nx; ++i) {
+                const int sx = clampi(fx + i, 0, SW - 1) - x0;
+                acc = fmaf(wrow[sx], __ldg(cx + i), acc);
+            }
+            const float deno = __ldg(a.denoX + rx);
+            if (deno != 0.0f) acc = acc / deno;
+            out[dx] = (uint8_t)clampi(__float2int_rn(acc), 0, 255);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
 // Specialised kernel: Lanczos 2:1 down-sampling on both axes, single-phase tables
 // (BASELINE configs 3 and 4).  One CTA = 256 threads = one tile of 120 x tileRows
 // destination pixels of one frame.
@@ -2377,6 +2438,12 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
 
     for (int b = blkFirst; b < blkEnd; ++b) {
         waitGroup();   // the rows of this block have landed
+        int2 vbNext = vb;
+        if (a.early && b + 1 < blkEnd) {
+            // early mode: the FIFO has room for the next block's new rows beside this block's: request them now
+            vbNext = __ldg(a.vBlock + b + 1);
+            issueUpTo((vbNext.x + vbNext.y - 1) >> 3);
+        }
 
         // ---------------- vertical pass ----------------
         uint32_t ra[VKS];   // k slot 32 s + lane reads the source row the planner's map names (unused slots: any resident row, zero coefficients)
@@ -2443,8 +2510,12 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
         __syncthreads();   // W is complete; every warp has finished reading the source rows of this block
         if (b + 1 < blkEnd) {
             // the next block's rows and coefficient fragments arrive during the horizontal pass
-            vb = __ldg(a.vBlock + b + 1);
-            issueUpTo((vb.x + vb.y - 1) >> 3);
+            if (a.early) {
+                vb = vbNext;
+            } else {
+                vb = __ldg(a.vBlock + b + 1);
+                issueUpTo((vb.x + vb.y - 1) >> 3);
+            }
 #pragma unroll
             for (int s = 0; s < VKS; ++s) {
                 af[s] = __ldg(a.vFrag + ((size_t)(b + 1) * VKS + s) * 32 + lane);
@@ -2652,6 +2723,37 @@ cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_
             resizeGenericKernel<true><<<grid, 256, g.smemBytes, stream>>>(b, g.tileW, g.tileH, g.workW);
         else
             resizeGenericKernel<false><<<grid, 256, g.smemBytes, stream>>>(b, g.tileW, g.tileH, g.workW);
+        g_launches.fetch_add(1);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t launchFloat(const FloatArgs &a, const GenericGeom &g, cudaStream_t stream)
+{
+    static PerDeviceOnce attrSet;
+    const int dev = currentDevice();
+    if (!attrSet.done(dev)) {
+        cudaError_t e = cudaFuncSetAttribute(resizeFloatKernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attrSet.set(dev);
+    }
+    // the float work tile needs twice the bytes of the 16-bit one: halve the tile height when it would not fit
+    int tileH = g.tileH;
+    while (tileH > 1 && size_t(tileH) * g.workW * 4 > 200 * 1024) tileH /= 2;
+    const size_t smem = size_t(tileH) * g.workW * 4;
+    if (smem > 200 * 1024) return cudaErrorInvalidConfiguration;
+    const int tilesX = (a.x.D + g.tileW - 1) / g.tileW;
+    const int tilesY = (a.dstRows + tileH - 1) / tileH;
+    if (tilesY > 65535) return cudaErrorInvalidConfiguration;
+    for (int f0 = 0; f0 < a.nFrames; f0 += 65535) {
+        FloatArgs b = a;
+        b.nFrames = std::min(65535, a.nFrames - f0);
+        b.src = a.src + (long long)f0 * a.srcFrameStride;
+        b.dst = a.dst + (long long)f0 * a.dstFrameStride;
+        dim3 grid(tilesX, tilesY, b.nFrames);
+        resizeFloatKernel<<<grid, 256, smem, stream>>>(b, g.tileW, tileH, g.workW);
         g_launches.fetch_add(1);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;

@@ -204,6 +204,8 @@ struct MmaArgs {
     int stripTiles, wcols;
     int vKMax, hKMax;
     int nChunks;                   // 8-row chunks of the source FIFO
+    int early;                     // request the next block's rows before (1) instead of after (0) the running block's vertical pass;
+                                   // needs nChunks >= a block's chunks + the most chunks a block adds
     int warps;                     // warps per CTA (1, 2 or 4): they share the strip's FIFO / W / tables
     int workBias;
     int mbY, meY, mbX, meX;
@@ -221,6 +223,19 @@ struct MmaArgs {
 };
 size_t mmaSmemBytes(int wcols, int stripTiles, int nChunks, int hKMax);
 cudaError_t launchMma(const MmaArgs &a, const CUtensorMap &tmap, cudaStream_t stream);
+
+// Float ("SIMD-semantics") mode, plan.hpp FloatPlan: the generic tile organisation with float tables and a float work tile.
+struct FloatArgs {
+    AxisDev x, y;                  // first / row maps and sizes of the integer plan (coef / deno unused)
+    const float *coefX, *coefY;    // [numRows][N]
+    const float *denoX, *denoY;    // [numRows], 0: no division
+    const uint8_t *src;
+    uint8_t *dst;
+    long long srcPitch, dstPitch, srcFrameStride, dstFrameStride;
+    int nFrames;
+    int srcRow0, srcRows, dstRow0, dstRows;
+};
+cudaError_t launchFloat(const FloatArgs &a, const GenericGeom &g, cudaStream_t stream);
 
 GenericGeom chooseGenericGeom(const int32_t *firstX, int N, int S, int D);
 cudaError_t launchGeneric(const ResizeArgs &a, const GenericGeom &g, cudaStream_t stream);

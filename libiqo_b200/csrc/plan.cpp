@@ -7,6 +7,8 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
 
 namespace iqo_b200 {
@@ -1085,6 +1087,13 @@ void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
         chunksNeeded = std::max(chunksNeeded, int(floorTo(rhi, kMmaChunkRows) / kMmaChunkRows - floorTo(rlo, kMmaChunkRows) / kMmaChunkRows + 1));
     }
     m.nChunks = std::max(2, chunksNeeded);
+    // most chunks a block adds to its predecessor's: the extra FIFO room the early-request mode of the kernel needs
+    m.maxNewChunks = 1;
+    for (int64_t b = 0; b + 1 < blocks; ++b) {
+        const int64_t hi0 = floorTo(int64_t(m.vBlock[size_t(b) * 2]) + m.vBlock[size_t(b) * 2 + 1] - 1, kMmaChunkRows) / kMmaChunkRows;
+        const int64_t hi1 = floorTo(int64_t(m.vBlock[size_t(b + 1) * 2]) + m.vBlock[size_t(b + 1) * 2 + 1] - 1, kMmaChunkRows) / kMmaChunkRows;
+        m.maxNewChunks = std::max(m.maxNewChunks, int(hi1 - hi0));
+    }
     m.vFrag.assign(size_t(blocks) * m.vKMax * 128, 0);
     m.vRowMap.assign(size_t(blocks) * m.vKMax * 32, 0);
     for (int64_t b = 0; b < blocks; ++b) {
@@ -1152,8 +1161,11 @@ void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
         m.hTile[size_t(T) * 2 + 1] = ks;
     }
     // strips: the largest even tile count whose source window [xs, xs + wcols) holds every tile's k range
+    // (tuning knob IQO_CUDA_MMA_TILE_MULT: strips of a multiple of that many tiles, so that the warps of a CTA get equal shares)
+    static const int tileMult = [] { const char *e = getenv("IQO_CUDA_MMA_TILE_MULT"); const int v = e ? atoi(e) : 2; return (v == 4 || v == 8) ? v : 2; }();
     int st = int(std::min<int64_t>(32, (tiles + 1) & ~1ll));
-    for (; st >= 2; st -= 2) {
+    if (tileMult > 2 && st >= 2 * tileMult) st = st / tileMult * tileMult;
+    for (; st >= 2; st -= (st > tileMult && tileMult > 2 ? tileMult : 2)) {
         bool ok = true;
         for (int64_t T0 = 0; T0 < tiles && ok; T0 += st) {
             const int64_t xs = floorTo(c0[size_t(T0)], 16);
@@ -1201,6 +1213,62 @@ void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
             }
     }
     m.eligible = true;
+}
+
+}  // namespace iqo_b200
+
+// ---------------------------------------------------------------------------------------------
+// Float ("SIMD-semantics") tables, SURVEY 8f-4
+// ---------------------------------------------------------------------------------------------
+namespace iqo_b200 {
+
+namespace {
+
+void floatAxis(const AxisPlan &a, int degree, uint64_t px, FloatAxis &f)
+{
+    const int N = a.N;
+    f.coef.assign(size_t(a.numRows) * N, 0.0f);
+    f.deno.assign(size_t(a.numRows), 0.0f);
+    if (a.identity) {
+        f.coef[0] = 1.0f;   // pass-through axis: the value itself
+        return;
+    }
+    std::vector<float> w(static_cast<size_t>(N));
+    for (int64_t t = 0; t < a.rD; ++t) {
+        const float sum = lanczosPhase(degree, uint64_t(a.rS), uint64_t(a.rD), uint64_t(t), px, w);
+        for (int i = 0; i < N; ++i) f.coef[size_t(t) * N + i] = w[size_t(i)] / sum;   // table[i] /= sumCoefs (float division)
+    }
+    for (int64_t d = 0; d < a.D; ++d) {
+        const int r = a.row[size_t(d)];
+        if (r < a.rD) continue;
+        // border index: taps outside the image dropped, denominator = float sum of the remaining normalised coefficients
+        // accumulated in tap order (src/IQOLanczosResizerImpl_AVX512.cpp:337-355)
+        const int64_t t = d % a.rD, first = a.first[size_t(d)];
+        float den = 0.0f;
+        for (int i = 0; i < N; ++i) {
+            const bool inside = first + i >= 0 && first + i < a.S;
+            const float c = inside ? f.coef[size_t(t) * N + i] : 0.0f;
+            f.coef[size_t(r) * N + i] = c;
+            if (inside) den += c;
+        }
+        f.deno[size_t(r)] = den;
+    }
+}
+
+}  // namespace
+
+void buildFloatPlan(const Plan &p, FloatPlan &f)
+{
+    f.eligible = false;
+    f.why.clear();
+    if (p.kind != kLanczos) { f.why = "the float mode exists for Lanczos only"; return; }
+    floatAxis(p.x, int(p.degree), p.pxScale, f.x);
+    floatAxis(p.y, int(p.degree), p.pxScale, f.y);
+    for (size_t r = size_t(p.x.rD); r < f.x.deno.size(); ++r)
+        if (!p.x.identity && !(f.x.deno[r] != 0.0f)) { f.why = "a border column's in-range coefficients sum to 0"; return; }
+    for (size_t r = size_t(p.y.rD); r < f.y.deno.size(); ++r)
+        if (!p.y.identity && !(f.y.deno[r] != 0.0f)) { f.why = "a border row's in-range coefficients sum to 0"; return; }
+    f.eligible = true;
 }
 
 }  // namespace iqo_b200

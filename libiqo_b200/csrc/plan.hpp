@@ -227,6 +227,7 @@ struct MmaPlan {
     // vertical: 16-row destination blocks (global block index = dst row / 16)
     int vKMax;                      // most k-steps of a block (<= kMmaMaxKSteps)
     int nChunks;                    // 8-row chunks of the kernel's source FIFO (holds any block's rows)
+    int maxNewChunks;               // most chunks a block needs beyond its predecessor's
     std::vector<int32_t> vBlock;    // [blocks][2]: first source row of the block's k range (may be negative), rows read from it
     std::vector<uint32_t> vFrag;    // [blocks][vKMax][32 lanes][4]: A fragments (coefficient bytes: s8 Lanczos, u8 Area / Linear)
     std::vector<int32_t> vRowMap;   // [blocks][vKMax * 32]: source row of every k slot.  Slots 0 .. rows-1 are the block's rows in
@@ -248,5 +249,26 @@ const int kMmaChunkRows = 8;      // source rows per TMA request of the kernel's
 
 // wcols: staged source columns per strip the kernel was launched for (208 unless tuned)
 void buildMmaPlan(const Plan &plan, MmaPlan &m, int wcols);
+
+}  // namespace iqo_b200
+
+namespace iqo_b200 {
+
+// Optional "SIMD-semantics" float mode: what the reference's AVX-512 / AVX2 implementations compute instead
+// of the Generic fixed-point path -- float tables normalised by their float sum (src/IQOLanczosResizerImpl_AVX512.cpp:
+// 179-185), float FMA accumulation in tap order (:385-431, :547-590), round-to-nearest-even and saturation (:47-60) --
+// with one deliberate difference: border rows AND border columns divide by the sum of the coefficients of the taps that
+// are inside the image (the reference's resizeXborder adds the masked-out coefficients to its denominator, :507-519).
+// Rows of `coef` follow AxisPlan's numbering (phase rows, then one row per border index); deno[r] == 0: no division.
+struct FloatAxis {
+    std::vector<float> coef;   // numRows x N
+    std::vector<float> deno;   // numRows
+};
+struct FloatPlan {
+    bool eligible;
+    std::string why;
+    FloatAxis x, y;
+};
+void buildFloatPlan(const Plan &plan, FloatPlan &f);
 
 }  // namespace iqo_b200

@@ -104,6 +104,12 @@ EncodeTiledFn encodeTiled()
     return fn;
 }
 
+#ifndef IQO_TMA_PROMO_DEFAULT
+#define IQO_TMA_PROMO_DEFAULT 1
+#endif
+#ifndef IQO_MMA_DIRECT_DEFAULT
+#define IQO_MMA_DIRECT_DEFAULT 0
+#endif
 #ifndef IQO_MMA_EARLY_DEFAULT
 #define IQO_MMA_EARLY_DEFAULT 0
 #endif
@@ -119,6 +125,14 @@ EncodeTiledFn encodeTiled()
 #ifndef IQO_STREAM_TMA_DEFAULT
 #define IQO_STREAM_TMA_DEFAULT 1
 #endif
+
+// L2 promotion of the streaming kernels' tensor maps (tuning knob IQO_CUDA_TMA_PROMO: 0 none, 1 64 B, 2 128 B, 3 256 B)
+CUtensorMapL2promotion streamPromotion()
+{
+    static const int v = [] { const char *e = getenv("IQO_CUDA_TMA_PROMO"); return e ? atoi(e) : IQO_TMA_PROMO_DEFAULT; }();
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE : v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : v == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                                                                 : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+}
 
 size_t alignUp(size_t v, size_t a)
 {
@@ -386,6 +400,8 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         q.vKMax = mp.vKMax;
         q.hKMax = mp.hKMax;
         q.nChunks = mp.nChunks;
+        static const int envMmaDirect = [] { const char *e = getenv("IQO_CUDA_MMA_DIRECT"); return e ? atoi(e) : IQO_MMA_DIRECT_DEFAULT; }();
+        q.direct = (envMmaDirect && ((uintptr_t)dst % 2) == 0 && dstSt % 2 == 0 && dstFrameStride % 2 == 0) ? 1 : 0;
         static const int envMmaEarly = [] { const char *e = getenv("IQO_CUDA_MMA_EARLY"); return e ? atoi(e) : IQO_MMA_EARLY_DEFAULT; }();
         q.early = envMmaEarly ? 1 : 0;
         if (q.early) q.nChunks += mp.maxNewChunks;
@@ -435,7 +451,7 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
                 const cuuint32_t estr[3] = {1, 1, 1};
                 CUresult cr = encodeTiled()(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint8_t *>(fsrc), dims, strides,
                                             box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                            streamPromotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                 if (cr != CUDA_SUCCESS) {
                     ok = false;   // e.g. a stride the descriptor cannot express: other kernels take the launch
                     if (f0 != 0) return fail(IQO_CUDA_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(cr));
@@ -590,7 +606,7 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
                     const cuuint32_t estr[3] = {1, 1, 1};
                     CUresult cr = encodeTiled()(&smap, CU_TENSOR_MAP_DATA_TYPE_UINT16, 3, const_cast<uint8_t *>(h.src), dims, strides,
                                                 box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                                                streamPromotion(), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
                     if (cr != CUDA_SUCCESS) tma = false;
                 }
                 CUDA_TRY(launchHalfStream(h, tma ? &smap : 0, stream));

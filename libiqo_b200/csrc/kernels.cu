@@ -2578,8 +2578,24 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
                     }
                 }
                 const uint32_t p01 = packSatU8(v[1], v[0], 0u), p23 = packSatU8(v[3], v[2], 0u);
-                *reinterpret_cast<uint16_t *>(oTile + g * oStride + 8 * ti + 2 * t) = (uint16_t)p01;
-                *reinterpret_cast<uint16_t *>(oTile + (g + 8) * oStride + 8 * ti + 2 * t) = (uint16_t)p23;
+                if (a.direct) {
+                    // straight to global: a quad writes the 8 bytes of a row, a warp 8 rows (the neighbouring tiles of the
+                    // row are written by the other warps at about the same time: the L2 merges the 32-byte sectors)
+                    const int yA = 16 * b + g, yB = yA + 8, x = 8 * ti + 2 * t;
+                    const int yLoD = max(a.dstRow0, 16 * b), yHiD = min(a.dstRow0 + a.dstRows, 16 * b + 16);
+                    uint8_t *pA = dst + (long long)(yA - a.dstRow0) * a.dstPitch + tx0 + x;
+                    uint8_t *pB = pA + 8 * a.dstPitch;
+                    if (x + 2 <= tw) {
+                        if (yA >= yLoD && yA < yHiD) *reinterpret_cast<uint16_t *>(pA) = (uint16_t)p01;
+                        if (yB >= yLoD && yB < yHiD) *reinterpret_cast<uint16_t *>(pB) = (uint16_t)p23;
+                    } else if (x < tw) {
+                        if (yA >= yLoD && yA < yHiD) *pA = (uint8_t)p01;
+                        if (yB >= yLoD && yB < yHiD) *pB = (uint8_t)p23;
+                    }
+                } else {
+                    *reinterpret_cast<uint16_t *>(oTile + g * oStride + 8 * ti + 2 * t) = (uint16_t)p01;
+                    *reinterpret_cast<uint16_t *>(oTile + (g + 8) * oStride + 8 * ti + 2 * t) = (uint16_t)p23;
+                }
             };
             // steps are numbered i = ti * HKS + s; a pair of tiles is 2 HKS steps, so the two operand buffers alternate
             // at compile-time positions inside the unrolled pair
@@ -2602,7 +2618,7 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
         __syncthreads();
 
         // ---------------- store the 16 x tw tile ----------------
-        {
+        if (!a.direct) {
             const int yb = 16 * b;
             const int yLo = max(a.dstRow0, yb), yHi = min(a.dstRow0 + a.dstRows, yb + 16);   // rows of the block inside the launch
             uint8_t *drow = dst + (long long)(yb + stRow - a.dstRow0) * a.dstPitch + tx0;

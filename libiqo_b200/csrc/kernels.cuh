@@ -204,6 +204,8 @@ struct MmaArgs {
     int stripTiles, wcols;
     int vKMax, hKMax;
     int nChunks;                   // 8-row chunks of the source FIFO
+    int direct;                    // the horizontal epilogue writes its 2-byte pieces straight to global memory (needs even dst rows start:
+                                   // dst base and pitch multiples of 2) instead of staging the 16-row tile in shared memory
     int early;                     // request the next block's rows before (1) instead of after (0) the running block's vertical pass;
                                    // needs nChunks >= a block's chunks + the most chunks a block adds
     int warps;                     // warps per CTA (1, 2 or 4): they share the strip's FIFO / W / tables

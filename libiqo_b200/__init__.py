@@ -25,7 +25,8 @@ ARITH_FIXED, ARITH_SIMD_FLOAT = 0, 1
 PATH_AUTO, PATH_GENERIC, PATH_NO_TMA, PATH_NO_STREAM, PATH_STREAM, PATH_MMA, PATH_NO_MMA = 0, 1, 2, 3, 4, 5, 6
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libiqo_cuda.so")
+# IQO_CUDA_LIB: load another build of the library (A/B runs of two kernel variants in one gpurun call)
+LIB_PATH = os.environ.get("IQO_CUDA_LIB") or os.path.join(_HERE, "lib", "libiqo_cuda.so")
 
 _sz = C.c_size_t
 _vp = C.c_void_p

@@ -107,12 +107,6 @@ EncodeTiledFn encodeTiled()
 #ifndef IQO_TMA_PROMO_DEFAULT
 #define IQO_TMA_PROMO_DEFAULT 1
 #endif
-#ifndef IQO_MMA_DIRECT_DEFAULT
-#define IQO_MMA_DIRECT_DEFAULT 0
-#endif
-#ifndef IQO_MMA_EARLY_DEFAULT
-#define IQO_MMA_EARLY_DEFAULT 0
-#endif
 #ifndef IQO_MMA_WARPS_DEFAULT
 #define IQO_MMA_WARPS_DEFAULT 4
 #endif
@@ -400,14 +394,6 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
         q.vKMax = mp.vKMax;
         q.hKMax = mp.hKMax;
         q.nChunks = mp.nChunks;
-        static const int envMmaDirect = [] { const char *e = getenv("IQO_CUDA_MMA_DIRECT"); return e ? atoi(e) : IQO_MMA_DIRECT_DEFAULT; }();
-        q.direct = (envMmaDirect && ((uintptr_t)dst % 2) == 0 && dstSt % 2 == 0 && dstFrameStride % 2 == 0) ? 1 : 0;
-        static const int envMmaEarly = [] { const char *e = getenv("IQO_CUDA_MMA_EARLY"); return e ? atoi(e) : IQO_MMA_EARLY_DEFAULT; }();
-        q.early = envMmaEarly ? 1 : 0;
-        if (q.early) q.nChunks += mp.maxNewChunks;
-        static const int envMmaPow2 = [] { const char *e = getenv("IQO_CUDA_MMA_POW2"); return e ? atoi(e) : 0; }();
-        if (envMmaPow2)   // tuning knob: round the FIFO up to a power of two chunks (more look-ahead room, fewer CTAs per SM)
-            while (q.nChunks & (q.nChunks - 1)) ++q.nChunks;
         static const int envMmaWarps = [] { const char *e = getenv("IQO_CUDA_MMA_WARPS"); return e ? atoi(e) : IQO_MMA_WARPS_DEFAULT; }();
         q.warps = (envMmaWarps == 1 || envMmaWarps == 2 || envMmaWarps == 4) ? envMmaWarps : IQO_MMA_WARPS_DEFAULT;
         q.workBias = mp.workBias;

@@ -2342,12 +2342,11 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     const int xs = __ldg(a.stripXs + strip);                    // source column of W element 0
     const int rowBytes = a.wcols;                               // FIFO row
     const int chunkBytes = kMmaChunk * rowBytes;
-    const uint32_t chunkRcp = (uint32_t)(0x100000000ull / (uint32_t)a.nChunks) + 1u;   // j mod nChunks by multiply-high (j < 2^27)
-    auto chunkSlot = [&](const int j) -> int { return j - (int)__umulhi((uint32_t)j, chunkRcp) * a.nChunks; };
     const int wStride = mmaWStride(a.wcols), oStride = mmaOutStride(a.stripTiles);
     const uint32_t fifoBase = smemAddr(mmaSmem);
     const uint32_t wBase = fifoBase + a.nChunks * chunkBytes;
     uint8_t *oTile = mmaSmem + a.nChunks * chunkBytes + 16 * wStride;
+    const uint32_t oTileS = wBase + 16 * wStride;
     uint8_t *tabs = oTile + 16 * oStride;
     uint4 *sFrag = reinterpret_cast<uint4 *>(tabs);                                        // [tile][HKS][lane]
     int *sOff = reinterpret_cast<int *>(tabs + a.stripTiles * HKS * 512);                  // [tile] byte offset of the tile's k range in a W row
@@ -2368,34 +2367,40 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     }
     __syncthreads();
 
-    // chunk c (global source rows 8 c ... 8 c + 7) lives in FIFO slot (c - cStart) mod nChunks.  The chunks requested for
-    // one block form a group that completes one phase of an mbarrier: group i uses barrier i & 1, phase (i >> 1) & 1.
+    // chunk c (global source rows 8 c ... 8 c + 7) lives in FIFO slot c mod nChunks (the planner's row map holds the byte
+    // offsets that follow from it).  The chunks requested for one block form a group that completes one phase of an
+    // mbarrier: group i uses barrier i & 1, phase (i >> 1) & 1.  Warp 0 requests, so only it keeps the request state.
     int2 vb = __ldg(a.vBlock + blkFirst);   // {first source row, rows}
-    const int cStart = vb.x >> 3;           // arithmetic shift: floor
-    int cIssued = cStart;                   // next chunk to request
-    int grpIssued = 0, grpWaited = 0;       // groups requested / waited for
+    int cIssued = vb.x >> 3;                // next chunk to request (arithmetic shift: floor)
+    uint32_t slotAddr = 0, barIssue = mbarBase;   // where chunk cIssued goes, the barrier of the next group
+    if (warp == 0) {
+        int sl = cIssued % a.nChunks;
+        if (sl < 0) sl += a.nChunks;
+        slotAddr = fifoBase + sl * chunkBytes;
+    }
+    const uint32_t fifoEnd = wBase;
+    int grpWaited = 0;                      // groups waited for
     auto issueUpTo = [&](const int cHi) {
         if (warp == 0) {
-            const uint32_t bar = mbarBase + 8 * (grpIssued & 1);
-            const int nNew = max(cHi + 1 - cIssued, 0);
+            const int nNew = cHi + 1 - cIssued;
             if (lane == 0) {
                 if (nNew > 0)
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(nNew * chunkBytes) : "memory");
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barIssue), "r"(nNew * chunkBytes) : "memory");
                 else
-                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");   // nothing new: the phase completes at once
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(barIssue) : "memory");   // nothing new: the phase completes at once
             }
-            for (int c = cIssued; c <= cHi; ++c) {
-                const int slot = chunkSlot(c - cStart);
+            for (; cIssued <= cHi; ++cIssued) {
                 if (lane == 0)
                     asm volatile(
                         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-                        ::"r"(fifoBase + slot * chunkBytes), "l"(reinterpret_cast<unsigned long long>(&prm)), "r"(xs >> 1),
-                          "r"(kMmaChunk * c - a.srcRow0), "r"((int)blockIdx.z), "r"(bar)
+                        ::"r"(slotAddr), "l"(reinterpret_cast<unsigned long long>(&prm)), "r"(xs >> 1),
+                          "r"(kMmaChunk * cIssued - a.srcRow0), "r"((int)blockIdx.z), "r"(barIssue)
                         : "memory");
+                slotAddr += chunkBytes;
+                if (slotAddr == fifoEnd) slotAddr = fifoBase;
             }
+            barIssue ^= 8u;
         }
-        cIssued = max(cIssued, cHi + 1);
-        ++grpIssued;
     };
     auto waitGroup = [&]() {
         asm volatile(
@@ -2404,15 +2409,23 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
             : "memory");
         ++grpWaited;
     };
-    auto rowAddr = [&](const int r) -> uint32_t {   // shared address of global source row r (its chunk must be resident)
-        return fifoBase + chunkSlot((r >> 3) - cStart) * chunkBytes + (r & 7) * rowBytes;
-    };
     issueUpTo((vb.x + vb.y - 1) >> 3);   // the first block's rows: in flight while the tables are staged
 
     // the strip's horizontal tables -> shared memory (every block of the band uses them)
-    for (int i = threadIdx.x; i < nt * HKS * 32; i += blockDim.x) sFrag[i] = __ldg(a.hFrag + (size_t)T0 * HKS * 32 + i);
+    // (asynchronous 16-byte copies: all of a thread's pieces are in flight at once)
+    for (int i = threadIdx.x; i < nt * HKS * 32; i += blockDim.x)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemAddr(sFrag + i)), "l"(a.hFrag + (size_t)T0 * HKS * 32 + i) : "memory");
     for (int i = threadIdx.x; i < nt; i += blockDim.x) sOff[i] = 2 * (__ldg(a.hTile + T0 + i).x - xs);
     for (int i = threadIdx.x; i < 8 * nt; i += blockDim.x) sCol[i] = __ldg(a.hCol + 8 * T0 + i);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
+    // tiles that hold border columns (divisions in the epilogue): a warp-uniform flag per tile
+    for (int i = threadIdx.x; i < nt; i += blockDim.x) {
+        int any = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) any |= sCol[8 * i + j].y;
+        sOff[a.stripTiles + i] = any;
+    }
     __syncthreads();
 
     // lane roles of the matrix loads / stores
@@ -2427,6 +2440,9 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     int lprShift = 0;
     while ((1 << lprShift) < nch && (1 << lprShift) < (int)blockDim.x) ++lprShift;
     const int stRow = threadIdx.x >> lprShift, stCh = threadIdx.x & ((1 << lprShift) - 1), stRows = (int)blockDim.x >> lprShift;
+    // with 16- or 8-byte pieces a thread owns one piece position of the rows stRow, stRow + stRows, ...
+    const int stX = stCh << pieceShift;
+    const int stKind = pieceShift == 0 ? 0 : stX >= tw ? -1 : (pieceShift == 4 && stX + 16 <= tw) ? 16 : (pieceShift == 3 && stX + 8 <= tw) ? 8 : 1;
 
     uint4 af[VKS];   // A fragments (coefficients) of the running block
     int rmap[VKS];   // source rows of this lane's k slots
@@ -2437,18 +2453,15 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     }
 
     for (int b = blkFirst; b < blkEnd; ++b) {
+        // the next block's row range is needed right after this block's vertical pass (by the warp that requests its rows):
+        // fetched here, a whole pass ahead, so that nobody waits on the L2 at that point
+        if (b + 1 < blkEnd) vb = __ldg(a.vBlock + b + 1);
         waitGroup();   // the rows of this block have landed
-        int2 vbNext = vb;
-        if (a.early && b + 1 < blkEnd) {
-            // early mode: the FIFO has room for the next block's new rows beside this block's: request them now
-            vbNext = __ldg(a.vBlock + b + 1);
-            issueUpTo((vbNext.x + vbNext.y - 1) >> 3);
-        }
 
         // ---------------- vertical pass ----------------
-        uint32_t ra[VKS];   // k slot 32 s + lane reads the source row the planner's map names (unused slots: any resident row, zero coefficients)
+        uint32_t ra[VKS];   // k slot 32 s + lane reads the FIFO row the planner's map names (unused slots: any resident row, zero coefficients)
 #pragma unroll
-        for (int s = 0; s < VKS; ++s) ra[s] = rowAddr(rmap[s]);
+        for (int s = 0; s < VKS; ++s) ra[s] = fifoBase + (uint32_t)rmap[s];
         const bool borderBlock = SIGNED && ((16 * b < a.mbY) || (16 * b + 16 > a.meY));
         int denoLo = 0, denoHi = 0;
         uint32_t magicLo = 0, magicHi = 0;
@@ -2476,7 +2489,7 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
                 mmaCoefU8k16<SIGNED>(dA, af[s].z, af[s].w, bf[s][2], false);    // k slots 32 s + 16 ... + 31
                 mmaCoefU8k16<SIGNED>(dB, af[s].z, af[s].w, bf[s][3], false);
             }
-            if (borderBlock && (denoLo | denoHi)) {
+            if (borderBlock) {
                 // resizeYborder: int16 numerator * 64 / denominator, C (truncating) division (see halfVerticalStrip)
                 auto bdiv = [&](int x, int deno, uint32_t magic) -> int {
                     if (!deno) return x;
@@ -2510,12 +2523,7 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
         __syncthreads();   // W is complete; every warp has finished reading the source rows of this block
         if (b + 1 < blkEnd) {
             // the next block's rows and coefficient fragments arrive during the horizontal pass
-            if (a.early) {
-                vb = vbNext;
-            } else {
-                vb = __ldg(a.vBlock + b + 1);
-                issueUpTo((vb.x + vb.y - 1) >> 3);
-            }
+            issueUpTo((vb.x + vb.y - 1) >> 3);
 #pragma unroll
             for (int s = 0; s < VKS; ++s) {
                 af[s] = __ldg(a.vFrag + ((size_t)(b + 1) * VKS + s) * 32 + lane);
@@ -2567,7 +2575,7 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
                 if (!SIGNED) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) v[e] = (int)(short)(v[e] >> 23);   // Area / Linear: 8 + 15 fixed-point bits
-                } else if ((hc.y | hc.w) == 0) {
+                } else if (sOff[a.stripTiles + ti] == 0) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) v[e] = (int)(short)(v[e] >> 20);
                 } else {
@@ -2578,24 +2586,8 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
                     }
                 }
                 const uint32_t p01 = packSatU8(v[1], v[0], 0u), p23 = packSatU8(v[3], v[2], 0u);
-                if (a.direct) {
-                    // straight to global: a quad writes the 8 bytes of a row, a warp 8 rows (the neighbouring tiles of the
-                    // row are written by the other warps at about the same time: the L2 merges the 32-byte sectors)
-                    const int yA = 16 * b + g, yB = yA + 8, x = 8 * ti + 2 * t;
-                    const int yLoD = max(a.dstRow0, 16 * b), yHiD = min(a.dstRow0 + a.dstRows, 16 * b + 16);
-                    uint8_t *pA = dst + (long long)(yA - a.dstRow0) * a.dstPitch + tx0 + x;
-                    uint8_t *pB = pA + 8 * a.dstPitch;
-                    if (x + 2 <= tw) {
-                        if (yA >= yLoD && yA < yHiD) *reinterpret_cast<uint16_t *>(pA) = (uint16_t)p01;
-                        if (yB >= yLoD && yB < yHiD) *reinterpret_cast<uint16_t *>(pB) = (uint16_t)p23;
-                    } else if (x < tw) {
-                        if (yA >= yLoD && yA < yHiD) *pA = (uint8_t)p01;
-                        if (yB >= yLoD && yB < yHiD) *pB = (uint8_t)p23;
-                    }
-                } else {
-                    *reinterpret_cast<uint16_t *>(oTile + g * oStride + 8 * ti + 2 * t) = (uint16_t)p01;
-                    *reinterpret_cast<uint16_t *>(oTile + (g + 8) * oStride + 8 * ti + 2 * t) = (uint16_t)p23;
-                }
+                *reinterpret_cast<uint16_t *>(oTile + g * oStride + 8 * ti + 2 * t) = (uint16_t)p01;
+                *reinterpret_cast<uint16_t *>(oTile + (g + 8) * oStride + 8 * ti + 2 * t) = (uint16_t)p23;
             };
             // steps are numbered i = ti * HKS + s; a pair of tiles is 2 HKS steps, so the two operand buffers alternate
             // at compile-time positions inside the unrolled pair
@@ -2618,24 +2610,35 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
         __syncthreads();
 
         // ---------------- store the 16 x tw tile ----------------
-        if (!a.direct) {
+        {
             const int yb = 16 * b;
-            const int yLo = max(a.dstRow0, yb), yHi = min(a.dstRow0 + a.dstRows, yb + 16);   // rows of the block inside the launch
+            const int rLo = max(a.dstRow0 - yb, 0), rHi = min(a.dstRow0 + a.dstRows - yb, 16);   // rows of the block inside the launch
             uint8_t *drow = dst + (long long)(yb + stRow - a.dstRow0) * a.dstPitch + tx0;
-            const long long dstep = (long long)stRows * a.dstPitch;
-            for (int r = stRow; r < 16; r += stRows, drow += dstep) {
-                const int y = yb + r;
-                if (y < yLo || y >= yHi) continue;
-                const uint8_t *srow = oTile + r * oStride;
-                for (int ch = stCh; ch < nch; ch += 1 << lprShift) {   // one trip unless a row has more pieces than the CTA has threads
-                    const int x = ch << pieceShift;
-                    if (pieceShift == 4 && x + 16 <= tw) {
-                        *reinterpret_cast<uint4 *>(drow + x) = *reinterpret_cast<const uint4 *>(srow + x);
-                    } else if (pieceShift == 3 && x + 8 <= tw) {
-                        *reinterpret_cast<uint2 *>(drow + x) = *reinterpret_cast<const uint2 *>(srow + x);
+            const long long stStep = (long long)stRows * a.dstPitch;
+            if (stKind > 0) {
+                uint8_t *d = drow + stX;
+                uint32_t sp = oTileS + stRow * oStride + stX;
+                for (int r = stRow; r < 16; r += stRows, d += stStep, sp += stRows * oStride) {
+                    if (r < rLo || r >= rHi) continue;
+                    if (stKind == 16) {
+                        uint4 v;
+                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sp));
+                        *reinterpret_cast<uint4 *>(d) = v;
+                    } else if (stKind == 8) {
+                        uint2 v;
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sp));
+                        *reinterpret_cast<uint2 *>(d) = v;
                     } else {
-                        for (int i = x; i < min(x + (1 << pieceShift), tw); ++i) drow[i] = srow[i];
+                        // the ragged piece at the end of the last strip
+                        for (int i = 0; i < min(1 << pieceShift, tw - stX); ++i) d[i] = oTile[(r * oStride + stX) + i];
                     }
+                }
+            } else if (stKind == 0) {
+                // single bytes (unaligned destination): a row may have more bytes than the CTA has threads
+                for (int r = stRow; r < 16; r += stRows, drow += stStep) {
+                    if (r < rLo || r >= rHi) continue;
+                    const uint8_t *srow = oTile + r * oStride;
+                    for (int x = stCh; x < tw; x += 1 << lprShift) drow[x] = srow[x];
                 }
             }
         }

@@ -203,11 +203,7 @@ struct MmaArgs {
     int bandBlocks;                // 16-row blocks per warp
     int stripTiles, wcols;
     int vKMax, hKMax;
-    int nChunks;                   // 8-row chunks of the source FIFO
-    int direct;                    // the horizontal epilogue writes its 2-byte pieces straight to global memory (needs even dst rows start:
-                                   // dst base and pitch multiples of 2) instead of staging the 16-row tile in shared memory
-    int early;                     // request the next block's rows before (1) instead of after (0) the running block's vertical pass;
-                                   // needs nChunks >= a block's chunks + the most chunks a block adds
+    int nChunks;                   // 8-row chunks of the source FIFO (the plan's: the row map is built for it)
     int warps;                     // warps per CTA (1, 2 or 4): they share the strip's FIFO / W / tables
     int workBias;
     int mbY, meY, mbX, meX;
@@ -215,7 +211,7 @@ struct MmaArgs {
     const int2 *vBlock;
     const uint4 *vFrag;
     const int2 *vRow;
-    const int32_t *vRowMap;        // [blocks][vKMax * 32]: source row of every k slot
+    const int32_t *vRowMap;        // [blocks][vKMax * 32]: FIFO byte offset of the source row of every k slot
     int isSigned;                  // Lanczos (signed coefficients, 20-bit shift, border divisions) or Area / Linear
     const int32_t *stripXs;
     const int2 *hTile;

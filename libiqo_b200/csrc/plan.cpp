@@ -1087,13 +1087,6 @@ void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
         chunksNeeded = std::max(chunksNeeded, int(floorTo(rhi, kMmaChunkRows) / kMmaChunkRows - floorTo(rlo, kMmaChunkRows) / kMmaChunkRows + 1));
     }
     m.nChunks = std::max(2, chunksNeeded);
-    // most chunks a block adds to its predecessor's: the extra FIFO room the early-request mode of the kernel needs
-    m.maxNewChunks = 1;
-    for (int64_t b = 0; b + 1 < blocks; ++b) {
-        const int64_t hi0 = floorTo(int64_t(m.vBlock[size_t(b) * 2]) + m.vBlock[size_t(b) * 2 + 1] - 1, kMmaChunkRows) / kMmaChunkRows;
-        const int64_t hi1 = floorTo(int64_t(m.vBlock[size_t(b + 1) * 2]) + m.vBlock[size_t(b + 1) * 2 + 1] - 1, kMmaChunkRows) / kMmaChunkRows;
-        m.maxNewChunks = std::max(m.maxNewChunks, int(hi1 - hi0));
-    }
     m.vFrag.assign(size_t(blocks) * m.vKMax * 128, 0);
     m.vRowMap.assign(size_t(blocks) * m.vKMax * 32, 0);
     for (int64_t b = 0; b < blocks; ++b) {
@@ -1101,13 +1094,20 @@ void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
         const int nslots = nrows + int(dup[size_t(b)].size());
         const int ks = (nslots + 31) / 32;
         int32_t *rmap = &m.vRowMap[size_t(b) * m.vKMax * 32];
-        for (int k = 0; k < m.vKMax * 32; ++k)
-            rmap[k] = int32_t(k < nrows ? lo[size_t(b)] + k : k < nslots ? dup[size_t(b)][size_t(k - nrows)] : lo[size_t(b)]);
+        std::vector<int64_t> slotRow(size_t(m.vKMax) * 32);
+        for (int k = 0; k < m.vKMax * 32; ++k) {
+            const int64_t row = k < nrows ? lo[size_t(b)] + k : k < nslots ? dup[size_t(b)][size_t(k - nrows)] : lo[size_t(b)];
+            slotRow[size_t(k)] = row;
+            // chunk c = floor(row / 8) lives in FIFO slot c mod nChunks; a FIFO row is wcols bytes
+            const int64_t c = floorTo(row, kMmaChunkRows) / kMmaChunkRows;
+            const int64_t slot = ((c % m.nChunks) + m.nChunks) % m.nChunks;
+            rmap[k] = int32_t((slot * kMmaChunkRows + (row - c * kMmaChunkRows)) * wcols);
+        }
         // A[row][k]: coefficient of destination row 16 b + row for the source row of slot k
         auto coefAt = [&](int row, int64_t k) -> uint32_t {
             const int64_t y = 16 * b + row;
             if (y >= Y.D || k >= nslots) return 0u;
-            const int64_t i = int64_t(rmap[k]) - Y.first[size_t(y)];
+            const int64_t i = slotRow[size_t(k)] - Y.first[size_t(y)];
             if (i < 0 || i >= NY) return 0u;
             const int c = Y.coef[size_t(Y.row[size_t(y)]) * NY + size_t(i)];
             if (c == 256) return k < nrows ? 255u : 1u;   // split over the row's own slot and its extra slot

@@ -227,11 +227,11 @@ struct MmaPlan {
     // vertical: 16-row destination blocks (global block index = dst row / 16)
     int vKMax;                      // most k-steps of a block (<= kMmaMaxKSteps)
     int nChunks;                    // 8-row chunks of the kernel's source FIFO (holds any block's rows)
-    int maxNewChunks;               // most chunks a block needs beyond its predecessor's
     std::vector<int32_t> vBlock;    // [blocks][2]: first source row of the block's k range (may be negative), rows read from it
     std::vector<uint32_t> vFrag;    // [blocks][vKMax][32 lanes][4]: A fragments (coefficient bytes: s8 Lanczos, u8 Area / Linear)
-    std::vector<int32_t> vRowMap;   // [blocks][vKMax * 32]: source row of every k slot.  Slots 0 .. rows-1 are the block's rows in
-                                    // order; an Area / Linear weight of 256 does not fit a byte and is split 255 + 1 over the row's
+    std::vector<int32_t> vRowMap;   // [blocks][vKMax * 32]: where the source row of every k slot sits in the kernel's FIFO (byte offset:
+                                    // chunk floor(row / 8) occupies slot chunk mod nChunks, rows are wcols bytes).  Slots 0 .. rows-1
+                                    // are the block's rows in order; an Area / Linear weight of 256 does not fit a byte and is split 255 + 1 over the row's
                                     // own slot and an extra slot that points at the same row; unused slots repeat the first row
     bool isSigned;                  // Lanczos: signed coefficients, 20-bit shift, border divisions; else unsigned, 23-bit shift
     std::vector<int32_t> vRow;      // [blocks * 16][2]: Lanczos border denominator (0: ordinary row), multiply-high constant

@@ -81,6 +81,20 @@ __global__ void __launch_bounds__(1024) mmaRate(int *out, long long *cyc, int it
     if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
 
+// latency: one warp per SM, one dependent chain of k = 16 products
+__global__ void __launch_bounds__(32) mmaLatencyK16(int *out, long long *cyc, int iters, uint32_t seed)
+{
+    uint32_t a0 = seed, a1 = seed * 3, b = seed ^ 0x01020304u;
+    int d[4] = {0, 0, 0, 0};
+    long long t0 = clock64();
+    for (int it = 0; it < iters; ++it)
+        asm volatile("mma.sync.aligned.m16n8k16.row.col.s32.s8.u8.s32 {%0,%1,%2,%3}, {%4,%5}, {%6}, {%0,%1,%2,%3};"
+                     : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3]) : "r"(a0), "r"(a1), "r"(b));
+    long long t1 = clock64();
+    out[blockIdx.x * 32 + threadIdx.x] = d[0] + d[1] + d[2] + d[3];
+    if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
+}
+
 // the same with a dp4a stream of the same warp mixed in (does the tensor pipe run beside the integer pipe?)
 __global__ void __launch_bounds__(1024) mmaPlusDp4a(int *out, long long *cyc, int iters, uint32_t seed, int ndp)
 {
@@ -188,6 +202,14 @@ int main()
     }
     mmaRate<1><<<sms, 1024>>>(o, cy, iters, 12345u);
     report("mma x1 dependent chain", 1, 0, 32);
+    mmaRate<1><<<sms, 32>>>(o, cy, iters, 12345u);
+    report("k32 latency: 1 warp/SM, dependent chain (cycles per mma = iters / rate)", 1, 0, 1);
+    mmaRate<2><<<sms, 32>>>(o, cy, iters, 12345u);
+    report("k32: 1 warp/SM, 2 chains", 2, 0, 1);
+    mmaRate<4><<<sms, 32>>>(o, cy, iters, 12345u);
+    report("k32: 1 warp/SM, 4 chains", 4, 0, 1);
+    mmaLatencyK16<<<sms, 32>>>(o, cy, iters, 12345u);
+    report("k16 latency: 1 warp/SM, dependent chain", 1, 0, 1);
     mmaPlusDp4a<<<sms, 1024>>>(o, cy, iters, 12345u, 0);
     report("mma x2 alone", 2, 0, 32);
     mmaPlusDp4a<<<sms, 1024>>>(o, cy, iters, 12345u, 1);

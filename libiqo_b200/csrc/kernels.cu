@@ -2316,7 +2316,7 @@ struct MmaKernelArgs {
 __host__ __device__ constexpr int mmaWStride(int wcols) { return 2 * wcols + 16; }          // bytes; (stride / 16) is odd
 __host__ __device__ constexpr int mmaOutStride(int stripTiles) { return (8 * stripTiles + 15) / 16 * 16 + 16 + ((((8 * stripTiles + 15) / 16) & 1) ? 16 : 0); }   // multiple of 16, odd number of 16-byte units: the 8 rows of an epilogue store fall on different banks
 // shared bytes of a warp: [FIFO chunks | W tile | output tile | strip tables: B fragments, W offsets, {init, divisor} | mbarriers]
-__host__ __device__ constexpr int mmaTableBytes(int stripTiles, int hks) { return stripTiles * (hks * 512 + 8 + 64); }
+__host__ __device__ constexpr int mmaTableBytes(int stripTiles, int hks) { return stripTiles * (hks * 512 + 8 + 64 + 32) + 8; }
 constexpr int kMmaChunk = 8;   // plan.hpp kMmaChunkRows
 
 #ifndef IQO_MMA_MINB
@@ -2349,9 +2349,10 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     const uint32_t oTileS = wBase + 16 * wStride;
     uint8_t *tabs = oTile + 16 * oStride;
     uint4 *sFrag = reinterpret_cast<uint4 *>(tabs);                                        // [tile][HKS][lane]
-    int *sOff = reinterpret_cast<int *>(tabs + a.stripTiles * HKS * 512);                  // [tile] byte offset of the tile's k range in a W row
-    int2 *sCol = reinterpret_cast<int2 *>(sOff + 2 * a.stripTiles);                        // [tile * 8] {init, divisor}
-    const uint32_t mbarBase = smemAddr(sCol + 8 * a.stripTiles);
+    int2 *sOff = reinterpret_cast<int2 *>(tabs + a.stripTiles * HKS * 512);                // [tile] {byte offset of the tile's k range in a W row, tile has border columns}
+    int *sInit = reinterpret_cast<int *>(sOff + ((a.stripTiles + 1) & ~1));                           // [tile][4 t][4]: rounding constants of columns 2t, 2t+1 as an accumulator quad {c0, c1, c0, c1}
+    int *sDiv = sInit + 16 * a.stripTiles;                                                 // [tile * 8] border divisor (0: ordinary column)
+    const uint32_t mbarBase = smemAddr(sDiv + 8 * a.stripTiles);
     uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
     const int nseg = a.wcols >> 4;
 
@@ -2415,16 +2416,19 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     // (asynchronous 16-byte copies: all of a thread's pieces are in flight at once)
     for (int i = threadIdx.x; i < nt * HKS * 32; i += blockDim.x)
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smemAddr(sFrag + i)), "l"(a.hFrag + (size_t)T0 * HKS * 32 + i) : "memory");
-    for (int i = threadIdx.x; i < nt; i += blockDim.x) sOff[i] = 2 * (__ldg(a.hTile + T0 + i).x - xs);
-    for (int i = threadIdx.x; i < 8 * nt; i += blockDim.x) sCol[i] = __ldg(a.hCol + 8 * T0 + i);
+    for (int i = threadIdx.x; i < 8 * nt; i += blockDim.x) {
+        const int2 hc = __ldg(a.hCol + 8 * T0 + i);   // {init, divisor} of a destination column
+        int *q = sInit + 16 * (i >> 3) + 4 * ((i & 7) >> 1) + (i & 1);
+        q[0] = q[2] = hc.x;
+        sDiv[i] = hc.y;
+    }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    // tiles that hold border columns (divisions in the epilogue): a warp-uniform flag per tile
     for (int i = threadIdx.x; i < nt; i += blockDim.x) {
-        int any = 0;
+        int any = 0;   // tiles that hold border columns divide in the epilogue: a warp-uniform flag per tile
 #pragma unroll
-        for (int j = 0; j < 8; ++j) any |= sCol[8 * i + j].y;
-        sOff[a.stripTiles + i] = any;
+        for (int j = 0; j < 8; ++j) any |= sDiv[8 * i + j];
+        sOff[i] = make_int2(2 * (__ldg(a.hTile + T0 + i).x - xs), any);
     }
     __syncthreads();
 
@@ -2537,19 +2541,29 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
                 uint32_t r[8];
                 uint4 bf;
             };
-            auto loadStep = [&](Step &st, const int ti, const int s) {
-                const uint32_t wl = wLd + sOff[ti] + 64 * s;
+            // tile ti of the strip: W offset + border flag at offS + 8 ti, B fragments at fragS + 512 HKS ti, rounding quad
+            // at initS + 64 ti, output bytes at outS + 8 ti.  This warp's tiles are warp, warp + nw, ...: the addresses run
+            auto loadStep = [&](Step &st, const int wOff, const uint32_t frag, const int s) {
+                const uint32_t wl = wLd + wOff + 64 * s;
                 asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                              : "=r"(st.r[0]), "=r"(st.r[1]), "=r"(st.r[2]), "=r"(st.r[3]) : "r"(wl));
                 asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
                              : "=r"(st.r[4]), "=r"(st.r[5]), "=r"(st.r[6]), "=r"(st.r[7]) : "r"(wl + 32));
-                st.bf = sFrag[(ti * HKS + s) * 32 + lane];
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(st.bf.x), "=r"(st.bf.y), "=r"(st.bf.z), "=r"(st.bf.w) : "r"(frag + 512 * s));
+            };
+            auto ldsInt2 = [](const uint32_t addr) -> int2 {
+                int2 v;
+                asm volatile("ld.shared.v2.s32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+                return v;
             };
             int ll[4], mid[4], hh[4];
-            auto computeStep = [&](const Step &st, const bool first) {
+            auto computeStep = [&](const Step &st, const bool first, const uint32_t init) {
                 if (first) {
+                    // the low product starts from the columns' rounding constants (one 16-byte load straight into the
+                    // accumulator quad), the other two from zero
+                    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(ll[0]), "=r"(ll[1]), "=r"(ll[2]), "=r"(ll[3]) : "r"(init));
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) ll[e] = mid[e] = hh[e] = 0;
+                    for (int e = 0; e < 4; ++e) mid[e] = hh[e] = 0;
                 }
                 uint32_t alo[4], ahi[4];
 #pragma unroll
@@ -2563,46 +2577,58 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
                 if (SIGNED) mmaU8S8(hh, ahi, st.bf.z, st.bf.w); else mmaU8U8(hh, ahi, st.bf.z, st.bf.w);
                 mmaU8U8(mid, ahi, st.bf.x, st.bf.y);
             };
-            auto finishTile = [&](const int ti) {
+            auto finishTile = [&](const int ti, const int border, const uint32_t out) {
                 // thread (g, t): rows g, g + 8; columns 8 (T0 + ti) + 2 t, + 1
-                const int4 hc = *reinterpret_cast<const int4 *>(sCol + 8 * ti + 2 * t);   // {init, divisor} of the two columns
                 int v[4];
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int init = (e & 1) ? hc.z : hc.x;
-                    v[e] = ll[e] + (mid[e] << 8) + (hh[e] << 16) + init;
-                }
+                for (int e = 0; e < 4; ++e) v[e] = ll[e] + (mid[e] << 8) + (hh[e] << 16);
                 if (!SIGNED) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) v[e] = (int)(short)(v[e] >> 23);   // Area / Linear: 8 + 15 fixed-point bits
-                } else if (sOff[a.stripTiles + ti] == 0) {
+                } else if (border == 0) {
 #pragma unroll
                     for (int e = 0; e < 4; ++e) v[e] = (int)(short)(v[e] >> 20);
                 } else {
+                    const int2 dv2 = *reinterpret_cast<const int2 *>(sDiv + 8 * ti + 2 * t);
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int dv = (e & 1) ? hc.w : hc.y;
+                        const int dv = (e & 1) ? dv2.y : dv2.x;
                         v[e] = (int)(short)(dv != 0 ? v[e] / dv : v[e] >> 20);   // resizeXborder: truncating division by deno * 64
                     }
                 }
                 const uint32_t p01 = packSatU8(v[1], v[0], 0u), p23 = packSatU8(v[3], v[2], 0u);
-                *reinterpret_cast<uint16_t *>(oTile + g * oStride + 8 * ti + 2 * t) = (uint16_t)p01;
-                *reinterpret_cast<uint16_t *>(oTile + (g + 8) * oStride + 8 * ti + 2 * t) = (uint16_t)p23;
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(out), "h"((uint16_t)p01) : "memory");
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(out + 8 * oStride), "h"((uint16_t)p23) : "memory");
             };
-            // steps are numbered i = ti * HKS + s; a pair of tiles is 2 HKS steps, so the two operand buffers alternate
-            // at compile-time positions inside the unrolled pair
-            // this warp's tiles: warp, warp + nw, ...
+            // steps are numbered i = (tile sequence) * HKS + s; a pair of tiles is 2 HKS steps, so the two operand buffers
+            // alternate at compile-time positions inside the unrolled pair
+            const uint32_t dOff = 8 * nw, dFrag = 512 * HKS * nw, dInit = 64 * nw, dOut = 8 * nw;
+            uint32_t aOff = smemAddr(sOff) + 8 * warp, aFrag = smemAddr(sFrag) + 512 * HKS * warp + 16 * lane;
+            uint32_t aInit = smemAddr(sInit) + 64 * warp + 16 * t, aOut = oTileS + g * oStride + 8 * warp + 2 * t;
             Step st[2];
-            if (warp < nt) loadStep(st[0], warp, 0);
+            int2 odCur = make_int2(0, 0), odNext = make_int2(0, 0);   // {W offset, border flag} of the running tile and the one after it
+            if (warp < nt) {
+                odCur = ldsInt2(aOff);
+                loadStep(st[0], odCur.x, aFrag, 0);
+                if (warp + nw < nt) odNext = ldsInt2(aOff + dOff);
+            }
             for (int tp = warp; tp < nt; tp += 2 * nw) {
 #pragma unroll
                 for (int u = 0; u < 2 * HKS; ++u) {
                     const int ti = tp + (u / HKS) * nw, s = u % HKS;
-                    const int nti = tp + ((u + 1) / HKS) * nw, ns = (u + 1) % HKS;
                     if (ti < nt) {
-                        if (nti < nt) loadStep(st[(u + 1) & 1], nti, ns);
-                        computeStep(st[u & 1], s == 0);
-                        if (s == HKS - 1) finishTile(ti);
+                        if (s + 1 < HKS) {
+                            loadStep(st[(u + 1) & 1], odCur.x, aFrag, s + 1);
+                        } else if (ti + nw < nt) {
+                            loadStep(st[(u + 1) & 1], odNext.x, aFrag + dFrag, 0);
+                        }
+                        computeStep(st[u & 1], s == 0, aInit);
+                        if (s == HKS - 1) {
+                            finishTile(ti, odCur.y, aOut);
+                            odCur = odNext;
+                            aOff += dOff, aFrag += dFrag, aInit += dInit, aOut += dOut;
+                            if (ti + 2 * nw < nt) odNext = ldsInt2(aOff + dOff);
+                        }
                     }
                 }
             }

@@ -2644,20 +2644,26 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
             if (stKind > 0) {
                 uint8_t *d = drow + stX;
                 uint32_t sp = oTileS + stRow * oStride + stX;
-                for (int r = stRow; r < 16; r += stRows, d += stStep, sp += stRows * oStride) {
-                    if (r < rLo || r >= rHi) continue;
-                    if (stKind == 16) {
-                        uint4 v;
-                        asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sp));
-                        *reinterpret_cast<uint4 *>(d) = v;
-                    } else if (stKind == 8) {
-                        uint2 v;
-                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sp));
-                        *reinterpret_cast<uint2 *>(d) = v;
-                    } else {
-                        // the ragged piece at the end of the last strip
-                        for (int i = 0; i < min(1 << pieceShift, tw - stX); ++i) d[i] = oTile[(r * oStride + stX) + i];
-                    }
+                const bool allRows = rLo == 0 && rHi == 16;   // every block but the first and last of a row band
+                if (stKind == 16) {
+                    for (int r = stRow; r < 16; r += stRows, d += stStep, sp += stRows * oStride)
+                        if (allRows || (r >= rLo && r < rHi)) {
+                            uint4 v;
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(sp));
+                            *reinterpret_cast<uint4 *>(d) = v;
+                        }
+                } else if (stKind == 8) {
+                    for (int r = stRow; r < 16; r += stRows, d += stStep, sp += stRows * oStride)
+                        if (allRows || (r >= rLo && r < rHi)) {
+                            uint2 v;
+                            asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(sp));
+                            *reinterpret_cast<uint2 *>(d) = v;
+                        }
+                } else {
+                    // the ragged piece at the end of the last strip
+                    for (int r = stRow; r < 16; r += stRows, d += stStep)
+                        if (r >= rLo && r < rHi)
+                            for (int i = 0; i < min(1 << pieceShift, tw - stX); ++i) d[i] = oTile[(r * oStride + stX) + i];
                 }
             } else if (stKind == 0) {
                 // single bytes (unaligned destination): a row may have more bytes than the CTA has threads

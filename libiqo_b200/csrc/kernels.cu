@@ -2334,6 +2334,7 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     const MmaArgs &a = prm.a;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), nw = blockDim.x >> 5;   // (the shuffle tells the compiler it is warp-uniform)
+    const int wv = nw - 1 - warp;   // segments and tiles are dealt out from the last warp down: warp 0, which also requests the rows, gets the short end
     const int strip = blockIdx.x;
     const int T0 = strip * a.stripTiles;                        // first destination tile of the strip
     const int tx0 = 8 * T0;
@@ -2511,11 +2512,11 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
             const uint32_t w2 = addU16x2(prmt((uint32_t)dB[0], (uint32_t)dB[1], 0x5410), biasLo), w3 = addU16x2(prmt((uint32_t)dB[2], (uint32_t)dB[3], 0x5410), biasHi);
             asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(wSt + 32 * seg), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
         };
-        if (warp < nseg) {
+        if (wv < nseg) {
             // this warp's segments: warp, warp + nw, ...
             uint32_t bf0[VKS][4], bf1[VKS][4];
-            loadSeg(bf0, warp);
-            int seg = warp;
+            loadSeg(bf0, wv);
+            int seg = wv;
             for (; seg + nw < nseg; seg += 2 * nw) {
                 loadSeg(bf1, seg + nw);
                 computeSeg(bf0, seg);
@@ -2603,16 +2604,16 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
             // steps are numbered i = (tile sequence) * HKS + s; a pair of tiles is 2 HKS steps, so the two operand buffers
             // alternate at compile-time positions inside the unrolled pair
             const uint32_t dOff = 8 * nw, dFrag = 512 * HKS * nw, dInit = 64 * nw, dOut = 8 * nw;
-            uint32_t aOff = smemAddr(sOff) + 8 * warp, aFrag = smemAddr(sFrag) + 512 * HKS * warp + 16 * lane;
-            uint32_t aInit = smemAddr(sInit) + 64 * warp + 16 * t, aOut = oTileS + g * oStride + 8 * warp + 2 * t;
+            uint32_t aOff = smemAddr(sOff) + 8 * wv, aFrag = smemAddr(sFrag) + 512 * HKS * wv + 16 * lane;
+            uint32_t aInit = smemAddr(sInit) + 64 * wv + 16 * t, aOut = oTileS + g * oStride + 8 * wv + 2 * t;
             Step st[2];
             int2 odCur = make_int2(0, 0), odNext = make_int2(0, 0);   // {W offset, border flag} of the running tile and the one after it
-            if (warp < nt) {
+            if (wv < nt) {
                 odCur = ldsInt2(aOff);
                 loadStep(st[0], odCur.x, aFrag, 0);
-                if (warp + nw < nt) odNext = ldsInt2(aOff + dOff);
+                if (wv + nw < nt) odNext = ldsInt2(aOff + dOff);
             }
-            for (int tp = warp; tp < nt; tp += 2 * nw) {
+            for (int tp = wv; tp < nt; tp += 2 * nw) {
 #pragma unroll
                 for (int u = 0; u < 2 * HKS; ++u) {
                     const int ti = tp + (u / HKS) * nw, s = u % HKS;

@@ -2236,22 +2236,28 @@ cudaError_t launchLStreamT(const LStreamArgs &a, cudaStream_t stream)
 
 
 // ---------------------------------------------------------------------------------------
-// Tensor-path Lanczos kernel (plan.hpp MmaPlan): any ratio, phase count and row band.  Both passes are banded
-// integer matrix products on the legacy integer tensor path (mma.sync.m16n8k32, SASS IMMA.16832: measured on
-// B200 at 2048 MAC/clk/SM against 256 for dp4a, tools/mma_probe.cu), exact like every integer sum.
-//   A warp (one per CTA) owns a strip of destination columns and walks down 16-row destination blocks.
-//   source      raw source rows travel global -> shared by TMA in chunks of 16 rows (circular FIFO of a.nChunks chunks,
-//               an mbarrier per chunk); the chunks the next block needs are requested right after the vertical pass of
-//               the running block, so their latency hides behind its horizontal pass.
+// Tensor-path kernel (plan.hpp MmaPlan): Lanczos at any ratio, phase count and row band; Area / Linear at general
+// ratios.  Both passes are banded integer matrix products on the legacy integer tensor path (mma.sync.m16n8k16 / k32,
+// SASS IMMA.16816 / IMMA.16832: measured on B200 at 2048 MAC/clk/SM against 256 for dp4a, tools/mma_probe.cu), exact
+// like every integer sum.
+//   A CTA of a.warps warps owns a strip of destination columns and walks down 16-row destination blocks; FIFO, W tile,
+//   output tile and tables are shared, segments / tiles / store rows are dealt out round robin from the last warp down
+//   (warp 0 also requests the rows), two CTA barriers per block separate the phases.
+//   source      raw source rows travel global -> shared by TMA in chunks of 8 rows: chunk c lives in FIFO slot
+//               c mod a.nChunks, one mbarrier phase per block's requests; the chunks the next block needs are requested
+//               right after the vertical pass of the running block, so their latency hides behind its horizontal pass.
 //   vertical    per 16 source columns: ldmatrix.m16n16.trans.b8 turns 32 source rows x 16 columns straight into the
 //               B fragments (four vertically adjacent bytes per register -- no PRMT transposes, no lane-private ring);
-//               the A fragments are the block's coefficient bytes from the planner (1 - 3 k-steps of 32 source rows);
-//               results + bias are packed to 16-bit pairs and written with stmatrix into the block's W tile.
+//               k slot -> FIFO row is a planner table of byte offsets; the A fragments are the block's coefficient
+//               bytes (1 - 3 k-steps of 32 source rows); results + bias are packed to 16-bit pairs and written with
+//               stmatrix into the block's W tile.
 //   horizontal  per 8 destination columns: ldmatrix of W (16 rows x 32 columns per k-step), PRMT splits the low and
 //               high bytes (the k order inside a fragment is {2t, 2t+1, 8+2t, 9+2t}; the planner permutes the
 //               coefficient fragments the same way), four mma per k-step (W low/high byte x coefficient low/high
-//               plane), recombination, rounding shift or border division, saturation.
-//   output      the block's 16 x stripW result tile is staged in shared memory and leaves as 16-byte row pieces.
+//               plane; the low product starts from the columns' rounding constants), recombination, rounding shift
+//               or border division, saturation.  Table addresses run from tile to tile, a tile's descriptor and the
+//               operands of a step are fetched one tile / step ahead.
+//   output      the block's 16 x stripW result tile is staged in shared memory and leaves as 16- or 8-byte row pieces.
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void mmaS8U8(int (&d)[4], const uint4 &a, uint32_t b0, uint32_t b1)
 {

@@ -147,6 +147,34 @@ def test_mma_bands_batches_and_device_pitches():
     assert np.array_equal(ddst.cpu().numpy(), oracle_resize(LANCZOS, host, 240, 135, 3, sw=480)[1])
 
 
+def test_auto_picks_the_kernel_by_ratio_taps_and_launch_size():
+    """AUTO: big batches of 3:2-style reductions with ten or more taps run on the tensor path, Lanczos2 at 3:2,
+    up-sampling and small launches stay on the 3:2 streaming / packed kernels (capi.cu, measured cross-overs in
+    DESIGN 4.8) -- and whatever runs is bit-exact."""
+    torch = pytest.importorskip("torch")
+    for deg, sw, sh, dw, dh, n, want_kernel in ((3, 960, 540, 640, 360, 96, "lanczos_mma"),
+                                                (4, 960, 540, 640, 360, 96, "lanczos_mma"),
+                                                (3, 960, 540, 480, 360, 96, "lanczos_mma"),   # 2:1 on X, 3:2 on Y
+                                                (2, 960, 540, 640, 360, 96, "ratio_stream"),
+                                                (3, 480, 270, 960, 540, 96, "ratio_stream"),
+                                                (3, 960, 540, 640, 360, 2, None)):
+        host = np.stack([lcg_image(sh, sw, seed=40 + f) for f in range(min(n, 3))])
+        want = np.stack([oracle_resize(LANCZOS, host[f], dw, dh, deg)[1] for f in range(host.shape[0])])
+        dsrc = torch.from_numpy(host).cuda()[torch.arange(n) % host.shape[0]].contiguous()
+        ddst = torch.zeros((n, dh, dw), dtype=torch.uint8, device="cuda")
+        with iqo.LanczosResizer(deg, sw, sh, dw, dh) as r:
+            r.resize_batch(n, sw, sw * sh, dsrc, dw, dw * dh, ddst, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            kernel = r.last_kernel()
+        if want_kernel is not None:
+            assert kernel == want_kernel, (deg, sw, sh, dw, dh, n, kernel)
+        else:
+            assert kernel != "lanczos_mma", kernel
+        got = ddst.cpu().numpy()
+        for f in range(n):
+            assert np.array_equal(got[f], want[f % host.shape[0]]), (deg, sw, sh, dw, dh, f, kernel)
+
+
 # ---------------------------------------------------------------------------------------------
 # Area / Linear on the same kernel (unsigned byte planes, 23-bit shift; a weight of 256 is split 255 + 1 over two
 # k slots that read the same source row).  Replaces src/IQOAreaResizerImpl_Generic.cpp:303-368 and

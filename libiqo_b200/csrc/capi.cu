@@ -318,6 +318,22 @@ bool isDevicePointer(const void *p)
     return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
 }
 
+// Linear up-sampling ratios the streaming kernel is instantiated for (items of 4 rS source columns)
+bool linearUpRatio(const AxisPlan &X)
+{
+    if (X.identity || X.N != 2) return false;
+    const bool known = (X.rS == 1 && (X.rD == 2 || X.rD == 3 || X.rD == 4)) || (X.rS == 2 && (X.rD == 3 || X.rD == 5)) ||
+                       (X.rS == 3 && X.rD == 4) || (X.rS == 4 && X.rD == 5);
+    return known && X.S % (4 * X.rS) == 0;
+}
+const char *linearUpName(const AxisPlan &X)
+{
+    return X.rS == 1   ? (X.rD == 2 ? "linear_up2" : X.rD == 3 ? "linear_up3" : "linear_up4")
+           : X.rS == 2 ? (X.rD == 3 ? "linear_up_2_3" : "linear_up_2_5")
+           : X.rS == 3 ? "linear_up_3_4"
+                       : "linear_up_4_5";
+}
+
 // AUTO gives a launch to the tensor-path kernel when it has enough warps (strip x band) to fill the device
 bool mmaWorthIt(const iqo_cuda_resizer *r, size_t nFrames, size_t dstRows)
 {
@@ -642,24 +658,20 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
             return IQO_CUDA_OK;
         }
     }
-    // Linear 2x / 3x up-sampling on X: streaming kernel
+    // Linear up-sampling at 1:2, 1:3, 1:4, 2:3, 2:5, 3:4 or 4:5 on X (any ratio on Y): streaming kernel
     {
         const AxisPlan &X = r->plan.x, &Y = r->plan.y;
-        const int K = (X.S > 0 && X.D % X.S == 0) ? int(X.D / X.S) : 0;
-        if (r->path == IQO_CUDA_PATH_AUTO && r->plan.kind == kLinear && whole && (K == 2 || K == 3) && X.S % 4 == 0 &&
-            !Y.identity && Y.N == 2 && Y.D <= 65535 && ((uintptr_t)src % 4) == 0 && srcSt % 4 == 0 && srcFrameStride % 4 == 0 &&
+        if (r->path == IQO_CUDA_PATH_AUTO && r->plan.kind == kLinear && whole && linearUpRatio(X) && !Y.identity && Y.N == 2 &&
+            Y.D <= 65535 && ((uintptr_t)src % 4) == 0 && srcSt % 4 == 0 && srcFrameStride % 4 == 0 &&
             ((uintptr_t)dst % 4) == 0 && dstSt % 4 == 0 && dstFrameStride % 4 == 0) {
-            uint32_t cw[3] = {0, 0, 0};
-            for (int t = 0; t < K; ++t) {
-                const uint32_t c0 = uint32_t(X.coef[size_t(t) * 2]), c1 = uint32_t(X.coef[size_t(t) * 2 + 1]);
-                cw[t] = (c0 & 0xff) | ((c1 & 0xff) << 8) | ((c0 >> 8) << 16) | ((c1 >> 8) << 24);
-            }
-            r->lastKernel = (K == 2) ? "linear_up2" : "linear_up3";
+            int q1[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            for (int t = 0; t < int(X.rD); ++t) q1[t] = X.coef[size_t(t) * 2 + 1];   // weight of the right column of phase t
+            r->lastKernel = linearUpName(X);
             for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
                 const int nf = int(std::min<size_t>(65535, nFrames - f0));
-                CUDA_TRY(launchLinearUp(K, src + f0 * srcFrameStride, dst + f0 * dstFrameStride, (long long)srcSt, (long long)dstSt,
-                                        (long long)srcFrameStride, (long long)dstFrameStride, int(X.S), int(Y.S), int(X.D), int(Y.D),
-                                        nf, sp.ty.first, sp.ty.row, sp.ty.coef, cw, stream));
+                CUDA_TRY(launchLinearUp(int(X.rS), int(X.rD), src + f0 * srcFrameStride, dst + f0 * dstFrameStride, (long long)srcSt,
+                                        (long long)dstSt, (long long)srcFrameStride, (long long)dstFrameStride, int(X.S), int(Y.S),
+                                        int(X.D), int(Y.D), nf, sp.ty.first, sp.ty.row, sp.ty.coef, q1, stream));
             }
             return IQO_CUDA_OK;
         }
@@ -1360,10 +1372,10 @@ int iqo_cuda_plan_kernel(int kind, unsigned degree, size_t srcW, size_t srcH, si
     const bool lstream = ls.eligible && lstreamHasKernel(q.NP);
     const bool area2 = p.kind == kArea && p.x.rD == 1 && p.x.rS == 2 && p.y.rD == 1 && p.y.rS == 2 && p.x.N == 2 && p.y.N == 2 && p.x.S % 16 == 0;
     const long long kx = (p.x.D % p.x.S == 0) ? p.x.D / p.x.S : 0;
-    const bool linup = p.kind == kLinear && (kx == 2 || kx == 3) && p.x.S % 4 == 0 && !p.y.identity;
+    const bool linup = p.kind == kLinear && linearUpRatio(p.x) && !p.y.identity;
     if (kernel && kernelCap)
         snprintf(kernel, kernelCap, "%s", sm.eligible ? "half_small" : h.eligible ? (h.symmetric ? "half_sym" : "half") : area2 ? "area2"
-                                          : linup ? (kx == 2 ? "linear_up2" : "linear_up3") : ratio ? "ratio_stream" : lstream ? "lanczos_stream" : q.eligible ? "packed" : "generic");
+                                          : linup ? linearUpName(p.x) : ratio ? "ratio_stream" : lstream ? "lanczos_stream" : q.eligible ? "packed" : "generic");
     if (why && whyCap)
         snprintf(why, whyCap, "%s%s%s%s%s", h.why.c_str(), rt.eligible ? "" : "; ratio: ", rt.eligible ? "" : rt.why.c_str(),
                  q.eligible ? "" : "; packed: ", q.eligible ? "" : q.why.c_str());

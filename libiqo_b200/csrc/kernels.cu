@@ -1506,11 +1506,10 @@ struct LinearUpArgs {
     uint8_t *dst;
     long long srcPitch, dstPitch, srcFrameStride, dstFrameStride;
     int SW, SH, DW, DH;
-    int wordsPerRow;           // SW / 4
-    uint32_t rcpWords;         // ceil(2^32 / wordsPerRow)
+    int itemsPerRow;           // SW / (4 RS)
+    uint32_t rcpItems;         // ceil(2^32 / itemsPerRow)
     const int32_t *firstY, *rowY, *coefY;   // generic vertical tables (two taps per row)
-    uint32_t cwX[3];           // per phase: bytes (lo(q0), lo(q1), hi(q0), hi(q1))
-    int q1X[3];                // per phase: twice the weight of the right column (the left one is 32768 - q1)
+    int q1X[8];                // per phase: twice the weight of the right column (the left one is 32768 - q1)
 };
 
 #ifndef IQO_LINEAR_UP_ROWS
@@ -1518,22 +1517,26 @@ struct LinearUpArgs {
 #endif
 constexpr int kLinearUpRows = IQO_LINEAR_UP_ROWS;  // destination rows per item: they mostly share their two source rows
 
-template <int K>
+// RS : RD up-sampling on X (1:2, 1:3, 1:4, 2:3, 2:5, 3:4, 4:5): an item is 4 RS source columns (RS aligned words) and the 4 RD
+// destination pixels they produce, for kLinearUpRows destination rows
+template <int RS, int RD>
 __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constant__ LinearUpArgs a)
 {
-    // item = (group of kLinearUpRows destination rows, source word), flattened so that rows whose word
+    constexpr int NC = 4 * RS + 2;   // source columns 4 RS j - 1 .. 4 RS j + 4 RS
+    // item = (group of kLinearUpRows destination rows, RS source words), flattened so that rows whose item
     // count is not a multiple of the block size do not leave threads idle
     const uint32_t item = blockIdx.x * 256u + threadIdx.x;
-    const int grp = (a.wordsPerRow == 1) ? (int)item : (int)__umulhi(item, a.rcpWords);
-    const int j = (int)item - grp * a.wordsPerRow;
+    const int grp = (a.itemsPerRow == 1) ? (int)item : (int)__umulhi(item, a.rcpItems);
+    const int j = (int)item - grp * a.itemsPerRow;
     const int y0 = grp * kLinearUpRows;
     if (y0 >= a.DH) return;
     const uint8_t *__restrict__ src = a.src + (long long)blockIdx.y * a.srcFrameStride;
-    uint8_t *__restrict__ out = a.dst + (long long)blockIdx.y * a.dstFrameStride + (long long)y0 * a.dstPitch + 4 * K * j;
-    const int jm = max(j - 1, 0), jp = min(j + 1, a.wordsPerRow - 1);
+    uint8_t *__restrict__ out = a.dst + (long long)blockIdx.y * a.dstFrameStride + (long long)y0 * a.dstPitch + 4 * RD * j;
+    const int wordsPerRow = a.itemsPerRow * RS;
+    const int w0 = RS * j, wm = max(w0 - 1, 0), wp = min(w0 + RS, wordsPerRow - 1);
 
-    // the six source columns 4j-1 .. 4j+4 of the two source rows in use
-    uint32_t A[6], Bv[6];
+    // the NC source columns of the two source rows in use
+    uint32_t A[NC], Bv[NC];
     int have = -(1 << 30);
 #pragma unroll
     for (int r = 0; r < kLinearUpRows; ++r) {
@@ -1548,37 +1551,47 @@ __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constan
             const int r0 = min(max(fy, 0), a.SH - 1), r1 = min(max(fy + 1, 0), a.SH - 1);
             const uint32_t *row0 = reinterpret_cast<const uint32_t *>(src + (long long)r0 * a.srcPitch);
             const uint32_t *row1 = reinterpret_cast<const uint32_t *>(src + (long long)r1 * a.srcPitch);
-            const uint32_t am = __ldg(row0 + jm), a0 = __ldg(row0 + j), ap = __ldg(row0 + jp);
-            const uint32_t bm = __ldg(row1 + jm), b0 = __ldg(row1 + j), bp = __ldg(row1 + jp);
+            uint32_t aw[RS], bw[RS];
+            const uint32_t am = __ldg(row0 + wm), ap = __ldg(row0 + wp);
+            const uint32_t bm = __ldg(row1 + wm), bp = __ldg(row1 + wp);
+#pragma unroll
+            for (int w = 0; w < RS; ++w) aw[w] = __ldg(row0 + w0 + w), bw[w] = __ldg(row1 + w0 + w);
             A[0] = am >> 24, Bv[0] = bm >> 24;
-            A[1] = a0 & 0xffu, Bv[1] = b0 & 0xffu;
-            A[2] = prmt(a0, 0u, 0x4441), Bv[2] = prmt(b0, 0u, 0x4441);
-            A[3] = prmt(a0, 0u, 0x4442), Bv[3] = prmt(b0, 0u, 0x4442);
-            A[4] = a0 >> 24, Bv[4] = b0 >> 24;
-            A[5] = ap & 0xffu, Bv[5] = bp & 0xffu;
+#pragma unroll
+            for (int w = 0; w < RS; ++w) {
+                A[4 * w + 1] = aw[w] & 0xffu, Bv[4 * w + 1] = bw[w] & 0xffu;
+                A[4 * w + 2] = prmt(aw[w], 0u, 0x4441), Bv[4 * w + 2] = prmt(bw[w], 0u, 0x4441);
+                A[4 * w + 3] = prmt(aw[w], 0u, 0x4442), Bv[4 * w + 3] = prmt(bw[w], 0u, 0x4442);
+                A[4 * w + 4] = aw[w] >> 24, Bv[4 * w + 4] = bw[w] >> 24;
+            }
+            A[NC - 1] = ap & 0xffu, Bv[NC - 1] = bp & 0xffu;
+            // columns -1 and S are the replicated edge columns (beyond 3x more than the first / last pixel read them)
+            if (j == 0) A[0] = A[1], Bv[0] = Bv[1];
+            if (j == a.itemsPerRow - 1) A[NC - 1] = A[NC - 2], Bv[NC - 1] = Bv[NC - 2];
         }
         // vertical blend per column (<= 255 * 256), then per pixel, with the two horizontal weights of a phase
         // summing to 32768:   2 * (lo * q0 + hi * q1 + 2^22) == (lo << 16) + 2^23 + (hi - lo) * 2 q1
         // -- one multiply-add per pixel; the doubled sum has the pixel in its top byte (a convex blend needs no
         // saturation, and 65280 * 65536 + 2^23 still fits 32 bits)
-        uint32_t V[6], baseN[5], diffN[5];
+        uint32_t V[NC], baseN[NC - 1], diffN[NC - 1];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) V[c] = A[c] * q0 + Bv[c] * q1;
+        for (int c = 0; c < NC; ++c) V[c] = A[c] * q0 + Bv[c] * q1;
 #pragma unroll
-        for (int n = 0; n < 5; ++n) {
+        for (int n = 0; n < NC - 1; ++n) {
             baseN[n] = V[n] * 65536u + (1u << 23);
             diffN[n] = V[n + 1] - V[n];
         }
-        uint32_t packed[K];
+        uint32_t packed[RD];
 #pragma unroll
-        for (int quad = 0; quad < K; ++quad) {
+        for (int quad = 0; quad < RD; ++quad) {
             uint32_t v[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int i = 4 * quad + e;
-                // pixel i blends the columns (4j-1+n, 4j+n), n = g(i) + 1 = floor((2 i + 1 + K) / (2 K))
-                const int n = (2 * i + 1 + K) / (2 * K);
-                v[e] = baseN[n] + diffN[n] * (uint32_t)a.q1X[i % K];  // q1X holds 2 * q1
+                // pixel i blends the columns (4 RS j - 1 + n, + 1), n = first tap + 1 = floor(((2 i + 1) RS + RD) / (2 RD))
+                // (plan.cpp linearAxis: first = floor(((2 d + 1) S - D) / (2 D)))
+                const int n = ((2 * i + 1) * RS + RD) / (2 * RD);
+                v[e] = baseN[n] + diffN[n] * (uint32_t)a.q1X[i % RD];  // q1X holds 2 * q1
             }
             packed[quad] = prmt(prmt(v[0], v[1], 0x0073), prmt(v[2], v[3], 0x0073), 0x5410);  // the four top bytes
         }
@@ -1587,13 +1600,13 @@ __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constan
             const int v = (int)(V[1] + 128u) >> 8;  // column 0
             packed[0] = (packed[0] & 0xffffff00u) | (uint32_t)min(v, 255);
         }
-        if (j == a.wordsPerRow - 1) {
-            const int v = (int)(V[4] + 128u) >> 8;  // column S-1
-            packed[K - 1] = (packed[K - 1] & 0x00ffffffu) | ((uint32_t)min(v, 255) << 24);
+        if (j == a.itemsPerRow - 1) {
+            const int v = (int)(V[NC - 2] + 128u) >> 8;  // column S-1
+            packed[RD - 1] = (packed[RD - 1] & 0x00ffffffu) | ((uint32_t)min(v, 255) << 24);
         }
         uint8_t *o = out + (long long)r * a.dstPitch;
 #pragma unroll
-        for (int quad = 0; quad < K; ++quad) *reinterpret_cast<uint32_t *>(o + 4 * quad) = packed[quad];
+        for (int quad = 0; quad < RD; ++quad) *reinterpret_cast<uint32_t *>(o + 4 * quad) = packed[quad];
     }
 }
 
@@ -2999,9 +3012,9 @@ cudaError_t launchArea2(const uint8_t *src, uint8_t *dst, long long srcPitch, lo
     return cudaGetLastError();
 }
 
-cudaError_t launchLinearUp(int K, const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch,
+cudaError_t launchLinearUp(int RS, int RD, const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch,
                            long long srcFrameStride, long long dstFrameStride, int SW, int SH, int DW, int DH, int nFrames,
-                           const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const uint32_t cwX[3],
+                           const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const int q1X[8],
                            cudaStream_t stream)
 {
     LinearUpArgs a;
@@ -3015,22 +3028,30 @@ cudaError_t launchLinearUp(int K, const uint8_t *src, uint8_t *dst, long long sr
     a.SH = SH;
     a.DW = DW;
     a.DH = DH;
-    a.wordsPerRow = SW / 4;
+    if (RS <= 0 || SW % (4 * RS) != 0) return cudaErrorInvalidValue;
+    a.itemsPerRow = SW / (4 * RS);
     a.firstY = firstY;
     a.rowY = rowY;
     a.coefY = coefY;
-    for (int i = 0; i < 3; ++i) {
-        a.cwX[i] = cwX[i];
-        a.q1X[i] = 2 * int(((cwX[i] >> 8) & 0xffu) | ((cwX[i] >> 24) << 8));  // low and high byte plane of the second weight
-    }
-    a.rcpWords = (uint32_t)((0x100000000ull + a.wordsPerRow - 1) / a.wordsPerRow);
-    const long long items = (long long)a.wordsPerRow * ((DH + kLinearUpRows - 1) / kLinearUpRows);
+    for (int i = 0; i < 8; ++i) a.q1X[i] = 2 * q1X[i];
+    a.rcpItems = (uint32_t)((0x100000000ull + a.itemsPerRow - 1) / a.itemsPerRow);
+    const long long items = (long long)a.itemsPerRow * ((DH + kLinearUpRows - 1) / kLinearUpRows);
     if (items >= (1ll << 31)) return cudaErrorInvalidConfiguration;
     dim3 grid((unsigned)((items + 255) / 256), nFrames);
-    if (K == 2)
-        resizeLinearUpKernel<2><<<grid, 256, 0, stream>>>(a);
-    else if (K == 3)
-        resizeLinearUpKernel<3><<<grid, 256, 0, stream>>>(a);
+    if (RS == 1 && RD == 2)
+        resizeLinearUpKernel<1, 2><<<grid, 256, 0, stream>>>(a);
+    else if (RS == 1 && RD == 3)
+        resizeLinearUpKernel<1, 3><<<grid, 256, 0, stream>>>(a);
+    else if (RS == 2 && RD == 3)
+        resizeLinearUpKernel<2, 3><<<grid, 256, 0, stream>>>(a);
+    else if (RS == 3 && RD == 4)
+        resizeLinearUpKernel<3, 4><<<grid, 256, 0, stream>>>(a);
+    else if (RS == 1 && RD == 4)
+        resizeLinearUpKernel<1, 4><<<grid, 256, 0, stream>>>(a);
+    else if (RS == 2 && RD == 5)
+        resizeLinearUpKernel<2, 5><<<grid, 256, 0, stream>>>(a);
+    else if (RS == 4 && RD == 5)
+        resizeLinearUpKernel<4, 5><<<grid, 256, 0, stream>>>(a);
     else
         return cudaErrorInvalidValue;
     g_launches.fetch_add(1);

@@ -128,9 +128,9 @@ cudaError_t launchArea2(const uint8_t *src, uint8_t *dst, long long srcPitch, lo
 
 // Linear up-sampling by K = 2 or 3 on X (any Linear ratio on Y): streaming kernel.  Needs SW % 4 == 0 and
 // 4-byte aligned source / destination rows; DH <= 65535, nFrames <= 65535.
-cudaError_t launchLinearUp(int K, const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch,
+cudaError_t launchLinearUp(int RS, int RD, const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch,
                            long long srcFrameStride, long long dstFrameStride, int SW, int SH, int DW, int DH, int nFrames,
-                           const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const uint32_t cwX[3],
+                           const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const int q1X[8],
                            cudaStream_t stream);
 
 // Arguments of the streaming 2:1 small-kernel path (plan.hpp SmallPlan).

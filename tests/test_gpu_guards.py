@@ -29,7 +29,8 @@ FAMILIES = [
     (AREA, 0, 1, 960, 540, 480, 270, iqo.PATH_AUTO, "area2"),
     (AREA, 0, 1, 960, 540, 640, 360, iqo.PATH_AUTO, "packed"),
     (LINEAR, 0, 1, 320, 180, 960, 540, iqo.PATH_AUTO, "linear_up3"),
-    (LINEAR, 0, 1, 320, 180, 800, 400, iqo.PATH_AUTO, "packed"),
+    (LINEAR, 0, 1, 320, 180, 480, 270, iqo.PATH_AUTO, "linear_up_2_3"),
+    (LINEAR, 0, 1, 320, 180, 700, 400, iqo.PATH_AUTO, "packed"),
 ]
 
 

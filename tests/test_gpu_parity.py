@@ -540,14 +540,23 @@ def test_more_than_65535_frames_in_one_call(kind, deg, sw, sh, dw, dh):
 @pytest.mark.parametrize("case", [(1280, 720, 3840, 2160, "linear_up3"), (64, 36, 192, 108, "linear_up3"),
                                   (64, 36, 128, 72, "linear_up2"), (64, 36, 128, 100, "linear_up2"),
                                   (64, 36, 192, 36, "packed"),      # Y pass-through: general kernel
-                                  (68, 10, 204, 23, "linear_up3"), (4, 4, 12, 12, "linear_up3"), (8, 3, 16, 7, "linear_up2")])
+                                  (68, 10, 204, 23, "linear_up3"), (4, 4, 12, 12, "linear_up3"), (8, 3, 16, 7, "linear_up2"),
+                                  # 2:3 and 3:4 on X (items of 8 / 12 source columns), any ratio on Y
+                                  (1280, 720, 1920, 1080, "linear_up_2_3"), (64, 36, 96, 54, "linear_up_2_3"),
+                                  (8, 3, 12, 7, "linear_up_2_3"), (72, 50, 108, 31, "linear_up_2_3"),
+                                  (1440, 810, 1920, 1080, "linear_up_3_4"), (12, 5, 16, 9, "linear_up_3_4"),
+                                  (84, 33, 112, 100, "linear_up_3_4"),
+                                  (64, 36, 256, 144, "linear_up4"), (4, 4, 16, 9, "linear_up4"),
+                                  (768, 432, 1920, 1080, "linear_up_2_5"), (8, 6, 20, 15, "linear_up_2_5"),
+                                  (1536, 864, 1920, 1080, "linear_up_4_5"), (16, 9, 20, 11, "linear_up_4_5"),
+                                  (60, 36, 90, 54, "linear_mma|packed")])     # 60 is not a multiple of 8: other kernels
 def test_linear_integer_upsampling_kernel(case):
     sw, sh, dw, dh, kname = case
     for seed, fill in ((41, None), (0, 255), (0, 0)):
         src = lcg_image(sh, sw, seed=seed) if fill is None else np.full((sh, sw), fill, np.uint8)
         rc, want = oracle_resize(LINEAR, src, dw, dh)
         got, kernel = gpu_resize(LINEAR, src, dw, dh)
-        assert kernel == kname
+        assert kernel in kname.split("|"), kernel
         bad = np.argwhere(got != want)
         assert bad.size == 0, (len(bad), bad[:6].tolist())
 

@@ -326,6 +326,17 @@ bool linearUpRatio(const AxisPlan &X)
                        (X.rS == 3 && X.rD == 4) || (X.rS == 4 && X.rD == 5);
     return known && X.S % (4 * X.rS) == 0;
 }
+// Area reductions the streaming kernel is instantiated for; *nxEff = taps up to the last one that is non-zero in some phase
+bool areaDownRatio(const AxisPlan &X, int *nxEff)
+{
+    if (X.identity || X.rS <= X.rD || X.rD > 3 || X.numRows < int(X.rD)) return false;
+    int n = 0;
+    for (int ph = 0; ph < int(X.rD); ++ph)
+        for (int k = 0; k < X.N; ++k)
+            if (X.coef[size_t(ph) * X.N + k] != 0) n = std::max(n, k + 1);
+    if (nxEff) *nxEff = n;
+    return areaDownHasKernel(int(X.rS), int(X.rD), n) && X.S % areaDownItemColumns(int(X.rS), int(X.rD)) == 0;
+}
 const char *linearUpName(const AxisPlan &X)
 {
     return X.rS == 1   ? (X.rD == 2 ? "linear_up2" : X.rD == 3 ? "linear_up3" : "linear_up4")
@@ -654,6 +665,24 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
                 CUDA_TRY(launchArea2(src + f0 * srcFrameStride, dst + f0 * dstFrameStride, (long long)srcSt, (long long)dstSt,
                                      (long long)srcFrameStride, (long long)dstFrameStride, int(X.D), int(Y.D), nf, &Y.coef[0],
                                      &X.coef[0], stream));
+            }
+            return IQO_CUDA_OK;
+        }
+    }
+    // Area reductions at 3:2, 4:3, 2:1, 5:2, 3:1 or 4:1 on X (any ratio on Y): streaming kernel
+    {
+        const AxisPlan &X = r->plan.x, &Y = r->plan.y;
+        int nxEff = 0;
+        if (r->path == IQO_CUDA_PATH_AUTO && r->plan.kind == kArea && whole && areaDownRatio(X, &nxEff) && !Y.identity && Y.N <= 16 &&
+            Y.D <= 65535 * 8 && ((uintptr_t)src % 4) == 0 && srcSt % 4 == 0 && srcFrameStride % 4 == 0 &&
+            ((uintptr_t)dst % 4) == 0 && dstSt % 4 == 0 && dstFrameStride % 4 == 0) {
+            r->lastKernel = "area_down";
+            for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
+                const int nf = int(std::min<size_t>(65535, nFrames - f0));
+                CUDA_TRY(launchAreaDown(int(X.rS), int(X.rD), X.N, nxEff, src + f0 * srcFrameStride, dst + f0 * dstFrameStride,
+                                        (long long)srcSt, (long long)dstSt, (long long)srcFrameStride, (long long)dstFrameStride,
+                                        int(X.S), int(Y.S), int(X.D), int(Y.D), nf, Y.N, sp.ty.first, sp.ty.row, sp.ty.coef,
+                                        &X.coef[0], stream));
             }
             return IQO_CUDA_OK;
         }
@@ -1371,10 +1400,12 @@ int iqo_cuda_plan_kernel(int kind, unsigned degree, size_t srcW, size_t srcH, si
     if (q.eligible) buildLStreamPlan(p, q, ls);
     const bool lstream = ls.eligible && lstreamHasKernel(q.NP);
     const bool area2 = p.kind == kArea && p.x.rD == 1 && p.x.rS == 2 && p.y.rD == 1 && p.y.rS == 2 && p.x.N == 2 && p.y.N == 2 && p.x.S % 16 == 0;
+    const bool areadown = p.kind == kArea && areaDownRatio(p.x, 0) && !p.y.identity;
     const long long kx = (p.x.D % p.x.S == 0) ? p.x.D / p.x.S : 0;
     const bool linup = p.kind == kLinear && linearUpRatio(p.x) && !p.y.identity;
     if (kernel && kernelCap)
         snprintf(kernel, kernelCap, "%s", sm.eligible ? "half_small" : h.eligible ? (h.symmetric ? "half_sym" : "half") : area2 ? "area2"
+                                          : areadown ? "area_down"
                                           : linup ? linearUpName(p.x) : ratio ? "ratio_stream" : lstream ? "lanczos_stream" : q.eligible ? "packed" : "generic");
     if (why && whyCap)
         snprintf(why, whyCap, "%s%s%s%s%s", h.why.c_str(), rt.eligible ? "" : "; ratio: ", rt.eligible ? "" : rt.why.c_str(),

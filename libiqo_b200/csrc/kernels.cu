@@ -1612,6 +1612,97 @@ __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constan
 
 
 // ---------------------------------------------------------------------------------------
+// Area reductions at small rational ratios on X (3:2, 4:3, 2:1, 5:2, 3:1, 4:1; any ratio on Y), pure streaming:
+// an item is WS aligned source words (4 WS = PS source columns) and the 4 WD = PD destination pixels they cover
+// (PS RD == PD RS), for kAreaDownRows destination rows.  Vertical pass: every source row of a destination row's taps is
+// loaded (L1 keeps the rows that consecutive destination rows share), its bytes spread into 16-bit lane pairs
+// (one PRMT per pair) and accumulated with ONE IMAD per pair and tap (weights sum to 256: a lane never exceeds
+// 65280); horizontal pass: compile-time first taps floor(i RS / RD), doubled 15-bit weights from the constant bank,
+// accumulator preset to 2^23, so the pixel is the top byte of the sum (no shift, and a convex sum needs no
+// saturation).  No shared memory.  Area has no border rows or columns; the one column beyond an item that its last
+// pixel's zero-weight tap names is read clamped.
+// ---------------------------------------------------------------------------------------
+constexpr int kAreaDownRows = 8;
+constexpr int kAreaDownMaxNX = 4, kAreaDownMaxRD = 3;
+
+struct AreaDownArgs {
+    const uint8_t *src;
+    uint8_t *dst;
+    long long srcPitch, dstPitch, srcFrameStride, dstFrameStride;
+    int SW, SH, DW, DH;
+    int itemsPerRow;           // SW / PS
+    uint32_t rcpItems;         // ceil(2^32 / itemsPerRow)
+    int NY;                    // vertical taps per row
+    const int32_t *firstY, *rowY, *coefY;   // generic vertical tables
+    int cx2[kAreaDownMaxRD][kAreaDownMaxNX];  // per phase: twice the horizontal weights
+};
+
+template <int WS, int WD, int RS, int RD, int NX>
+__global__ void __launch_bounds__(256) resizeAreaDownKernel(const __grid_constant__ AreaDownArgs a)
+{
+    constexpr int PS = 4 * WS, PD = 4 * WD;
+    static_assert(PS * RD == PD * RS, "item geometry");
+    static_assert(((PD - 1) * RS) / RD + NX - 1 <= PS, "the last pixel reads at most one column beyond the item");
+    constexpr bool kExtra = ((PD - 1) * RS) / RD + NX - 1 == PS;   // some tap names the column after the item
+    const uint32_t item = blockIdx.x * 256u + threadIdx.x;
+    const int grp = (a.itemsPerRow == 1) ? (int)item : (int)__umulhi(item, a.rcpItems);
+    const int j = (int)item - grp * a.itemsPerRow;
+    const int y0 = grp * kAreaDownRows;
+    if (y0 >= a.DH) return;
+    const uint8_t *__restrict__ src = a.src + (long long)blockIdx.y * a.srcFrameStride;
+    uint8_t *__restrict__ out = a.dst + (long long)blockIdx.y * a.dstFrameStride + (long long)y0 * a.dstPitch + PD * j;
+    const int w0 = WS * j, wx = min(w0 + WS, a.itemsPerRow * WS - 1);
+    for (int r = 0; r < kAreaDownRows; ++r) {
+        const int y = y0 + r;
+        if (y >= a.DH) break;
+        const int fy = __ldg(a.firstY + y);
+        const int32_t *cy = a.coefY + __ldg(a.rowY + y) * a.NY;
+        uint32_t P[2 * WS], Px = 0u;   // lane pairs (column 4w + 2h, + 1) and the extra column
+#pragma unroll
+        for (int i = 0; i < 2 * WS; ++i) P[i] = 0u;
+        for (int t = 0; t < a.NY; ++t) {
+            const uint32_t c = (uint32_t)__ldg(cy + t);
+            if (c == 0u) continue;
+            const int row = min(max(fy + t, 0), a.SH - 1);
+            const uint32_t *rp = reinterpret_cast<const uint32_t *>(src + (long long)row * a.srcPitch);
+            uint32_t wv[WS];
+#pragma unroll
+            for (int w = 0; w < WS; ++w) wv[w] = __ldg(rp + w0 + w);
+            const uint32_t we = kExtra ? __ldg(rp + wx) : 0u;
+#pragma unroll
+            for (int w = 0; w < WS; ++w) {
+                P[2 * w] += prmt(wv[w], 0u, 0x4140) * c;
+                P[2 * w + 1] += prmt(wv[w], 0u, 0x4342) * c;
+            }
+            Px += (we & 0xffu) * c;
+        }
+        uint32_t V[PS + 1];
+#pragma unroll
+        for (int i = 0; i < 2 * WS; ++i) V[2 * i] = P[i] & 0xffffu, V[2 * i + 1] = P[i] >> 16;
+        V[PS] = Px;
+        uint32_t packed[WD];
+#pragma unroll
+        for (int quad = 0; quad < WD; ++quad) {
+            uint32_t v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int i = 4 * quad + e;
+                const int n = (i * RS) / RD;   // plan.cpp areaAxis: first = floor(d S / D)
+                uint32_t acc = 1u << 23;
+#pragma unroll
+                for (int k = 0; k < NX; ++k) acc += V[n + k] * (uint32_t)a.cx2[i % RD][k];
+                v[e] = acc;
+            }
+            packed[quad] = prmt(prmt(v[0], v[1], 0x0073), prmt(v[2], v[3], 0x0073), 0x5410);  // the four top bytes
+        }
+        uint8_t *o = out + (long long)r * a.dstPitch;
+#pragma unroll
+        for (int quad = 0; quad < WD; ++quad) *reinterpret_cast<uint32_t *>(o + 4 * quad) = packed[quad];
+    }
+}
+
+
+// ---------------------------------------------------------------------------------------
 // Streaming 2:1 x 2:1 Lanczos for kernels with at most four non-zero taps per axis (the pxScale=2
 // chroma planes of YUV420 4K->1080p, Lanczos1).  No shared memory: a thread owns 8 adjacent
 // destination pixels (16 source columns + one word either side) for 6 consecutive destination
@@ -3008,6 +3099,65 @@ cudaError_t launchArea2(const uint8_t *src, uint8_t *dst, long long srcPitch, lo
     const long long items = (long long)a.chunksPerRow * DH;
     dim3 grid((unsigned)((items + 255) / 256), (unsigned)nFrames);
     resizeArea2Kernel<<<grid, 256, 0, stream>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+bool areaDownHasKernel(int RS, int RD, int NX)
+{
+    // NX: taps up to the last one that is non-zero in some phase
+    return (RS == 3 && RD == 2 && NX <= 2) || (RS == 4 && RD == 3 && NX <= 2) || (RS == 2 && RD == 1 && NX <= 2) ||
+           (RS == 5 && RD == 2 && NX <= 3) || (RS == 3 && RD == 1 && NX <= 3) || (RS == 4 && RD == 1 && NX <= 4);
+}
+
+int areaDownItemColumns(int RS, int RD)
+{
+    // source columns per item: 4 WS with WS RD == WD RS
+    return RD == 1 ? 4 * RS : RD == 2 ? 4 * RS : 4 * RS;
+}
+
+cudaError_t launchAreaDown(int RS, int RD, int NX, int NXeff, const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch,
+                           long long srcFrameStride, long long dstFrameStride, int SW, int SH, int DW, int DH, int nFrames, int NY,
+                           const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const int32_t *cx /* [RD][NX] */,
+                           cudaStream_t stream)
+{
+    if (!areaDownHasKernel(RS, RD, NXeff)) return cudaErrorInvalidValue;
+    AreaDownArgs a;
+    a.src = src;
+    a.dst = dst;
+    a.srcPitch = srcPitch;
+    a.dstPitch = dstPitch;
+    a.srcFrameStride = srcFrameStride;
+    a.dstFrameStride = dstFrameStride;
+    a.SW = SW;
+    a.SH = SH;
+    a.DW = DW;
+    a.DH = DH;
+    const int PS = areaDownItemColumns(RS, RD);
+    if (SW % PS != 0) return cudaErrorInvalidValue;
+    a.itemsPerRow = SW / PS;
+    a.rcpItems = (uint32_t)((0x100000000ull + a.itemsPerRow - 1) / a.itemsPerRow);
+    a.NY = NY;
+    a.firstY = firstY;
+    a.rowY = rowY;
+    a.coefY = coefY;
+    for (int ph = 0; ph < kAreaDownMaxRD; ++ph)
+        for (int k = 0; k < kAreaDownMaxNX; ++k) a.cx2[ph][k] = (ph < RD && k < NX) ? 2 * cx[ph * NX + k] : 0;
+    const long long items = (long long)a.itemsPerRow * ((DH + kAreaDownRows - 1) / kAreaDownRows);
+    if (items >= (1ll << 31)) return cudaErrorInvalidConfiguration;
+    dim3 grid((unsigned)((items + 255) / 256), nFrames);
+    if (RS == 3 && RD == 2)
+        resizeAreaDownKernel<3, 2, 3, 2, 2><<<grid, 256, 0, stream>>>(a);
+    else if (RS == 4 && RD == 3)
+        resizeAreaDownKernel<4, 3, 4, 3, 2><<<grid, 256, 0, stream>>>(a);
+    else if (RS == 2 && RD == 1)
+        resizeAreaDownKernel<2, 1, 2, 1, 2><<<grid, 256, 0, stream>>>(a);
+    else if (RS == 5 && RD == 2)
+        resizeAreaDownKernel<5, 2, 5, 2, 3><<<grid, 256, 0, stream>>>(a);
+    else if (RS == 3 && RD == 1)
+        resizeAreaDownKernel<3, 1, 3, 1, 3><<<grid, 256, 0, stream>>>(a);
+    else
+        resizeAreaDownKernel<4, 1, 4, 1, 4><<<grid, 256, 0, stream>>>(a);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }

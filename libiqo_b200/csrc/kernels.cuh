@@ -128,6 +128,13 @@ cudaError_t launchArea2(const uint8_t *src, uint8_t *dst, long long srcPitch, lo
 
 // Linear up-sampling by K = 2 or 3 on X (any Linear ratio on Y): streaming kernel.  Needs SW % 4 == 0 and
 // 4-byte aligned source / destination rows; DH <= 65535, nFrames <= 65535.
+// Area reductions at 3:2, 4:3, 2:1, 5:2, 3:1, 4:1 on X (streaming, no shared memory)
+bool areaDownHasKernel(int RS, int RD, int NX);
+int areaDownItemColumns(int RS, int RD);
+cudaError_t launchAreaDown(int RS, int RD, int NX, int NXeff, const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch,
+                           long long srcFrameStride, long long dstFrameStride, int SW, int SH, int DW, int DH, int nFrames, int NY,
+                           const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const int32_t *cx,
+                           cudaStream_t stream);
 cudaError_t launchLinearUp(int RS, int RD, const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch,
                            long long srcFrameStride, long long dstFrameStride, int SW, int SH, int DW, int DH, int nFrames,
                            const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const int q1X[8],

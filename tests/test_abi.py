@@ -123,7 +123,8 @@ def test_kernel_family_of_the_baseline_configs():
         ((L, 3, 1920, 1080, 960, 540, 1), "half_sym"),           # cfg4
         ((L, 4, 32768, 32768, 12000, 12000, 1), "lanczos_stream"),  # cfg5
         ((L, 3, 1000, 700, 333, 500, 1), "lanczos_stream"),      # arbitrary Lanczos ratio
-        ((A, 0, 1920, 1080, 1280, 720, 1), "packed"),            # Area at 3:2
+        ((A, 0, 1920, 1080, 1280, 720, 1), "area_down"),         # Area at 3:2
+        ((A, 0, 1000, 700, 700, 400, 1), "packed"),              # Area at 10:7
         ((L, 3, 1920, 1080, 960, 720, 1), "ratio_stream"),       # 2:1 on X only
     ]
     for args, name in expect:

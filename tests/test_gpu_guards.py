@@ -27,7 +27,8 @@ FAMILIES = [
     (LANCZOS, 4, 1, 1024, 512, 375, 188, iqo.PATH_NO_STREAM, "packed"),
     (LANCZOS, 3, 1, 333, 222, 200, 150, iqo.PATH_GENERIC, "generic"),
     (AREA, 0, 1, 960, 540, 480, 270, iqo.PATH_AUTO, "area2"),
-    (AREA, 0, 1, 960, 540, 640, 360, iqo.PATH_AUTO, "packed"),
+    (AREA, 0, 1, 960, 540, 640, 360, iqo.PATH_AUTO, "area_down"),
+    (AREA, 0, 1, 960, 540, 600, 360, iqo.PATH_AUTO, "packed"),
     (LINEAR, 0, 1, 320, 180, 960, 540, iqo.PATH_AUTO, "linear_up3"),
     (LINEAR, 0, 1, 320, 180, 480, 270, iqo.PATH_AUTO, "linear_up_2_3"),
     (LINEAR, 0, 1, 320, 180, 700, 400, iqo.PATH_AUTO, "packed"),

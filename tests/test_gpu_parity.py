@@ -561,6 +561,37 @@ def test_linear_integer_upsampling_kernel(case):
         assert bad.size == 0, (len(bad), bad[:6].tolist())
 
 
+@pytest.mark.parametrize("case", [(1920, 1080, 1280, 720, "area_down"),      # 3:2 both axes
+                                  (96, 60, 64, 40, "area_down"), (12, 9, 8, 6, "area_down"),
+                                  (1920, 1080, 1440, 810, "area_down"),      # 4:3
+                                  (64, 48, 48, 17, "area_down"),             # 4:3 on X, arbitrary Y
+                                  (1920, 1080, 960, 720, "area_down"),       # 2:1 on X, 3:2 on Y
+                                  (3840, 2160, 1536, 864, "area_down"),      # 5:2
+                                  (40, 30, 16, 12, "area_down"),
+                                  (3840, 2160, 1280, 720, "area_down"),      # 3:1
+                                  (36, 21, 12, 50, "area_down"),             # 3:1 on X, up-sampling on Y
+                                  (3840, 2160, 960, 540, "area_down"),       # 4:1
+                                  (32, 20, 8, 5, "area_down"),
+                                  (90, 60, 60, 40, "area_mma|packed"),       # 90 is not a multiple of 12: other kernels
+                                  (1000, 700, 700, 400, "area_mma|packed")]) # 10:7
+def test_area_reduction_kernel(case):
+    sw, sh, dw, dh, kname = case
+    for seed, fill in ((43, None), (0, 255), (0, 0)):
+        src = lcg_image(sh, sw, seed=seed) if fill is None else np.full((sh, sw), fill, np.uint8)
+        rc, want = oracle_resize(AREA, src, dw, dh)
+        assert rc == 0
+        got, kernel = gpu_resize(AREA, src, dw, dh)
+        assert kernel in kname.split("|"), kernel
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, (len(bad), bad[:6].tolist())
+    # padded rows on both sides
+    src = lcg_image(sh, sw + 8, seed=44)
+    rc, want = oracle_resize(AREA, src, dw, dh, sw=sw, dst_stride=dw + 4)
+    got, kernel = gpu_resize(AREA, src, dw, dh, sw=sw, dst_stride=dw + 4)
+    assert kernel in kname.split("|"), kernel
+    assert np.array_equal(got, want)
+
+
 def test_resize_is_ordered_after_the_producer_of_a_device_source():
     """iqo_cuda_resize with device pointers runs on the legacy default stream: a source that torch is still
     producing on its (default) current stream must be complete before the kernel reads it (the call

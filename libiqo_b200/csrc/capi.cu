@@ -318,13 +318,19 @@ bool isDevicePointer(const void *p)
     return attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
 }
 
-// Linear up-sampling ratios the streaming kernel is instantiated for (items of 4 rS source columns)
+static int64_t floorDivI64(int64_t a, int64_t b) { return a >= 0 ? a / b : -((-a + b - 1) / b); }
+// Linear ratios the streaming kernel is instantiated for (items of 4 rS source columns)
 bool linearUpRatio(const AxisPlan &X)
 {
     if (X.identity || X.N != 2) return false;
     const bool known = (X.rS == 1 && (X.rD == 2 || X.rD == 3 || X.rD == 4)) || (X.rS == 2 && (X.rD == 3 || X.rD == 5)) ||
-                       (X.rS == 3 && X.rD == 4) || (X.rS == 4 && X.rD == 5);
-    return known && X.S % (4 * X.rS) == 0;
+                       (X.rS == 3 && (X.rD == 4 || X.rD == 2)) || (X.rS == 4 && (X.rD == 5 || X.rD == 3));
+    if (!known || X.S % (4 * X.rS) != 0) return false;
+    // the kernel's compile-time first tap floor(((2 d + 1) S - D) / (2 D)) must be the planner's (it is for these ratios;
+    // from 2:1 on the reference's iterator starts elsewhere): checked on the first items
+    for (int64_t d = 1; d < std::min<int64_t>(X.D - 1, 64); ++d)
+        if (X.first[size_t(d)] != floorDivI64((2 * d + 1) * X.S - X.D, 2 * X.D)) return false;
+    return true;
 }
 // Area reductions the streaming kernel is instantiated for; *nxEff = taps up to the last one that is non-zero in some phase
 bool areaDownRatio(const AxisPlan &X, int *nxEff)
@@ -341,8 +347,8 @@ const char *linearUpName(const AxisPlan &X)
 {
     return X.rS == 1   ? (X.rD == 2 ? "linear_up2" : X.rD == 3 ? "linear_up3" : "linear_up4")
            : X.rS == 2 ? (X.rD == 3 ? "linear_up_2_3" : "linear_up_2_5")
-           : X.rS == 3 ? "linear_up_3_4"
-                       : "linear_up_4_5";
+           : X.rS == 3 ? (X.rD == 4 ? "linear_up_3_4" : "linear_3_2")
+                       : (X.rD == 5 ? "linear_up_4_5" : "linear_4_3");
 }
 
 // AUTO gives a launch to the tensor-path kernel when it has enough warps (strip x band) to fill the device
@@ -687,7 +693,7 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
             return IQO_CUDA_OK;
         }
     }
-    // Linear up-sampling at 1:2, 1:3, 1:4, 2:3, 2:5, 3:4 or 4:5 on X (any ratio on Y): streaming kernel
+    // Linear at 1:2, 1:3, 1:4, 2:3, 2:5, 3:4, 4:5 (up-sampling), 3:2 or 4:3 on X (any ratio on Y): streaming kernel
     {
         const AxisPlan &X = r->plan.x, &Y = r->plan.y;
         if (r->path == IQO_CUDA_PATH_AUTO && r->plan.kind == kLinear && whole && linearUpRatio(X) && !Y.identity && Y.N == 2 &&

@@ -1517,7 +1517,7 @@ struct LinearUpArgs {
 #endif
 constexpr int kLinearUpRows = IQO_LINEAR_UP_ROWS;  // destination rows per item: they mostly share their two source rows
 
-// RS : RD up-sampling on X (1:2, 1:3, 1:4, 2:3, 2:5, 3:4, 4:5): an item is 4 RS source columns (RS aligned words) and the 4 RD
+// RS : RD on X (up-sampling at 1:2, 1:3, 1:4, 2:3, 2:5, 3:4, 4:5; the mild reductions 3:2 and 4:3): an item is 4 RS source columns (RS aligned words) and the 4 RD
 // destination pixels they produce, for kLinearUpRows destination rows
 template <int RS, int RD>
 __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constant__ LinearUpArgs a)
@@ -3202,6 +3202,10 @@ cudaError_t launchLinearUp(int RS, int RD, const uint8_t *src, uint8_t *dst, lon
         resizeLinearUpKernel<2, 5><<<grid, 256, 0, stream>>>(a);
     else if (RS == 4 && RD == 5)
         resizeLinearUpKernel<4, 5><<<grid, 256, 0, stream>>>(a);
+    else if (RS == 3 && RD == 2)   // mild reductions share the item geometry and the first-tap formula
+        resizeLinearUpKernel<3, 2><<<grid, 256, 0, stream>>>(a);
+    else if (RS == 4 && RD == 3)
+        resizeLinearUpKernel<4, 3><<<grid, 256, 0, stream>>>(a);
     else
         return cudaErrorInvalidValue;
     g_launches.fetch_add(1);

@@ -549,6 +549,10 @@ def test_more_than_65535_frames_in_one_call(kind, deg, sw, sh, dw, dh):
                                   (64, 36, 256, 144, "linear_up4"), (4, 4, 16, 9, "linear_up4"),
                                   (768, 432, 1920, 1080, "linear_up_2_5"), (8, 6, 20, 15, "linear_up_2_5"),
                                   (1536, 864, 1920, 1080, "linear_up_4_5"), (16, 9, 20, 11, "linear_up_4_5"),
+                                  # mild reductions on X with the same item geometry
+                                  (1920, 1080, 1280, 720, "linear_3_2"), (12, 9, 8, 6, "linear_3_2"), (96, 50, 64, 77, "linear_3_2"),
+                                  (1920, 1080, 1440, 810, "linear_4_3"), (16, 12, 12, 9, "linear_4_3"),
+                                  (1920, 1080, 960, 540, "linear_mma|packed"),   # from 2:1 on: other kernels
                                   (60, 36, 90, 54, "linear_mma|packed")])     # 60 is not a multiple of 8: other kernels
 def test_linear_integer_upsampling_kernel(case):
     sw, sh, dw, dh, kname = case

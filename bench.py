@@ -179,13 +179,19 @@ def time_cpu(work, steps, warmup, seconds=60.0, max_frames=256):
     reps = -(-frames // probe)
     src = np.concatenate([src] * reps)[:frames].copy()
     dst = np.zeros((frames, dh, dw), dtype=np.uint8)
-    for _ in range(warmup):
-        run(frames, src, dst)
-    times = []
-    for _ in range(steps):
-        t = time.perf_counter()
-        run(frames, src, dst)
-        times.append(time.perf_counter() - t)
+    # two passes of warm-up + K timed steps, the faster pass counts: the GPU boxes share their host with other
+    # tenants, and a burst of foreign load during one pass used to make the two arms of this file disagree by 35 %
+    times = None
+    for _pass in range(2):
+        for _ in range(warmup):
+            run(frames, src, dst)
+        cur = []
+        for _ in range(steps):
+            t = time.perf_counter()
+            run(frames, src, dst)
+            cur.append(time.perf_counter() - t)
+        if times is None or sum(cur) < sum(times):
+            times = cur
     # one image per call, the way the reference's own benchmark loops (benchmark/benchmark.cpp:1017-1033)
     one_s, one_d = src[:1].copy(), dst[:1].copy()
     for _ in range(5):
@@ -198,7 +204,7 @@ def time_cpu(work, steps, warmup, seconds=60.0, max_frames=256):
     close()
     mean = sum(times) / len(times)
     return dict(value=round(frames * dw * dh / mean / 1e6, 1), unit=UNIT, cores=used, kind=label,
-                sample="%d frames/step x %d steps (+%d warm-up) of %dx%d->%dx%d, host memory, %s"
+                sample="%d frames/step x %d steps (+%d warm-up), faster of two passes, of %dx%d->%dx%d, host memory, %s"
                        % (frames, steps, warmup, sw, sh, dw, dh,
                           "reference public API, CPUID dispatch + OpenMP (oracle/_ref)" if label == "reference"
                           else "scalar oracle port (oracle/iqo_oracle.c)"),

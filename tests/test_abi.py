@@ -126,6 +126,15 @@ def test_kernel_family_of_the_baseline_configs():
         ((A, 0, 1920, 1080, 1280, 720, 1), "area_down"),         # Area at 3:2
         ((A, 0, 1000, 700, 700, 400, 1), "packed"),              # Area at 10:7
         ((L, 3, 1920, 1080, 960, 720, 1), "ratio_stream"),       # 2:1 on X only
+        ((A, 0, 3840, 2160, 1280, 720, 1), "area_down"),         # Area at 3:1
+        ((A, 0, 1920, 1080, 1280, 540, 1), "area_down"),         # Area at 3:2 on X, 2:1 on Y
+        ((A, 0, 1910, 1080, 955, 720, 1), "packed"),             # Area 2:1 on X, width not a multiple of 8
+        ((Li, 0, 1280, 720, 1920, 1080, 1), "linear_up_2_3"),    # Linear at 2:3
+        ((Li, 0, 1440, 810, 1920, 1080, 1), "linear_up_3_4"),
+        ((Li, 0, 1920, 1080, 1280, 720, 1), "linear_3_2"),       # mild reductions share the Linear kernel
+        ((Li, 0, 1920, 1080, 1440, 810, 1), "linear_4_3"),
+        ((Li, 0, 1920, 1080, 960, 540, 1), "packed"),            # from 2:1 on the reference's iterator starts elsewhere
+        ((Li, 0, 1284, 720, 1926, 1080, 1), "packed"),           # 2:3, width not a multiple of 8
     ]
     for args, name in expect:
         assert iqo.plan_kernel(*args)[0] == name, args

@@ -480,6 +480,17 @@ def run_cfg5(torch, iqo, dist, rank, world, local, dev):
         ms_kernel = one_pass(True)
         ms_e2e = (time.perf_counter() - t0) * 1e3
         kernel = r.last_kernel()
+        one_launch = None
+        if world == 1 and lo == 0 and hi == sh:
+            # the same image as ONE launch (what a single-GPU caller would do): warm launches back to back
+            del dsrc
+            whole = torch.empty((sh, sw), dtype=torch.uint8, device=dev)
+            whole.copy_(host, non_blocking=True)
+            out1 = torch.empty((dh, dw), dtype=torch.uint8, device=dev)
+            ms1 = time_launches(torch, lambda: r.resize_band(0, dh, 0, sh, sw, whole, dw, out1, stream), 2, 5)
+            one_launch = {"ms_kernel": round(ms1, 3), "gpix_s_kernel": round(dw * dh / ms1 / 1e6, 1), "kernel": r.last_kernel(),
+                          "equal_to_bands": bool(torch.equal(out1, out_dev)), "timing": "mean of 5 back-to-back launches after 2 warm-up"}
+            del whole, out1
     t = torch.tensor([ms_kernel, ms_e2e, float(uploaded)], dtype=torch.float64, device=dev)
     tsum = t.clone()
     if dist is not None:
@@ -500,6 +511,7 @@ def run_cfg5(torch, iqo, dist, rank, world, local, dev):
     d2h_ok = bool(torch.equal(out_host, out_dev.cpu()))
     return {"workload": "cfg5 32768x32768 -> 12000x12000 Lanczos4, row bands + host-side halo", "n_gpus": world,
             "bands_per_gpu": nb, "kernel": kernel, "ms_kernel": round(float(t[0]), 3), "ms_e2e": round(float(t[1]), 3),
+            "one_launch": one_launch,
             "timing": "max over ranks; ms_kernel = sum of the rank's band launches (CUDA events), ms_e2e = wall clock of "
                       "upload (pinned host -> device) + kernels + download of the rank's bands",
             "gpix_s_kernel": round(dw * dh / float(t[0]) / 1e6, 1), "gpix_s_e2e": round(dw * dh / float(t[1]) / 1e6, 1),

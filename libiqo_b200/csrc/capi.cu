@@ -476,6 +476,25 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
                     if (f0 != 0) return fail(IQO_CUDA_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", int(cr));
                     break;
                 }
+                // reductions of the RD | 8 family whose 3:2-kernel pattern exists (cfg1): tensor-path vertical pass, the
+                // compile-time dp2a horizontal pass of the 3:2 kernel (IQO_CUDA_MMA_DP2A=0: the all-mma kernel)
+                static const int envMmaDp2a = [] { const char *e = getenv("IQO_CUDA_MMA_DP2A"); return e ? atoi(e) : 1; }();
+                const RatioPlan &rp = sp.ratio;
+                if (envMmaDp2a && r->plan.kind == kLanczos && rp.eligible && mmaRatioHasKernel(rp.RS, rp.RD, rp.NX, rp.odd) &&
+                    (rp.c0 & 1) == 0 && q.DW % 8 == 0 && rp.RD <= 4) {
+                    RatioArgs ra;
+                    memset(&ra, 0, sizeof ra);
+                    ra.RS = rp.RS, ra.RD = rp.RD, ra.NX = rp.NX, ra.odd = rp.odd;
+                    ra.tailZeros = rp.tailZeros;
+                    ra.c0 = rp.c0;
+                    for (int ph = 0; ph < rp.RD && ph < 4; ++ph)
+                        for (int par = 0; par < 2; ++par)
+                            for (int j = 0; j < 7; ++j) ra.cwX[ph][par][j] = rp.cwX[(size_t(ph) * 2 + par) * 7 + j];
+                    ra.gx = a.x;
+                    r->lastKernel = "lanczos_mma_dp2a";
+                    CUDA_TRY(launchMmaRatio(q, tmap, ra, stream));
+                    continue;
+                }
                 r->lastKernel = r->plan.kind == kLanczos ? "lanczos_mma" : r->plan.kind == kArea ? "area_mma" : "linear_mma";
                 CUDA_TRY(launchMma(q, tmap, stream));
             }

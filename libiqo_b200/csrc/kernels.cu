@@ -2790,6 +2790,266 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
     }
 }
 
+
+// ---------------------------------------------------------------------------------------
+// Tensor-path vertical pass + compile-time dp2a horizontal pass, for the reductions of the RD | 8 family (cfg1: 3:2).
+// Geometry, source FIFO (TMA chunks, mbarrier groups) and vertical pass are resizeLanczosMmaKernel's; the horizontal
+// pass is resizeRatioStreamKernel's: an item is (row of the 16-row W tile, group of 8 destination pixels), the pair
+// words of the group's window come from the W row with 8-byte loads, the coefficient words of each (phase, parity) are
+// constant-bank operands, and the 8 pixels leave as one 8-byte store straight from registers -- no output tile, no
+// store phase, no horizontal tables in shared memory.  Border columns (first / last strip) are recomputed from the
+// W rows with the generic tables.  Needs: first tap of every group on an even W element (c0 even), DW % 8 == 0.
+// ---------------------------------------------------------------------------------------
+struct MmaRatioKernelArgs {
+    alignas(64) CUtensorMap tmap;
+    MmaArgs a;
+    uint32_t cwX[4][2][7];     // [phase][parity][pair word] (RatioArgs)
+    int accInit;               // 2^19 - workBias * sum of the low plane ... (start of the low-plane sum)
+    int c0;                    // first tap of destination pixel 0
+    int dstVec8;               // destination rows may be written with 8-byte stores
+    AxisDev gx;                // generic horizontal tables: border columns
+};
+
+template <int VKS, int RS, int RD, int NX, int TZ>
+__global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaRatioKernel(const __grid_constant__ MmaRatioKernelArgs prm)
+{
+    extern __shared__ __align__(128) uint8_t mmaSmem[];
+    constexpr bool SIGNED = true;
+    constexpr int GS = 8 * RS / RD;
+    const MmaArgs &a = prm.a;
+    const int lane = threadIdx.x & 31, g = lane >> 2;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), nw = blockDim.x >> 5;
+    const int wv = nw - 1 - warp;
+    const int strip = blockIdx.x;
+    const int T0 = strip * a.stripTiles;
+    const int tx0 = 8 * T0;
+    const int ngs = min(a.stripTiles, (a.DW >> 3) - T0);       // 8-pixel groups of this strip
+    const int xs = __ldg(a.stripXs + strip);                    // source column of W element 0
+    const int rowBytes = a.wcols;
+    const int chunkBytes = kMmaChunk * rowBytes;
+    const int wStride = mmaWStride(a.wcols);
+    const uint32_t fifoBase = smemAddr(mmaSmem);
+    const uint32_t wBase = fifoBase + a.nChunks * chunkBytes;
+    const uint32_t mbarBase = wBase + 16 * wStride;
+    uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
+    const int nseg = a.wcols >> 4;
+    const int i0 = GS * T0 + prm.c0 - xs;                       // W element of the first tap of pixel tx0 (even)
+
+    const int blkFirst = (a.dstRow0 >> 4) + blockIdx.y * a.bandBlocks;
+    const int blkEnd = min(blkFirst + a.bandBlocks, (a.dstRow0 + a.dstRows + 15) >> 4);
+    if (blkFirst >= blkEnd) return;
+
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarBase));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbarBase + 8));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    int2 vb = __ldg(a.vBlock + blkFirst);   // {first source row, rows}
+    int cIssued = vb.x >> 3;
+    uint32_t slotAddr = 0, barIssue = mbarBase;
+    if (warp == 0) {
+        int sl = cIssued % a.nChunks;
+        if (sl < 0) sl += a.nChunks;
+        slotAddr = fifoBase + sl * chunkBytes;
+    }
+    const uint32_t fifoEnd = wBase;
+    int grpWaited = 0;
+    auto issueUpTo = [&](const int cHi) {
+        if (warp == 0) {
+            const int nNew = cHi + 1 - cIssued;
+            if (lane == 0) {
+                if (nNew > 0)
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(barIssue), "r"(nNew * chunkBytes) : "memory");
+                else
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(barIssue) : "memory");
+            }
+            for (; cIssued <= cHi; ++cIssued) {
+                if (lane == 0)
+                    asm volatile(
+                        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                        ::"r"(slotAddr), "l"(reinterpret_cast<unsigned long long>(&prm)), "r"(xs >> 1),
+                          "r"(kMmaChunk * cIssued - a.srcRow0), "r"((int)blockIdx.z), "r"(barIssue)
+                        : "memory");
+                slotAddr += chunkBytes;
+                if (slotAddr == fifoEnd) slotAddr = fifoBase;
+            }
+            barIssue ^= 8u;
+        }
+    };
+    auto waitGroup = [&]() {
+        asm volatile(
+            "{\n\t.reg .pred q;\n\tIQO_MMAR_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n\t@!q bra IQO_MMAR_WAIT;\n\t}"
+            ::"r"(mbarBase + 8 * (grpWaited & 1)), "r"((grpWaited >> 1) & 1)
+            : "memory");
+        ++grpWaited;
+    };
+    issueUpTo((vb.x + vb.y - 1) >> 3);
+
+    const int mi = lane >> 3, ri = lane & 7;
+    const uint32_t wSt = wBase + ((mi & 1) * 8 + ri) * wStride + (mi >> 1) * 16;
+    const int bias = a.workBias;
+    const uint32_t rcp = (65536u + ngs - 1) / ngs;   // item / ngs for item < 16 * 34
+    const bool left = tx0 < a.mbX, right = tx0 + 8 * ngs > a.meX;
+
+    uint4 af[VKS];
+    int rmap[VKS];
+#pragma unroll
+    for (int s = 0; s < VKS; ++s) {
+        af[s] = __ldg(a.vFrag + ((size_t)blkFirst * VKS + s) * 32 + lane);
+        rmap[s] = __ldg(a.vRowMap + ((size_t)blkFirst * VKS + s) * 32 + lane);
+    }
+
+    for (int b = blkFirst; b < blkEnd; ++b) {
+        if (b + 1 < blkEnd) vb = __ldg(a.vBlock + b + 1);
+        waitGroup();
+
+        // ---------------- vertical pass (as in resizeLanczosMmaKernel) ----------------
+        uint32_t ra[VKS];
+#pragma unroll
+        for (int s = 0; s < VKS; ++s) ra[s] = fifoBase + (uint32_t)rmap[s];
+        const bool borderBlock = (16 * b < a.mbY) || (16 * b + 16 > a.meY);
+        int denoLo = 0, denoHi = 0;
+        uint32_t magicLo = 0, magicHi = 0;
+        if (borderBlock) {
+            const int2 v0 = __ldg(a.vRow + 16 * b + g), v1 = __ldg(a.vRow + 16 * b + g + 8);
+            denoLo = v0.x, magicLo = (uint32_t)v0.y, denoHi = v1.x, magicHi = (uint32_t)v1.y;
+        }
+        const uint32_t biasPair = (uint32_t)bias | ((uint32_t)bias << 16);
+        const uint32_t biasLo = denoLo ? 0u : biasPair, biasHi = denoHi ? 0u : biasPair;
+        auto loadSeg = [&](uint32_t (&bf)[VKS][4], const int seg) {
+#pragma unroll
+            for (int s = 0; s < VKS; ++s)
+                asm volatile("ldmatrix.sync.aligned.m16n16.x2.trans.shared.b8 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(bf[s][0]), "=r"(bf[s][1]), "=r"(bf[s][2]), "=r"(bf[s][3]) : "r"(ra[s] + 16 * seg));
+        };
+        auto computeSeg = [&](const uint32_t (&bf)[VKS][4], const int seg) {
+            int dA[4], dB[4];
+#pragma unroll
+            for (int s = 0; s < VKS; ++s) {
+                mmaCoefU8k16<SIGNED>(dA, af[s].x, af[s].y, bf[s][0], s == 0);
+                mmaCoefU8k16<SIGNED>(dB, af[s].x, af[s].y, bf[s][1], s == 0);
+                mmaCoefU8k16<SIGNED>(dA, af[s].z, af[s].w, bf[s][2], false);
+                mmaCoefU8k16<SIGNED>(dB, af[s].z, af[s].w, bf[s][3], false);
+            }
+            if (borderBlock) {
+                auto bdiv = [&](int x, int deno, uint32_t magic) -> int {
+                    if (!deno) return x;
+                    const int n = (int)(short)x * 64;
+                    const uint32_t mm = (uint32_t)abs(n);
+                    const int q = magic ? (int)__umulhi(mm, magic) : (int)mm;
+                    return (int)(short)(n < 0 ? -q : q) + bias;
+                };
+                dA[0] = bdiv(dA[0], denoLo, magicLo), dA[1] = bdiv(dA[1], denoLo, magicLo);
+                dB[0] = bdiv(dB[0], denoLo, magicLo), dB[1] = bdiv(dB[1], denoLo, magicLo);
+                dA[2] = bdiv(dA[2], denoHi, magicHi), dA[3] = bdiv(dA[3], denoHi, magicHi);
+                dB[2] = bdiv(dB[2], denoHi, magicHi), dB[3] = bdiv(dB[3], denoHi, magicHi);
+            }
+            const uint32_t w0 = addU16x2(prmt((uint32_t)dA[0], (uint32_t)dA[1], 0x5410), biasLo), w1 = addU16x2(prmt((uint32_t)dA[2], (uint32_t)dA[3], 0x5410), biasHi);
+            const uint32_t w2 = addU16x2(prmt((uint32_t)dB[0], (uint32_t)dB[1], 0x5410), biasLo), w3 = addU16x2(prmt((uint32_t)dB[2], (uint32_t)dB[3], 0x5410), biasHi);
+            asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};" ::"r"(wSt + 32 * seg), "r"(w0), "r"(w1), "r"(w2), "r"(w3) : "memory");
+        };
+        if (wv < nseg) {
+            uint32_t bf0[VKS][4], bf1[VKS][4];
+            loadSeg(bf0, wv);
+            int seg = wv;
+            for (; seg + nw < nseg; seg += 2 * nw) {
+                loadSeg(bf1, seg + nw);
+                computeSeg(bf0, seg);
+                if (seg + 2 * nw < nseg) loadSeg(bf0, seg + 2 * nw);
+                computeSeg(bf1, seg + nw);
+            }
+            if (seg < nseg) computeSeg(bf0, seg);
+        }
+        __syncthreads();   // W is complete; the source rows of this block are free
+        if (b + 1 < blkEnd) {
+            issueUpTo((vb.x + vb.y - 1) >> 3);
+#pragma unroll
+            for (int s = 0; s < VKS; ++s) {
+                af[s] = __ldg(a.vFrag + ((size_t)(b + 1) * VKS + s) * 32 + lane);
+                rmap[s] = __ldg(a.vRowMap + ((size_t)(b + 1) * VKS + s) * 32 + lane);
+            }
+        }
+
+        // ---------------- horizontal pass: (row, group of 8 pixels) items, compile-time tap pattern ----------------
+        const int yb = 16 * b;
+        const int rLo = max(a.dstRow0 - yb, 0), rHi = min(a.dstRow0 + a.dstRows - yb, 16);   // rows of the block inside the launch
+        for (int item = threadIdx.x; item < 16 * ngs; item += blockDim.x) {
+            const int r = (int)(((uint32_t)item * rcp) >> 16);
+            const int q = item - r * ngs;
+            if (r < rLo || r >= rHi) continue;
+            const uint32_t wl = wBase + r * wStride + 2 * (i0 + GS * q);
+            constexpr int NXE = NX - TZ;  // taps left after the zero taps that end every phase
+            constexpr int kWords = (((7 * RS / RD) >> 1) + (NXE + 2) / 2 + 1) & ~1;  // pair words the 8 pixels span (even count)
+            uint32_t n[kWords];
+            if ((wl & 7) == 0) {
+#pragma unroll
+                for (int j = 0; j < kWords; j += 2)
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(n[j]), "=r"(n[j + 1]) : "r"(wl + 4 * j) : "memory");
+            } else {
+#pragma unroll
+                for (int j = 0; j < kWords; ++j) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(n[j]) : "r"(wl + 4 * j) : "memory");
+            }
+            int px[8];
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                const int off = (p * RS) / RD;
+                const int wp = off >> 1, par = off & 1, ph = p % RD;
+                const int nwd = (NXE + par + 1) / 2;
+                int acc = prm.accInit;
+#pragma unroll
+                for (int j = 0; j < nwd; ++j) acc = dp2a_lo_uu(n[wp + j], prm.cwX[ph][par][j], acc);
+                acc >>= 8;
+#pragma unroll
+                for (int j = 0; j < nwd; ++j) acc = dp2a_hi_us(n[wp + j], prm.cwX[ph][par][j], acc);
+                px[p] = acc >> 12;
+            }
+            uint2 o2;
+            o2.x = packSatU8(px[1], px[0], packSatU8(px[3], px[2], 0u));
+            o2.y = packSatU8(px[5], px[4], packSatU8(px[7], px[6], 0u));
+            uint8_t *out = dst + (long long)(yb + r - a.dstRow0) * a.dstPitch + tx0 + 8 * q;
+            if (prm.dstVec8)
+                *reinterpret_cast<uint2 *>(out) = o2;
+            else
+                halfStoreBytes(out, o2, 0, 8);
+        }
+        if (left || right) {
+            __syncthreads();  // the main stores of these pixels come first
+            const int c0b = left ? tx0 : max(a.meX, tx0);
+            const int c1b = left ? min(a.mbX, tx0 + 8 * ngs) : tx0 + 8 * ngs;
+            for (int side = 0; side < 2; ++side) {
+                int b0 = c0b, b1 = c1b;
+                if (side == 1) {
+                    if (!(left && right)) break;
+                    b0 = max(a.meX, max(tx0, a.mbX));
+                    b1 = tx0 + 8 * ngs;
+                }
+                const int nb = b1 - b0;
+                for (int item = threadIdx.x; item < 16 * nb; item += blockDim.x) {
+                    // resizeXborder from the W row: masked taps, truncating division (finishPixel)
+                    const int r = item / nb, d = b0 + item - r * nb;
+                    if (r < rLo || r >= rHi) continue;
+                    const int fx = __ldg(prm.gx.first + d), rx = __ldg(prm.gx.row + d);
+                    const int32_t *cx = prm.gx.coef + rx * NX;
+                    const uint32_t wr = wBase + r * wStride + 2 * (fx - xs);
+                    int nume = 0;
+#pragma unroll
+                    for (int i = 0; i < NX; ++i) {
+                        const int cxi = __ldg(cx + i);
+                        if (cxi == 0) continue;   // masked taps may lie outside the W row
+                        uint32_t w16;
+                        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(w16) : "r"(wr + 2 * i) : "memory");
+                        nume += ((int)w16 - bias) * cxi;
+                    }
+                    dst[(long long)(yb + r - a.dstRow0) * a.dstPitch + d] = finishPixel(nume, __ldg(prm.gx.deno + rx), 20);
+                }
+            }
+        }
+        __syncthreads();   // the next vertical pass may overwrite W
+    }
+}
+
 }  // namespace
 
 size_t mmaSmemBytes(int wcols, int stripTiles, int nChunks, int hKMax)
@@ -2831,6 +3091,57 @@ cudaError_t launchMma(const MmaArgs &a, const CUtensorMap &tmap, cudaStream_t st
     IQO_MMA_CASE(2, 1) IQO_MMA_CASE(2, 2) IQO_MMA_CASE(2, 3)
     IQO_MMA_CASE(3, 1) IQO_MMA_CASE(3, 2) IQO_MMA_CASE(3, 3)
 #undef IQO_MMA_CASE
+    return cudaErrorInvalidValue;
+}
+
+size_t mmaRatioSmemBytes(int wcols, int nChunks)
+{
+    return size_t(nChunks) * kMmaChunk * wcols + 16 * size_t(mmaWStride(wcols)) + 16;
+}
+
+bool mmaRatioHasKernel(int RS, int RD, int NX, int odd)
+{
+    return odd == 0 && RS == 3 && RD == 2 && NX == 10;
+}
+
+template <int VKS, int RS, int RD, int NX, int TZ>
+cudaError_t launchMmaRatioT(const MmaRatioKernelArgs &p, dim3 grid, size_t smem, cudaStream_t stream)
+{
+    static PerDeviceOnce attrSet;
+    const int dev = currentDevice();
+    if (!attrSet.done(dev)) {
+        cudaError_t e = cudaFuncSetAttribute(resizeLanczosMmaRatioKernel<VKS, RS, RD, NX, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attrSet.set(dev);
+    }
+    resizeLanczosMmaRatioKernel<VKS, RS, RD, NX, TZ><<<grid, 32 * p.a.warps, smem, stream>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launchMmaRatio(const MmaArgs &a, const CUtensorMap &tmap, const RatioArgs &ra, cudaStream_t stream)
+{
+    if (!mmaRatioHasKernel(ra.RS, ra.RD, ra.NX, ra.odd) || !a.isSigned || (a.DW & 7)) return cudaErrorInvalidValue;
+    const int tiles = a.DW / 8;
+    const int strips = (tiles + a.stripTiles - 1) / a.stripTiles;
+    const int blocks = ((a.dstRow0 + a.dstRows + 15) >> 4) - (a.dstRow0 >> 4);
+    const int bands = (blocks + a.bandBlocks - 1) / a.bandBlocks;
+    if (bands > 65535 || a.nFrames > 65535) return cudaErrorInvalidConfiguration;
+    const size_t smem = mmaRatioSmemBytes(a.wcols, a.nChunks);
+    MmaRatioKernelArgs p;
+    p.tmap = tmap;
+    p.a = a;
+    memcpy(p.cwX, ra.cwX, sizeof p.cwX);
+    // the low-plane sum starts at 2^19 minus the bias share of the whole sum: RatioPlan's accInit is stated for its own
+    // bias, the same formula with this plan's bias (the horizontal weights of a main column sum to 16384)
+    p.accInit = (1 << 19) - a.workBias * 16384;
+    p.c0 = ra.c0;
+    p.dstVec8 = a.dstVec >= 1;
+    p.gx = ra.gx;
+    dim3 grid(strips, bands, a.nFrames);
+    g_launches.fetch_add(1);
+    if (a.vKMax == 1) return ra.tailZeros ? launchMmaRatioT<1, 3, 2, 10, 1>(p, grid, smem, stream) : launchMmaRatioT<1, 3, 2, 10, 0>(p, grid, smem, stream);
+    if (a.vKMax == 2) return ra.tailZeros ? launchMmaRatioT<2, 3, 2, 10, 1>(p, grid, smem, stream) : launchMmaRatioT<2, 3, 2, 10, 0>(p, grid, smem, stream);
+    if (a.vKMax == 3) return ra.tailZeros ? launchMmaRatioT<3, 3, 2, 10, 1>(p, grid, smem, stream) : launchMmaRatioT<3, 3, 2, 10, 0>(p, grid, smem, stream);
     return cudaErrorInvalidValue;
 }
 

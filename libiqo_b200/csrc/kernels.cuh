@@ -226,8 +226,12 @@ struct MmaArgs {
     const int2 *hCol;
     int nFrames;
 };
+size_t mmaRatioSmemBytes(int wcols, int nChunks);
+bool mmaRatioHasKernel(int RS, int RD, int NX, int odd);
 size_t mmaSmemBytes(int wcols, int stripTiles, int nChunks, int hKMax);
 cudaError_t launchMma(const MmaArgs &a, const CUtensorMap &tmap, cudaStream_t stream);
+// tensor-path vertical pass + the 3:2 kernel's compile-time dp2a horizontal pass (cfg1)
+cudaError_t launchMmaRatio(const MmaArgs &a, const CUtensorMap &tmap, const RatioArgs &ra, cudaStream_t stream);
 
 // Float ("SIMD-semantics") mode, plan.hpp FloatPlan: the generic tile organisation with float tables and a float work tile.
 struct FloatArgs {

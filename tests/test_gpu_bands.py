@@ -98,7 +98,7 @@ def test_gigapixel_full_size_hash():
             ddst = torch.zeros((rows, dw), dtype=torch.uint8, device="cuda")
             r.resize_band(y0, rows, s0, sn, sw, dsrc, dw, ddst, torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
-            assert r.last_kernel() in ("lanczos_mma", "lanczos_stream")   # big launches: the tensor-path kernel
+            assert r.last_kernel() in ("lanczos_mma", "lanczos_mma_dp2a", "lanczos_stream")   # big launches: the tensor-path kernel
             out[y0:y0 + rows] = ddst.cpu().numpy()
             del dsrc, ddst
     assert out[0, :4].tolist() == [125, 123, 132, 113]

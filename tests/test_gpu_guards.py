@@ -22,7 +22,7 @@ FAMILIES = [
     (LANCZOS, 3, 1, 960, 540, 640, 360, iqo.PATH_STREAM, "ratio_stream"),
     (LANCZOS, 4, 1, 1024, 512, 375, 188, iqo.PATH_STREAM, "lanczos_stream"),
     (LANCZOS, 4, 1, 1024, 512, 375, 188, iqo.PATH_MMA, "lanczos_mma"),
-    (LANCZOS, 3, 1, 960, 540, 640, 360, iqo.PATH_MMA, "lanczos_mma"),
+    (LANCZOS, 3, 1, 960, 540, 640, 360, iqo.PATH_MMA, "lanczos_mma_dp2a"),
     (LANCZOS, 3, 1, 960, 540, 480, 270, iqo.PATH_MMA, "lanczos_mma"),
     (LANCZOS, 4, 1, 1024, 512, 375, 188, iqo.PATH_NO_STREAM, "packed"),
     (LANCZOS, 3, 1, 333, 222, 200, 150, iqo.PATH_GENERIC, "generic"),

@@ -57,7 +57,7 @@ def test_mma_kernel_matches_oracle(case):
     rc, want = oracle_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
     assert rc == 0
     got, kernel = mma_resize(src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
-    assert kernel == "lanczos_mma", kernel
+    assert kernel in ("lanczos_mma", "lanczos_mma_dp2a"), kernel
     bad = np.argwhere(got != want)
     assert bad.size == 0, (len(bad), bad[:8].tolist())
 
@@ -73,7 +73,7 @@ def test_mma_extreme_values():
             rc, want = oracle_resize(LANCZOS, src, dw, dh, deg, px)
             assert rc == 0
             got, kernel = mma_resize(src, dw, dh, deg, px)
-            assert kernel == "lanczos_mma"
+            assert kernel in ("lanczos_mma", "lanczos_mma_dp2a")
             assert np.array_equal(got, want), (name, deg, px, dw, dh)
 
 
@@ -97,7 +97,7 @@ def test_mma_random_sweep():
             continue
         got, kernel = mma_resize(src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
         assert np.array_equal(got, want), (deg, px, sw, sh, dw, dh, kernel)
-        ran += kernel == "lanczos_mma"
+        ran += kernel in ("lanczos_mma", "lanczos_mma_dp2a")
     assert ran >= 80, ran
 
 
@@ -115,7 +115,7 @@ def test_mma_bands_batches_and_device_pitches():
             ddst = torch.full((n, dw + 16), 0xA5, dtype=torch.uint8, device="cuda")
             r.resize_band(y0, n, s0, sn, sw, dsrc, dw + 16, ddst, torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
-            assert r.last_kernel() == "lanczos_mma"
+            assert r.last_kernel() in ("lanczos_mma", "lanczos_mma_dp2a")
             got = ddst.cpu().numpy()
             assert (got[:, dw:] == 0xA5).all()
             out[y0:y0 + n] = got[:, :dw]
@@ -133,7 +133,7 @@ def test_mma_bands_batches_and_device_pitches():
             r.set_path(iqo.PATH_MMA)
             r.resize_batch(n, pitch, pitch * sh, dsrc, dw, dw * dh, ddst, torch.cuda.current_stream().cuda_stream)
             torch.cuda.synchronize()
-            assert r.last_kernel() == "lanczos_mma"
+            assert r.last_kernel() in ("lanczos_mma", "lanczos_mma_dp2a")
         assert np.array_equal(ddst.cpu().numpy(), want), (deg, sw, sh, dw, dh)
     # a pitch that is not 16-byte aligned is declined (TMA needs it): another kernel takes the launch
     host = lcg_image(270, 488, seed=3)
@@ -143,8 +143,68 @@ def test_mma_bands_batches_and_device_pitches():
         r.set_path(iqo.PATH_MMA)
         r.resize_batch(1, 488, 488 * 270, dsrc, 240, 240 * 135, ddst, torch.cuda.current_stream().cuda_stream)
         torch.cuda.synchronize()
-        assert r.last_kernel() != "lanczos_mma"
+        assert not r.last_kernel().startswith("lanczos_mma")
     assert np.array_equal(ddst.cpu().numpy(), oracle_resize(LANCZOS, host, 240, 135, 3, sw=480)[1])
+
+
+DP2A_CASES = [
+    # (degree, pxScale, srcW, srcH, dstW, dstH, src pad, dst pad): Lanczos3 at 3:2 on X -- tensor-path vertical pass,
+    # the 3:2 kernel's compile-time dp2a horizontal pass
+    (3, 1, 1920, 1080, 1280, 720, 0, 0),     # cfg1
+    (3, 1, 96, 60, 64, 40, 0, 0),            # one narrow strip holding both border sides
+    (3, 1, 528, 333, 352, 222, 16, 8),       # partial last strip, padded rows
+    (3, 1, 1920, 1080, 1280, 540, 0, 0),     # 3:2 on X, 2:1 on Y
+    (3, 1, 960, 540, 640, 333, 0, 0),        # arbitrary Y ratio
+    (3, 1, 480, 270, 320, 180, 0, 4),        # destination stride not a multiple of 8: byte stores
+    (3, 1, 480, 100, 320, 250, 0, 0),        # up-sampling on Y
+    (3, 1, 3840, 64, 2560, 43, 0, 0),        # many strips, few rows
+]
+
+
+@pytest.mark.parametrize("case", DP2A_CASES)
+def test_mma_dp2a_kernel(case):
+    deg, px, sw, sh, dw, dh, spad, dpad = case
+    for seed, fill in ((61, None), (0, 255), (0, 0)):
+        src = lcg_image(sh, sw + spad, seed=seed) if fill is None else np.full((sh, sw + spad), fill, np.uint8)
+        rc, want = oracle_resize(LANCZOS, src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+        assert rc == 0
+        got, kernel = mma_resize(src, dw, dh, deg, px, sw=sw, dst_stride=dw + dpad)
+        assert kernel == "lanczos_mma_dp2a", kernel
+        bad = np.argwhere(got != want)
+        assert bad.size == 0, (len(bad), bad[:8].tolist())
+
+
+def test_mma_dp2a_bands_and_batches():
+    torch = pytest.importorskip("torch")
+    sw, sh, dw, dh = 1920, 1080, 1280, 720
+    src = lcg_image(sh, sw, seed=8)
+    rc, want = oracle_resize(LANCZOS, src, dw, dh, 3)
+    out = np.zeros((dh, dw), dtype=np.uint8)
+    with iqo.LanczosResizer(3, sw, sh, dw, dh) as r:
+        r.set_path(iqo.PATH_MMA)
+        for y0, n in [(0, 7), (7, 300), (307, 1), (308, 401), (709, 11)]:
+            s0, sn = r.band_src_rows(y0, n)
+            dsrc = torch.from_numpy(src[s0:s0 + sn].copy()).cuda()
+            ddst = torch.full((n, dw + 16), 0xA5, dtype=torch.uint8, device="cuda")
+            r.resize_band(y0, n, s0, sn, sw, dsrc, dw + 16, ddst, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert r.last_kernel() == "lanczos_mma_dp2a"
+            got = ddst.cpu().numpy()
+            assert (got[:, dw:] == 0xA5).all()
+            out[y0:y0 + n] = got[:, :dw]
+    assert np.array_equal(out, want)
+    n = 7
+    host = np.stack([lcg_image(540, 960 + 32, seed=90 + f) for f in range(n)])
+    host[2] = 255
+    wants = np.stack([oracle_resize(LANCZOS, host[f], 640, 360, 3, sw=960)[1] for f in range(n)])
+    dsrc = torch.from_numpy(host).cuda()
+    ddst = torch.zeros((n, 360, 640), dtype=torch.uint8, device="cuda")
+    with iqo.LanczosResizer(3, 960, 540, 640, 360) as r:
+        r.set_path(iqo.PATH_MMA)
+        r.resize_batch(n, 992, 992 * 540, dsrc, 640, 640 * 360, ddst, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert r.last_kernel() == "lanczos_mma_dp2a"
+    assert np.array_equal(ddst.cpu().numpy(), wants)
 
 
 def test_auto_picks_the_kernel_by_ratio_taps_and_launch_size():
@@ -152,7 +212,7 @@ def test_auto_picks_the_kernel_by_ratio_taps_and_launch_size():
     up-sampling and small launches stay on the 3:2 streaming / packed kernels (capi.cu, measured cross-overs in
     DESIGN 4.8) -- and whatever runs is bit-exact."""
     torch = pytest.importorskip("torch")
-    for deg, sw, sh, dw, dh, n, want_kernel in ((3, 960, 540, 640, 360, 96, "lanczos_mma"),
+    for deg, sw, sh, dw, dh, n, want_kernel in ((3, 960, 540, 640, 360, 96, "lanczos_mma_dp2a"),   # 3:2 with the 10-tap pattern: dp2a horizontal pass
                                                 (4, 960, 540, 640, 360, 96, "lanczos_mma"),
                                                 (3, 960, 540, 480, 360, 96, "lanczos_mma"),   # 2:1 on X, 3:2 on Y
                                                 (2, 960, 540, 640, 360, 96, "ratio_stream"),
@@ -169,7 +229,7 @@ def test_auto_picks_the_kernel_by_ratio_taps_and_launch_size():
         if want_kernel is not None:
             assert kernel == want_kernel, (deg, sw, sh, dw, dh, n, kernel)
         else:
-            assert kernel != "lanczos_mma", kernel
+            assert not kernel.startswith("lanczos_mma"), kernel
         got = ddst.cpu().numpy()
         for f in range(n):
             assert np.array_equal(got[f], want[f % host.shape[0]]), (deg, sw, sh, dw, dh, f, kernel)

@@ -1099,7 +1099,12 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
         }
     }
     static const int envMmaWcols = [] { const char *e = getenv("IQO_CUDA_MMA_WCOLS"); return e ? atoi(e) : 0; }();
-    buildMmaPlan(sp->plan, sp->mma, envMmaWcols > 0 ? envMmaWcols : IQO_MMA_WCOLS_DEFAULT);
+    // strips of 272 source columns for the all-mma kernel; the variant with the dp2a horizontal pass keeps no tables and
+    // no output tile in shared memory and is 4 % faster with 400 (measured 272 / 336 / 400 / 448 / 512: 2.22 / 2.14 / 2.14 / 2.13 / 2.76 ms on cfg1)
+    const bool dp2aVariant = sp->plan.kind == kLanczos && sp->ratio.eligible &&
+                             mmaRatioHasKernel(sp->ratio.RS, sp->ratio.RD, sp->ratio.NX, sp->ratio.odd) && (sp->ratio.c0 & 1) == 0 &&
+                             sp->plan.x.D % 8 == 0;
+    buildMmaPlan(sp->plan, sp->mma, envMmaWcols > 0 ? envMmaWcols : dp2aVariant ? 400 : IQO_MMA_WCOLS_DEFAULT);
     if (sp->mma.eligible) {
         const MmaPlan &q = sp->mma;
         if (encodeTiled() == 0 || !uploadVec(sp->mVBlock, q.vBlock) || !uploadVec(sp->mVRow, q.vRow) || !uploadVec(sp->mVRowMap, q.vRowMap) || !uploadVec(sp->mStripXs, q.stripXs) ||

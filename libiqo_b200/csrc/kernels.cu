@@ -2810,8 +2810,11 @@ struct MmaRatioKernelArgs {
     AxisDev gx;                // generic horizontal tables: border columns
 };
 
+#ifndef IQO_MMAR_MINB
+#define IQO_MMAR_MINB 4
+#endif
 template <int VKS, int RS, int RD, int NX, int TZ>
-__global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaRatioKernel(const __grid_constant__ MmaRatioKernelArgs prm)
+__global__ void __launch_bounds__(128, IQO_MMAR_MINB) resizeLanczosMmaRatioKernel(const __grid_constant__ MmaRatioKernelArgs prm)
 {
     extern __shared__ __align__(128) uint8_t mmaSmem[];
     constexpr bool SIGNED = true;

@@ -481,7 +481,7 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
                 static const int envMmaDp2a = [] { const char *e = getenv("IQO_CUDA_MMA_DP2A"); return e ? atoi(e) : 1; }();
                 const RatioPlan &rp = sp.ratio;
                 if (envMmaDp2a && r->plan.kind == kLanczos && rp.eligible && mmaRatioHasKernel(rp.RS, rp.RD, rp.NX, rp.odd) &&
-                    (rp.c0 & 1) == 0 && q.DW % 8 == 0 && rp.RD <= 4) {
+                    (rp.c0 & 1) == rp.odd && q.DW % 8 == 0 && rp.RD <= 4) {
                     RatioArgs ra;
                     memset(&ra, 0, sizeof ra);
                     ra.RS = rp.RS, ra.RD = rp.RD, ra.NX = rp.NX, ra.odd = rp.odd;
@@ -1102,7 +1102,7 @@ int buildSharedPlan(std::shared_ptr<SharedPlan> &out, int device, int kind, unsi
     // strips of 272 source columns for the all-mma kernel; the variant with the dp2a horizontal pass keeps no tables and
     // no output tile in shared memory and is 4 % faster with 400 (measured 272 / 336 / 400 / 448 / 512: 2.22 / 2.14 / 2.14 / 2.13 / 2.76 ms on cfg1)
     const bool dp2aVariant = sp->plan.kind == kLanczos && sp->ratio.eligible &&
-                             mmaRatioHasKernel(sp->ratio.RS, sp->ratio.RD, sp->ratio.NX, sp->ratio.odd) && (sp->ratio.c0 & 1) == 0 &&
+                             mmaRatioHasKernel(sp->ratio.RS, sp->ratio.RD, sp->ratio.NX, sp->ratio.odd) && (sp->ratio.c0 & 1) == sp->ratio.odd &&
                              sp->plan.x.D % 8 == 0;
     buildMmaPlan(sp->plan, sp->mma, envMmaWcols > 0 ? envMmaWcols : dp2aVariant ? 400 : IQO_MMA_WCOLS_DEFAULT);
     if (sp->mma.eligible) {

@@ -2798,7 +2798,8 @@ __global__ void __launch_bounds__(128, IQO_MMA_MINB / 2) resizeLanczosMmaKernel(
 // words of the group's window come from the W row with 8-byte loads, the coefficient words of each (phase, parity) are
 // constant-bank operands, and the 8 pixels leave as one 8-byte store straight from registers -- no output tile, no
 // store phase, no horizontal tables in shared memory.  Border columns (first / last strip) are recomputed from the
-// W rows with the generic tables.  Needs: first tap of every group on an even W element (c0 even), DW % 8 == 0.
+// W rows with the generic tables.  ODD: the first tap of a group sits on an odd W element (the pair words start one
+// element earlier and every pixel's offset grows by one).  Needs DW % 8 == 0.
 // ---------------------------------------------------------------------------------------
 struct MmaRatioKernelArgs {
     alignas(64) CUtensorMap tmap;
@@ -2813,7 +2814,20 @@ struct MmaRatioKernelArgs {
 #ifndef IQO_MMAR_MINB
 #define IQO_MMAR_MINB 4
 #endif
-template <int VKS, int RS, int RD, int NX, int TZ>
+// pair words the 8 pixels of a group span (even count: 8-byte loads), ODD: the first tap sits on an odd W element
+template <int RS, int RD, int NXE, int ODD>
+__host__ __device__ constexpr int mmaRatioWords()
+{
+    int m = 0;
+    for (int p = 0; p < 8; ++p) {
+        const int off = (p * RS) / RD + ODD;
+        const int e = (off >> 1) + (NXE + (off & 1) + 1) / 2;
+        m = e > m ? e : m;
+    }
+    return (m + 1) & ~1;
+}
+
+template <int VKS, int RS, int RD, int NX, int TZ, int ODD>
 __global__ void __launch_bounds__(128, IQO_MMAR_MINB) resizeLanczosMmaRatioKernel(const __grid_constant__ MmaRatioKernelArgs prm)
 {
     extern __shared__ __align__(128) uint8_t mmaSmem[];
@@ -2836,7 +2850,7 @@ __global__ void __launch_bounds__(128, IQO_MMAR_MINB) resizeLanczosMmaRatioKerne
     const uint32_t mbarBase = wBase + 16 * wStride;
     uint8_t *__restrict__ dst = a.dst + (long long)blockIdx.z * a.dstFrameStride;
     const int nseg = a.wcols >> 4;
-    const int i0 = GS * T0 + prm.c0 - xs;                       // W element of the first tap of pixel tx0 (even)
+    const int i0 = GS * T0 + prm.c0 - xs - ODD;                 // W element the pair words of pixel tx0 start at (even; ODD: one before its first tap)
 
     const int blkFirst = (a.dstRow0 >> 4) + blockIdx.y * a.bandBlocks;
     const int blkEnd = min(blkFirst + a.bandBlocks, (a.dstRow0 + a.dstRows + 15) >> 4);
@@ -2984,7 +2998,7 @@ __global__ void __launch_bounds__(128, IQO_MMAR_MINB) resizeLanczosMmaRatioKerne
             if (r < rLo || r >= rHi) continue;
             const uint32_t wl = wBase + r * wStride + 2 * (i0 + GS * q);
             constexpr int NXE = NX - TZ;  // taps left after the zero taps that end every phase
-            constexpr int kWords = (((7 * RS / RD) >> 1) + (NXE + 2) / 2 + 1) & ~1;  // pair words the 8 pixels span (even count)
+            constexpr int kWords = mmaRatioWords<RS, RD, NXE, ODD>();
             uint32_t n[kWords];
             if ((wl & 7) == 0) {
 #pragma unroll
@@ -2997,7 +3011,7 @@ __global__ void __launch_bounds__(128, IQO_MMAR_MINB) resizeLanczosMmaRatioKerne
             int px[8];
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
-                const int off = (p * RS) / RD;
+                const int off = (p * RS) / RD + ODD;
                 const int wp = off >> 1, par = off & 1, ph = p % RD;
                 const int nwd = (NXE + par + 1) / 2;
                 int acc = prm.accInit;
@@ -3104,20 +3118,22 @@ size_t mmaRatioSmemBytes(int wcols, int nChunks)
 
 bool mmaRatioHasKernel(int RS, int RD, int NX, int odd)
 {
+    // measured in one run (512 frames 1080p): Lanczos3 at 3:2 0.557 ms here, 0.61 on the all-mma kernel, 0.67 on the 3:2
+    // kernel; the 12-tap patterns (Lanczos4 at 3:2: 0.72 vs 0.69, 2:1 on X only: 0.66 vs 0.56) are faster all-mma
     return odd == 0 && RS == 3 && RD == 2 && NX == 10;
 }
 
-template <int VKS, int RS, int RD, int NX, int TZ>
+template <int VKS, int RS, int RD, int NX, int TZ, int ODD>
 cudaError_t launchMmaRatioT(const MmaRatioKernelArgs &p, dim3 grid, size_t smem, cudaStream_t stream)
 {
     static PerDeviceOnce attrSet;
     const int dev = currentDevice();
     if (!attrSet.done(dev)) {
-        cudaError_t e = cudaFuncSetAttribute(resizeLanczosMmaRatioKernel<VKS, RS, RD, NX, TZ>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(resizeLanczosMmaRatioKernel<VKS, RS, RD, NX, TZ, ODD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attrSet.set(dev);
     }
-    resizeLanczosMmaRatioKernel<VKS, RS, RD, NX, TZ><<<grid, 32 * p.a.warps, smem, stream>>>(p);
+    resizeLanczosMmaRatioKernel<VKS, RS, RD, NX, TZ, ODD><<<grid, 32 * p.a.warps, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
@@ -3142,9 +3158,10 @@ cudaError_t launchMmaRatio(const MmaArgs &a, const CUtensorMap &tmap, const Rati
     p.gx = ra.gx;
     dim3 grid(strips, bands, a.nFrames);
     g_launches.fetch_add(1);
-    if (a.vKMax == 1) return ra.tailZeros ? launchMmaRatioT<1, 3, 2, 10, 1>(p, grid, smem, stream) : launchMmaRatioT<1, 3, 2, 10, 0>(p, grid, smem, stream);
-    if (a.vKMax == 2) return ra.tailZeros ? launchMmaRatioT<2, 3, 2, 10, 1>(p, grid, smem, stream) : launchMmaRatioT<2, 3, 2, 10, 0>(p, grid, smem, stream);
-    if (a.vKMax == 3) return ra.tailZeros ? launchMmaRatioT<3, 3, 2, 10, 1>(p, grid, smem, stream) : launchMmaRatioT<3, 3, 2, 10, 0>(p, grid, smem, stream);
+#define IQO_MMAR_CASE(V) \
+    if (a.vKMax == V) return ra.tailZeros ? launchMmaRatioT<V, 3, 2, 10, 1, 0>(p, grid, smem, stream) : launchMmaRatioT<V, 3, 2, 10, 0, 0>(p, grid, smem, stream);
+    IQO_MMAR_CASE(1) IQO_MMAR_CASE(2) IQO_MMAR_CASE(3)
+#undef IQO_MMAR_CASE
     return cudaErrorInvalidValue;
 }
 

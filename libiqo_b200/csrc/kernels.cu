@@ -1565,9 +1565,12 @@ __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constan
                 A[4 * w + 4] = aw[w] >> 24, Bv[4 * w + 4] = bw[w] >> 24;
             }
             A[NC - 1] = ap & 0xffu, Bv[NC - 1] = bp & 0xffu;
-            // columns -1 and S are the replicated edge columns (beyond 3x more than the first / last pixel read them)
-            if (j == 0) A[0] = A[1], Bv[0] = Bv[1];
-            if (j == a.itemsPerRow - 1) A[NC - 1] = A[NC - 2], Bv[NC - 1] = Bv[NC - 2];
+            // columns -1 and S are the replicated edge columns: beyond 3x more than the first / last pixel (which are
+            // patched below) read them
+            if (RD > 3 * RS) {
+                if (j == 0) A[0] = A[1], Bv[0] = Bv[1];
+                if (j == a.itemsPerRow - 1) A[NC - 1] = A[NC - 2], Bv[NC - 1] = Bv[NC - 2];
+            }
         }
         // vertical blend per column (<= 255 * 256), then per pixel, with the two horizontal weights of a phase
         // summing to 32768:   2 * (lo * q0 + hi * q1 + 2^22) == (lo << 16) + 2^23 + (hi - lo) * 2 q1

@@ -449,6 +449,9 @@ void buildHalfPlan(const Plan &p, HalfPlan &h)
             if (den < 0) { h.why = "negative border denominator"; return; }
             lo = lo * 64 / den - 1;
             hi = hi * 64 / den + 1;
+            // the reference casts the rescaled border row to int16 (resizeYborder): content that would wrap it lies outside
+            // the biased 16-bit window of the fast kernels, so such tables go to the generic kernel, which wraps like the reference
+            if (lo < -32768 || hi > 32767) { h.why = "border row may wrap int16 after its division"; return; }
         }
         wmin = std::min(wmin, lo);
         wmax = std::max(wmax, hi);
@@ -627,6 +630,9 @@ void buildPackedPlan(const Plan &p, PackedPlan &q, int padNP)
             if (den < 0 || den > 255) { q.why = "border denominator out of range"; return; }
             lo = lo * 64 / den - 1;
             hi = hi * 64 / den + 1;
+            // the reference casts the rescaled border row to int16 (resizeYborder): content that would wrap it lies outside
+            // the biased 16-bit window of the fast kernels, so such tables go to the generic kernel, which wraps like the reference
+            if (lo < -32768 || hi > 32767) { q.why = "border row may wrap int16 after its division"; return; }
             if (den > 1) q.magicY[size_t(r)] = uint32_t((1ull << 32) / uint64_t(den) + 1);
         }
         wmin = std::min(wmin, lo);
@@ -750,6 +756,9 @@ void buildSmallPlan(const Plan &p, SmallPlan &s)
             if (den < 0 || den > 255) { s.why = "border denominator out of range"; return; }
             lo = lo * 64 / den - 1;
             hi = hi * 64 / den + 1;
+            // the reference casts the rescaled border row to int16 (resizeYborder): content that would wrap it lies outside
+            // the biased 16-bit window of the fast kernels, so such tables go to the generic kernel, which wraps like the reference
+            if (lo < -32768 || hi > 32767) { s.why = "border row may wrap int16 after its division"; return; }
             if (den > 1) s.magicY[size_t(r)] = uint32_t((1ull << 32) / uint64_t(den) + 1);
         }
         wmin = std::min(wmin, lo);
@@ -831,6 +840,9 @@ void buildRatioPlan(const Plan &p, RatioPlan &r)
             if (den < 0 || den > 255) { r.why = "border denominator out of range"; return; }
             lo = lo * 64 / den - 1;
             hi = hi * 64 / den + 1;
+            // the reference casts the rescaled border row to int16 (resizeYborder): content that would wrap it lies outside
+            // the biased 16-bit window of the fast kernels, so such tables go to the generic kernel, which wraps like the reference
+            if (lo < -32768 || hi > 32767) { r.why = "border row may wrap int16 after its division"; return; }
         }
         wmin = std::min(wmin, lo);
         wmax = std::max(wmax, hi);
@@ -1030,6 +1042,9 @@ void buildMmaPlan(const Plan &p, MmaPlan &m, int wcols)
             if (den < 0 || den > 255) { m.why = "border denominator out of range"; return; }
             lo = lo * 64 / den - 1;
             hi = hi * 64 / den + 1;
+            // the reference casts the rescaled border row to int16 (resizeYborder): content that would wrap it lies outside
+            // the biased 16-bit window of the fast kernels, so such tables go to the generic kernel, which wraps like the reference
+            if (lo < -32768 || hi > 32767) { m.why = "border row may wrap int16 after its division"; return; }
         }
         wmin = std::min(wmin, lo);
         wmax = std::max(wmax, hi);

@@ -14,7 +14,24 @@ def _pad(rng):
 
 def single_case(rng):
     """(kind, degree, pxScale, sw, sh, dw, dh, srcPad, dstPad) drawn from the kernel families."""
-    fam = rng.randint(0, 7)
+    fam = rng.randint(0, 10)
+    if fam == 7:      # Area reductions with their own streaming kernel (items of 4 RS source columns), any Y ratio
+        rs, rd = [(3, 2), (4, 3), (2, 1), (5, 2), (3, 1), (4, 1)][rng.randint(0, 6)]
+        m = int(rng.randint(1, 60))
+        sh = int(rng.randint(4, 400))
+        dh = int(rng.randint(max(2, sh // 5), sh + 1)) if rng.rand() < 0.8 else int(rng.randint(sh, 2 * sh))
+        return (AREA, 0, 1, 4 * rs * m, sh, 4 * rd * m, dh, _pad(rng), int(rng.choice([0, 0, 4, 8])))
+    if fam == 8:      # Linear at the rational ratios of the streaming Linear kernel, any Y ratio
+        rs, rd = [(1, 2), (1, 3), (1, 4), (2, 3), (2, 5), (3, 4), (4, 5), (3, 2), (4, 3)][rng.randint(0, 9)]
+        m = int(rng.randint(1, 50))
+        sh = int(rng.randint(4, 300))
+        dh = int(rng.randint(max(2, sh // 2), 3 * sh + 1))
+        return (LINEAR, 0, 1, 4 * rs * m, sh, 4 * rd * m, dh, int(rng.choice([0, 0, 4, 8])), int(rng.choice([0, 0, 4, 8])))
+    if fam == 9:      # Lanczos3 at 3:2 on X (tensor-path vertical + dp2a horizontal when the tensor path is forced)
+        k = int(rng.randint(1, 80)) * 8
+        sh = int(rng.randint(16, 500))
+        dh = int(rng.randint(max(8, sh // 3), 2 * sh))
+        return (LANCZOS, 3, 1, 3 * k, sh, 2 * k, dh, int(rng.choice([0, 0, 16, 32])), _pad(rng))
     if fam == 0:      # 2:1 Lanczos
         dw, dh = int(rng.randint(2, 400)) * 2, int(rng.randint(8, 300))
         return (LANCZOS, int(rng.choice([1, 2, 3, 4])), int(rng.choice([1, 1, 2, 3])), 2 * dw, 2 * dh, dw, dh, _pad(rng), _pad(rng))

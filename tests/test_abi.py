@@ -135,6 +135,7 @@ def test_kernel_family_of_the_baseline_configs():
         ((Li, 0, 1920, 1080, 1440, 810, 1), "linear_4_3"),
         ((Li, 0, 1920, 1080, 960, 540, 1), "packed"),            # from 2:1 on the reference's iterator starts elsewhere
         ((Li, 0, 1284, 720, 1926, 1080, 1), "packed"),           # 2:3, width not a multiple of 8
+        ((L, 5, 614, 411, 401, 342, 1), "generic"),              # a border row may wrap int16 after its division
     ]
     for args, name in expect:
         assert iqo.plan_kernel(*args)[0] == name, args

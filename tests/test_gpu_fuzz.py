@@ -9,11 +9,11 @@ import libiqo_b200 as iqo
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("path,seed", [(iqo.PATH_AUTO, 101), (iqo.PATH_STREAM, 102), (iqo.PATH_NO_STREAM, 103)])
+@pytest.mark.parametrize("path,seed", [(iqo.PATH_AUTO, 101), (iqo.PATH_STREAM, 102), (iqo.PATH_NO_STREAM, 103), (iqo.PATH_MMA, 104)])
 def test_fuzz_single_images(path, seed):
     rng = np.random.RandomState(seed)
     stats, bad, done = {}, [], 0
-    for _ in range(150):
+    for _ in range(200):
         case = fuzz_lib.single_case(rng)
         res = fuzz_lib.run_single(rng, case, path)
         if res is None:
@@ -28,6 +28,10 @@ def test_fuzz_single_images(path, seed):
         for k in ("lanczos_stream", "ratio_stream"):
             assert stats.get(k, 0) > 0, stats
         assert any(k.endswith("_stream") and k.startswith("half") for k in stats), stats
+    if path == iqo.PATH_AUTO:     # the Area / Linear streaming kernels take single images too
+        assert stats.get("area_down", 0) > 0 and any(k.startswith("linear_") and k != "linear_mma" for k in stats), stats
+    if path == iqo.PATH_MMA:      # both tensor-path variants
+        assert stats.get("lanczos_mma", 0) > 0 and stats.get("lanczos_mma_dp2a", 0) > 0, stats
 
 
 @pytest.mark.parametrize("path,seed", [(iqo.PATH_AUTO, 201), (iqo.PATH_STREAM, 202)])

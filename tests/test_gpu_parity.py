@@ -596,6 +596,23 @@ def test_area_reduction_kernel(case):
     assert np.array_equal(got, want)
 
 
+@pytest.mark.parametrize("case", [(5, 614, 411, 401, 342, 7), (5, 332, 289, 636, 285, 1)])
+def test_border_row_that_wraps_int16_after_its_division(case):
+    """Lanczos5 tables whose first / last rows keep few taps: `int16(int16(nume) * 64 / deno)` (resizeYborder) can exceed
+    int16 for some content and wraps in the reference.  Found by the long fuzz runs (tools/dev/fuzz_paths.sh): the
+    biased 16-bit window of the fast kernels cannot hold the wrapped value, so the planner hands such tables to the
+    generic kernel whatever path is asked for."""
+    deg, sw, sh, dw, dh, seed = case
+    src = lcg_image(sh, sw, seed=seed)
+    rc, want = oracle_resize(LANCZOS, src, dw, dh, deg)
+    assert rc == 0
+    assert iqo.plan_kernel(LANCZOS, deg, sw, sh, dw, dh, 1)[0] == "generic"
+    for path in (iqo.PATH_AUTO, iqo.PATH_STREAM, iqo.PATH_MMA, iqo.PATH_NO_STREAM, iqo.PATH_GENERIC):
+        got, kernel = gpu_resize(LANCZOS, src, dw, dh, deg, path=path)
+        assert kernel == "generic", (path, kernel)
+        assert np.array_equal(got, want), path
+
+
 def test_resize_is_ordered_after_the_producer_of_a_device_source():
     """iqo_cuda_resize with device pointers runs on the legacy default stream: a source that torch is still
     producing on its (default) current stream must be complete before the kernel reads it (the call

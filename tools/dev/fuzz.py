@@ -1,6 +1,6 @@
 """Open-ended randomized parity fuzz of single images against the oracle (time budget; the bounded, seeded
 form of the same cases runs in tests/test_gpu_fuzz.py).  usage: fuzz.py [seed] [seconds]; FUZZ_STREAM=1 forces
-the streaming kernels on small launches too."""
+the streaming kernels on small launches too, FUZZ_MMA=1 the tensor-path kernels."""
 import os, sys, time
 sys.path.insert(0, "."); sys.path.insert(0, "tests")
 import numpy as np
@@ -9,7 +9,7 @@ import fuzz_lib
 
 rng = np.random.RandomState(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 120.0
-PATH = iqo.PATH_STREAM if os.environ.get("FUZZ_STREAM") else iqo.PATH_AUTO
+PATH = iqo.PATH_STREAM if os.environ.get("FUZZ_STREAM") else iqo.PATH_MMA if os.environ.get("FUZZ_MMA") else iqo.PATH_AUTO
 t0, stats, bad = time.time(), {}, 0
 while time.time() - t0 < budget:
     case = fuzz_lib.single_case(rng)

@@ -77,8 +77,22 @@ def run_single(rng, case, path):
 
 
 def batch_case(rng):
-    fam = rng.randint(0, 5)
-    if fam == 0:
+    fam = rng.randint(0, 8)
+    if fam == 5:      # Area reductions with their own streaming kernel
+        rs, rd = [(3, 2), (4, 3), (2, 1), (5, 2), (3, 1), (4, 1)][rng.randint(0, 6)]
+        m = int(rng.randint(1, 30))
+        kind, deg, px, sw, sh, dw = AREA, 0, 1, 4 * rs * m, int(rng.randint(4, 150)), 4 * rd * m
+        dh = int(rng.randint(max(2, sh // 4), sh + 1))
+    elif fam == 6:    # Linear at the rational ratios of the streaming Linear kernel
+        rs, rd = [(1, 2), (1, 4), (2, 3), (2, 5), (3, 4), (4, 5), (3, 2), (4, 3)][rng.randint(0, 8)]
+        m = int(rng.randint(1, 30))
+        kind, deg, px, sw, sh, dw = LINEAR, 0, 1, 4 * rs * m, int(rng.randint(4, 120)), 4 * rd * m
+        dh = int(rng.randint(max(2, sh // 2), 3 * sh + 1))
+    elif fam == 7:    # Lanczos3 / 4 at 3:2 and 2:1-on-X (tensor-path variants when that path is forced)
+        k = int(rng.randint(1, 40)) * 8
+        rs, rd = [(3, 2), (3, 2), (2, 1)][rng.randint(0, 3)]
+        kind, deg, px, sw, sh, dw, dh = LANCZOS, int(rng.choice([3, 3, 4])), 1, rs * k, int(rng.randint(16, 200)), rd * k, int(rng.randint(16, 200))
+    elif fam == 0:
         dw, dh = int(rng.randint(4, 200)) * 2, int(rng.randint(8, 120))
         kind, deg, px, sw, sh = LANCZOS, int(rng.choice([2, 3])), 1, 2 * dw, 2 * dh
     elif fam == 1:

@@ -34,7 +34,7 @@ def test_fuzz_single_images(path, seed):
         assert stats.get("lanczos_mma", 0) > 0 and stats.get("lanczos_mma_dp2a", 0) > 0, stats
 
 
-@pytest.mark.parametrize("path,seed", [(iqo.PATH_AUTO, 201), (iqo.PATH_STREAM, 202)])
+@pytest.mark.parametrize("path,seed", [(iqo.PATH_AUTO, 201), (iqo.PATH_STREAM, 202), (iqo.PATH_MMA, 203)])
 def test_fuzz_device_batches(path, seed):
     pytest.importorskip("torch")
     rng = np.random.RandomState(seed)

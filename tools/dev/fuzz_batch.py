@@ -8,7 +8,7 @@ import fuzz_lib
 
 rng = np.random.RandomState(int(sys.argv[1]) if len(sys.argv) > 1 else 1)
 budget = float(sys.argv[2]) if len(sys.argv) > 2 else 60.0
-PATH = iqo.PATH_STREAM if os.environ.get("FUZZ_STREAM") else iqo.PATH_AUTO
+PATH = iqo.PATH_STREAM if os.environ.get("FUZZ_STREAM") else iqo.PATH_MMA if os.environ.get("FUZZ_MMA") else iqo.PATH_AUTO
 t0, stats, bad = time.time(), {}, 0
 while time.time() - t0 < budget:
     case = fuzz_lib.batch_case(rng)

@@ -145,6 +145,39 @@ def run_batch(rng, case, path):
     return k, ok
 
 
+def run_band_case(rng, path):
+    """A random shape of any kind in a random ragged partition of destination row bands, each band resized with
+    iqo_cuda_resize_band from a device buffer that holds only the band + halo rows (srcRow0 != 0); the assembled image
+    must equal the oracle's whole-image result.  Returns (kernel of the last band, ok) or None."""
+    import torch
+    kind, deg, px, sw, sh, dw, dh, _, _ = single_case(rng)
+    spad = int(rng.choice([0, 0, 16, 32]))
+    src = lcg_image(sh, sw, seed=int(rng.randint(1, 1 << 20)))
+    rc, want = oracle_resize(kind, src, dw, dh, deg, px)
+    if rc != 0:
+        return None
+    cuts = sorted(set([0, dh] + [int(v) for v in rng.randint(1, max(2, dh), size=int(rng.randint(0, 4)))]))
+    out = np.full((dh, dw), 0xEE, dtype=np.uint8)
+    k = "none"
+    with iqo.make_resizer(kind, deg, sw, sh, dw, dh, px) as r:
+        r.set_path(path)
+        for y0, y1 in zip(cuts[:-1], cuts[1:]):
+            n = y1 - y0
+            s0, sn = r.band_src_rows(y0, n)
+            host = np.zeros((sn, sw + spad), dtype=np.uint8)
+            host[:, :sw] = src[s0:s0 + sn]
+            dsrc = torch.from_numpy(host).cuda()
+            ddst = torch.full((n, dw + 8), 0xA5, dtype=torch.uint8, device="cuda")
+            r.resize_band(y0, n, s0, sn, sw + spad, dsrc, dw + 8, ddst, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            got = ddst.cpu().numpy()
+            if not (got[:, dw:] == 0xA5).all():
+                return r.last_kernel(), False
+            out[y0:y1] = got[:, :dw]
+            k = r.last_kernel()
+    return k, bool(np.array_equal(out, want)), (kind, deg, px, sw, sh, dw, dh, spad, cuts)
+
+
 def yuv_layout(w, h):
     sx, sy = w + w % 2, h + h % 2
     return sx, sy, sx * sy, sx * sy // 4

@@ -51,6 +51,22 @@ def test_fuzz_device_batches(path, seed):
     assert done >= 60
 
 
+@pytest.mark.parametrize("path,seed", [(iqo.PATH_AUTO, 301), (iqo.PATH_STREAM, 302), (iqo.PATH_MMA, 303)])
+def test_fuzz_row_bands(path, seed):
+    pytest.importorskip("torch")
+    rng = np.random.RandomState(seed)
+    bad, done = [], 0
+    for _ in range(120):
+        res = fuzz_lib.run_band_case(rng, path)
+        if res is None:
+            continue
+        done += 1
+        if not res[1]:
+            bad.append(res)
+    assert not bad, bad[:5]
+    assert done >= 90
+
+
 def test_fuzz_yuv420_frames():
     pytest.importorskip("torch")
     rng = np.random.RandomState(301)

@@ -1625,7 +1625,10 @@ __global__ void __launch_bounds__(256) resizeLinearUpKernel(const __grid_constan
 // saturation).  No shared memory.  Area has no border rows or columns; the one column beyond an item that its last
 // pixel's zero-weight tap names is read clamped.
 // ---------------------------------------------------------------------------------------
-constexpr int kAreaDownRows = 8;
+#ifndef IQO_AREA_DOWN_ROWS
+#define IQO_AREA_DOWN_ROWS 8
+#endif
+constexpr int kAreaDownRows = IQO_AREA_DOWN_ROWS;   // destination rows per item
 constexpr int kAreaDownMaxNX = 4, kAreaDownMaxRD = 3;
 
 struct AreaDownArgs {

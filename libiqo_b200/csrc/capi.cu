@@ -702,11 +702,15 @@ int launch(iqo_cuda_resizer *r, size_t nFrames, size_t dstRow0, size_t dstRows, 
             Y.D <= 65535 * 8 && ((uintptr_t)src % 4) == 0 && srcSt % 4 == 0 && srcFrameStride % 4 == 0 &&
             ((uintptr_t)dst % 4) == 0 && dstSt % 4 == 0 && dstFrameStride % 4 == 0) {
             r->lastKernel = "area_down";
+            int nyEff = 1;   // vertical taps up to the last one that is non-zero in some row (3:2: the third tap is zero in both phases)
+            for (int row = 0; row < Y.numRows; ++row)
+                for (int k = 0; k < Y.N; ++k)
+                    if (Y.coef[size_t(row) * Y.N + k] != 0) nyEff = std::max(nyEff, k + 1);
             for (size_t f0 = 0; f0 < nFrames; f0 += 65535) {
                 const int nf = int(std::min<size_t>(65535, nFrames - f0));
                 CUDA_TRY(launchAreaDown(int(X.rS), int(X.rD), X.N, nxEff, src + f0 * srcFrameStride, dst + f0 * dstFrameStride,
                                         (long long)srcSt, (long long)dstSt, (long long)srcFrameStride, (long long)dstFrameStride,
-                                        int(X.S), int(Y.S), int(X.D), int(Y.D), nf, Y.N, sp.ty.first, sp.ty.row, sp.ty.coef,
+                                        int(X.S), int(Y.S), int(X.D), int(Y.D), nf, Y.N, nyEff, sp.ty.first, sp.ty.row, sp.ty.coef,
                                         &X.coef[0], stream));
             }
             return IQO_CUDA_OK;

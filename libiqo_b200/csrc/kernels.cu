@@ -1638,7 +1638,7 @@ struct AreaDownArgs {
     int SW, SH, DW, DH;
     int itemsPerRow;           // SW / PS
     uint32_t rcpItems;         // ceil(2^32 / itemsPerRow)
-    int NY;                    // vertical taps per row
+    int NY, NYstride;          // vertical taps per row up to the last one that is non-zero in some row; taps per table row
     const int32_t *firstY, *rowY, *coefY;   // generic vertical tables
     int cx2[kAreaDownMaxRD][kAreaDownMaxNX];  // per phase: twice the horizontal weights
 };
@@ -1662,7 +1662,7 @@ __global__ void __launch_bounds__(256) resizeAreaDownKernel(const __grid_constan
         const int y = y0 + r;
         if (y >= a.DH) break;
         const int fy = __ldg(a.firstY + y);
-        const int32_t *cy = a.coefY + __ldg(a.rowY + y) * a.NY;
+        const int32_t *cy = a.coefY + __ldg(a.rowY + y) * a.NYstride;
         uint32_t P[2 * WS], Px = 0u;   // lane pairs (column 4w + 2h, + 1) and the extra column
 #pragma unroll
         for (int i = 0; i < 2 * WS; ++i) P[i] = 0u;
@@ -3455,7 +3455,7 @@ int areaDownItemColumns(int RS, int RD)
 
 cudaError_t launchAreaDown(int RS, int RD, int NX, int NXeff, const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch,
                            long long srcFrameStride, long long dstFrameStride, int SW, int SH, int DW, int DH, int nFrames, int NY,
-                           const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const int32_t *cx /* [RD][NX] */,
+                           int NYeff, const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const int32_t *cx /* [RD][NX] */,
                            cudaStream_t stream)
 {
     if (!areaDownHasKernel(RS, RD, NXeff)) return cudaErrorInvalidValue;
@@ -3474,7 +3474,8 @@ cudaError_t launchAreaDown(int RS, int RD, int NX, int NXeff, const uint8_t *src
     if (SW % PS != 0) return cudaErrorInvalidValue;
     a.itemsPerRow = SW / PS;
     a.rcpItems = (uint32_t)((0x100000000ull + a.itemsPerRow - 1) / a.itemsPerRow);
-    a.NY = NY;
+    a.NY = NYeff;
+    a.NYstride = NY;
     a.firstY = firstY;
     a.rowY = rowY;
     a.coefY = coefY;

@@ -133,7 +133,7 @@ bool areaDownHasKernel(int RS, int RD, int NX);
 int areaDownItemColumns(int RS, int RD);
 cudaError_t launchAreaDown(int RS, int RD, int NX, int NXeff, const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch,
                            long long srcFrameStride, long long dstFrameStride, int SW, int SH, int DW, int DH, int nFrames, int NY,
-                           const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const int32_t *cx,
+                           int NYeff, const int32_t *firstY, const int32_t *rowY, const int32_t *coefY, const int32_t *cx,
                            cudaStream_t stream);
 cudaError_t launchLinearUp(int RS, int RD, const uint8_t *src, uint8_t *dst, long long srcPitch, long long dstPitch,
                            long long srcFrameStride, long long dstFrameStride, int SW, int SH, int DW, int DH, int nFrames,
